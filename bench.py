@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the sapr assignment2 HMM hot path on B200.
+
+Workload (BASELINE.json configs[1]): batched Viterbi decoding, 100 000 synthetic utterances x 11 word
+models, T = 200 frames, N = 8 emitting states, D = 39 -- per GPU (weak scaling: every rank decodes its own
+100k-utterance shard, no data-path collective).  Metric: HMM frame*state updates per second =
+sum over (utterance, model) pairs of T_u * N / time.
+
+One "step" = one pass of the fused Viterbi path (sapr_viterbi through the C ABI) over the resident batch.
+  value   : features already resident in HBM (3.2 GB per GPU > 126 MB L2, so no L2 flush is needed)
+  e2e     : the same pass through the host-buffer entry point (sapr_viterbi_host): pinned host features ->
+            chunked H2D overlapped with decoding -> words/scores/paths back to host, all inside the timed region
+  roofline: the dominant kernel (k_viterbi_fused) timed with CUDA events on the launching stream inside the
+            timed region; algorithmic bytes = 31 412 B per utterance x utterances per launch
+  cpu_baseline: the CPU oracle port (oracle/sapr_oracle.c, OpenMP) on a bounded sample of the same tensors
+  estep   : secondary headline (configs[2] shape): Baum-Welch E-step + statistics (+ all-reduce + M-step)
+
+`--impl reference` times the reference's algorithm on the host cores instead (oracle port, all threads).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_WORDS, N_STATES, DIM, T_FRAMES = 11, 8, 39, 200
+ALG_BYTES_PER_UTT = 4 * T_FRAMES * DIM + T_FRAMES + 4 + 8          # 31 412 (cfg 2)
+ESTEP_BYTES_PER_UTT = 4 * T_FRAMES * DIM + 8                       # 31 208 (cfg 3)
+SEED = 20241118 + 2
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                smax = float(f[2])
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(f[1]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_sample(corpus_host, offs_host, labels_host, A, means, var, leg, target_s=12.0):
+    """Time the oracle port on a bounded sample of the bench tensors, all host threads."""
+    from oracle import oracle as orc
+    nthreads = orc.num_threads()
+    B = len(offs_host) - 1
+    probe = min(B, 64 * max(1, nthreads))
+
+    def run(nu):
+        X = corpus_host[:offs_host[nu], :DIM].astype(np.float64)
+        t = time.perf_counter()
+        if leg == "viterbi":
+            orc.viterbi_batch(X, offs_host[:nu + 1], A, means, var, nthreads=nthreads, want_scores=False)
+        else:
+            orc.estep_batch(X, offs_host[:nu + 1], labels_host[:nu], A, means, var, nthreads=nthreads)
+        return time.perf_counter() - t
+
+    dt = run(probe)
+    nu = int(min(B, max(probe, probe * target_s / max(dt, 1e-3))))
+    dt = run(nu)
+    per = T_FRAMES * N_STATES * (M_WORDS if leg == "viterbi" else 1)
+    return nu * per / dt, nu, nthreads, dt
+
+
+def reference_arm(args):
+    """--impl reference: the reference's algorithm on the host cores (oracle port; the Python reference does
+    not travel to the GPU box and runs ~1e4x slower)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    from sapr_b200 import synth
+    nthreads = orc.num_threads()
+    nu = 192 * max(1, nthreads)
+    feats, labels, mu, sd = synth.make_corpus(nu, M_WORDS, N_STATES, DIM, T_FRAMES, T_FRAMES, seed=SEED)
+    A, means, var = synth.truth_models(mu, sd, 0.9)
+    X, offs = orc.pack(feats)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        orc.viterbi_batch(X, offs, A, means, var, nthreads=nthreads, want_scores=False)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t)
+    ms = 1e3 * float(np.mean(times))
+    val = nu * T_FRAMES * N_STATES * M_WORDS / (ms / 1e3)
+    line = {"impl": "reference", "metric": "HMM frame*state updates/sec (Viterbi)", "value": val, "unit": "updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2 batched Viterbi: utterances x 11 word models, T=200, N=8, D=39 (synth-v1)",
+                       "utterances_per_step": nu, "topology": "sapr entry/exit", "emission": "diagonal Gaussian"},
+            "cpu_baseline": {"value": val, "unit": "updates/s", "cores": nthreads, "kind": "port",
+                             "sample": f"{nu} utterances x 11 models per step (oracle/sapr_oracle.c, OpenMP)"},
+            "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sapr_b200")
+    ap.add_argument("--utts", type=int, default=100_000, help="utterances per GPU")
+    ap.add_argument("--estep-utts", type=int, default=200_000, help="utterances per GPU for the E-step leg (0 = skip)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    from sapr_b200 import _lib, engine, synth
+    from sapr_b200.dist import Dist
+
+    dist = Dist()
+    rank, world = dist.rank, dist.world
+    torch.cuda.set_device(dist.local_rank)
+    dev = torch.device("cuda", dist.local_rank)
+    ctx = _lib.default_context()
+    prec = engine.FP64 if args.precision == "fp64" else engine.FP32
+    W = max(args.warmup, 3)
+    B = args.utts
+
+    # ---- synthetic corpus in HBM: every rank its own shard (content depends on seed + rank only) ----
+    X, offsets, labels, mu, sd = synth.device_corpus(B, M_WORDS, N_STATES, DIM, T_FRAMES, SEED + 7919 * rank, dev)
+    A, means, var = synth.truth_models(mu, sd, 0.9)
+    models = engine.WordModels(M_WORDS, N_STATES, DIM)
+    models.set(means, var, A)
+    offs_host = offsets.cpu().numpy()
+    batch = engine.PackedBatch(X, offsets, DIM, offs_host, labels)
+    updates_per_step = B * T_FRAMES * N_STATES * M_WORDS
+
+    def step():
+        return models.viterbi(batch, None, prec, 0, want_scores=False, want_path=True)
+
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dist.local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ctx.profile(True)
+    l0 = ctx.launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step()
+    ev1.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    dist.barrier()
+    launches = ctx.launches() - l0
+    k_ms, k_n = ctx.profile_read(0)
+    f_ms, f_n = ctx.profile_read(1)
+    ctx.profile(False)
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    dist.max_(ms)
+    ms_per_step = float(ms.item()) / args.steps
+    value = world * updates_per_step / (ms_per_step / 1e3)
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+
+    # ---- roofline of the dominant kernel (this rank) ----
+    peak, peak_src = peaks()
+    utt_per_launch = B * args.steps / max(k_n, 1)
+    k_avg_ms = k_ms / max(k_n, 1)
+    achieved = ALG_BYTES_PER_UTT * utt_per_launch / (k_avg_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_viterbi_fused<float,u16,8>", "achieved": achieved, "peak": peak,
+                "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback",
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "launches": k_n,
+                "avg_launch_ms": k_avg_ms, "alg_bytes_per_launch": ALG_BYTES_PER_UTT * utt_per_launch,
+                "kernel_share_of_step": k_ms / (ms_per_step * args.steps),
+                "finish_kernel_ms_per_step": f_ms / args.steps,
+                "note": "SIMT fp32 emission: FMA-issue bound (SURVEY 8d), not yet HBM bound"}
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host features) ----
+    e2e = None
+    if not args.no_e2e:
+        Xh = torch.empty(X.shape, dtype=torch.float32, pin_memory=True)
+        Xh.copy_(X)
+        res = dict(best_word=torch.empty(B, dtype=torch.int32, pin_memory=True).numpy(),
+                   best_score=torch.empty(B, dtype=torch.float64, pin_memory=True).numpy(),
+                   path=torch.empty(batch.total_frames, dtype=torch.uint8, pin_memory=True).numpy())
+        Xh_np = Xh.numpy()
+        e_steps = max(2, min(args.steps, 4))
+        models.viterbi_host(Xh_np, offs_host, prec, 0, 8192, True, res)      # warm-up (allocates staging)
+        dist.barrier()
+        torch.cuda.synchronize()
+        te = time.perf_counter()
+        for _ in range(e_steps):
+            models.viterbi_host(Xh_np, offs_host, prec, 0, 8192, True, res)   # returns after the D2H completed
+        torch.cuda.synchronize()
+        e_ms = torch.tensor([(time.perf_counter() - te) * 1e3 / e_steps], dtype=torch.float64, device=dev)
+        dist.max_(e_ms)
+        same = bool(np.array_equal(res["best_word"], out["best_word"].cpu().numpy()))
+        e2e = {"value": world * updates_per_step / (float(e_ms.item()) / 1e3), "unit": "updates/s",
+               "h2d_bytes_per_step": int(Xh_np.nbytes + offs_host.nbytes),
+               "d2h_bytes_per_step": int(res["best_word"].nbytes + res["best_score"].nbytes + res["path"].nbytes),
+               "ms_per_step": float(e_ms.item()), "steps": e_steps, "matches_device_path": same,
+               "call": "sapr_viterbi_host (chunked H2D on a copy stream overlapped with decoding)"}
+        del Xh
+
+    # ---- secondary leg: Baum-Welch E-step (+ all-reduce + M-step) ----
+    estep = None
+    if args.estep_utts > 0:
+        Be = args.estep_utts
+        if Be != B:
+            del X, batch
+            torch.cuda.empty_cache()
+            Xe, offe, labe, _, _ = synth.device_corpus(Be, M_WORDS, N_STATES, DIM, T_FRAMES, SEED + 31 + 7919 * rank, dev)
+            be = engine.PackedBatch(Xe, offe, DIM, offe.cpu().numpy(), labe)
+        else:
+            be, labe = batch, labels
+        order = engine.group_by_model(labe)
+        floor_v = 1e-3
+
+        def estep_iter():
+            stats, ll, _ = models.estep(be, labe, order, prec)
+            if world > 1:
+                dist.allreduce_(stats)
+            return stats, ll
+
+        for _ in range(2):
+            estep_iter()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ctx.profile(True)
+        n_it = 5
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(n_it):
+            stats, ll = estep_iter()
+        a1.record()
+        torch.cuda.synchronize()
+        fb_ms, fb_n = ctx.profile_read(2)
+        st_ms, st_n = ctx.profile_read(3)
+        ctx.profile(False)
+        em = torch.tensor([a0.elapsed_time(a1) / n_it], dtype=torch.float64, device=dev)
+        dist.max_(em)
+        e_val = world * Be * T_FRAMES * N_STATES / (float(em.item()) / 1e3)
+        e_gbs = ESTEP_BYTES_PER_UTT * Be / (float(em.item()) / 1e3) / 1e9
+        estep = {"metric": "Baum-Welch E-step frame*state updates/s (fwd-bwd + statistics + all-reduce)",
+                 "value": e_val, "unit": "updates/s", "ms_per_iteration": float(em.item()), "utterances_per_gpu": Be,
+                 "roofline": {"bound": "hbm", "achieved": e_gbs, "peak": peak, "unit": "GB/s", "frac": e_gbs / peak,
+                              "fwdbwd_kernel_ms": fb_ms / n_it, "stats_kernel_ms": st_ms / n_it,
+                              "alg_bytes_per_iteration": ESTEP_BYTES_PER_UTT * Be}}
+        models.mstep(stats, floor_v)
+        torch.cuda.synchronize()
+
+    # ---- CPU baseline (rank 0, N = 1 only): oracle port on a bounded sample of the same tensors ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        Xs, offs_s, labs_s, _, _ = synth.device_corpus(min(B, 16384), M_WORDS, N_STATES, DIM, T_FRAMES, SEED, dev)
+        v, nu, nt, dt = cpu_sample(Xs.cpu().numpy(), offs_s.cpu().numpy(), labs_s.cpu().numpy(), A, means, var, "viterbi")
+        cpu = {"value": v, "unit": "updates/s", "cores": nt, "kind": "port",
+               "sample": f"first {nu} utterances x 11 models of the same synth-v1 corpus, {dt:.1f} s "
+                         f"(oracle/sapr_oracle.c float64, OpenMP {nt} threads); the Python reference itself runs "
+                         f"~2.5e4 updates/s single-threaded (BASELINE.md)"}
+        if estep is not None:
+            v2, nu2, _, dt2 = cpu_sample(Xs.cpu().numpy(), offs_s.cpu().numpy(), labs_s.cpu().numpy(), A, means, var,
+                                         "estep", 6.0)
+            estep["cpu_baseline"] = {"value": v2, "unit": "updates/s", "cores": nt, "kind": "port",
+                                     "sample": f"{nu2} utterances, {dt2:.1f} s"}
+
+    if rank == 0:
+        line = {"metric": "HMM frame*state updates/sec (Viterbi)", "value": value, "unit": "updates/s", "n_gpus": world,
+                "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if prec == engine.FP32 else "f64",
+                "data": "synthetic",
+                "config": {"workload": "cfg2 batched Viterbi: 100k utterances x 11 word models, T=200, N=8, D=39 "
+                                       "(synth-v1), per GPU", "utterances_per_gpu": B, "models": M_WORDS, "T": T_FRAMES,
+                           "N": N_STATES, "D": DIM, "topology": "sapr entry/exit (custom_hmm.py)",
+                           "emission": "diagonal Gaussian", "sharding": f"utterances x{world}, no collective",
+                           "l2": "inputs (3.2 GB/GPU) larger than L2; no flush needed"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "estep": estep}
+        print(json.dumps(line), flush=True)
+    dist.shutdown()
+
+
+if __name__ == "__main__":
+    main()

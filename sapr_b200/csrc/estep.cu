@@ -1,0 +1,552 @@
+// estep.cu -- Baum-Welch E-step with fused diagonal-Gaussian emission, and the M-step.
+//
+// Replaces custom_hmm.py:417-439 (compute_emission_matrix, forward, backward, compute_gamma,
+// compute_xi and the accumulators of baum_welch) plus the sums update_B consumes (:372-386), for
+// every utterance against its own word model, and update_A / update_B (:351-400).
+//
+// k_estep_fused   one thread per utterance: log-space forward with a running max (alpha is kept
+//                 relative to a per-frame offset accumulated in float64, so fp32 never sees the
+//                 -1e4 magnitudes of a 200-frame likelihood), then the backward sweep producing
+//                 gamma_t(j) and xi_t(j,j) on the fly.  Only sum_t xi_t(j,j) and sum_t gamma_t(j)
+//                 are ever consumed (custom_hmm.py:359-361), so no S x S tensor exists.
+// k_stats_diag    sum gamma (x - c) and sum gamma (x - c)^2 per (model, state, dim), pivot c = the
+//                 model's current mean (every rank has it, so ONE all-reduce suffices); fp32 inside
+//                 one utterance, float64 across utterances, fixed-order reduction across CTAs.
+// k_stats_reduce  deterministic reduction of the per-tile partials into the packed stats block.
+// k_mstep_diag    A_ii = Xi/G, means, variances with the reference's floor.
+#include "common.cuh"
+
+template <typename R> struct alignas(16) Vec4e { R x, y, z, w; };
+
+template <typename R> __host__ __device__ inline size_t model_stride(size_t per_model) {
+    return per_model + 16 / sizeof(R);   // +16 B: models land in different banks when lanes differ
+}
+
+template <typename R, int NMAX>
+__device__ __forceinline__ void emit_diag_e(const float *__restrict__ xrow, int nchunk, int N,
+                                            const R *__restrict__ spk_model, const R *cst, R *e) {
+    R acc[NMAX];
+#pragma unroll
+    for (int j = 0; j < NMAX; j++) acc[j] = R(0);
+    const float4 *xr = reinterpret_cast<const float4 *>(xrow);
+    for (int c = 0; c < nchunk; c++) {
+        float4 xv = __ldg(xr + c);
+        const R *p = spk_model + (size_t)c * N * 8;
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) {
+            if (j < N) {
+                Vec4e<R> mu = *reinterpret_cast<const Vec4e<R> *>(p + j * 8);
+                Vec4e<R> h = *reinterpret_cast<const Vec4e<R> *>(p + j * 8 + 4);
+                R d0 = R(xv.x) - mu.x, d1 = R(xv.y) - mu.y, d2 = R(xv.z) - mu.z, d3 = R(xv.w) - mu.w;
+                R a = acc[j];
+                a = fma(d0 * d0, h.x, a);
+                a = fma(d1 * d1, h.y, a);
+                a = fma(d2 * d2, h.z, a);
+                a = fma(d3 * d3, h.w, a);
+                acc[j] = a;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NMAX; j++) e[j] = (j < N) ? cst[j] - acc[j] : R(0);
+}
+
+// scratch layout per block of 32 pairs: [t][j][lane] (coalesced), two planes: alpha-hat and e.
+template <typename R, int NMAX, bool RENORM>
+__global__ void __launch_bounds__(128)
+k_estep_fused(const float *__restrict__ X, int ldx, const int64_t *__restrict__ offsets, int p0, int np, int M, int N,
+              int nchunk, const R *__restrict__ pk, const R *__restrict__ cst_g, const R *__restrict__ la_g,
+              const R *__restrict__ lb_g, const int32_t *__restrict__ model_of_utt, const int32_t *__restrict__ order,
+              R *__restrict__ scr_alpha, R *__restrict__ scr_e, int maxT, R *__restrict__ gamma_out,
+              R *__restrict__ ustats, double *__restrict__ loglik) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *spk = reinterpret_cast<R *>(smem_raw);
+    const int S = N + 2;
+    const size_t per_model = (size_t)nchunk * N * 8;
+    const size_t mstride = model_stride<R>(per_model);
+    for (int mm = 0; mm < M; mm++)
+        for (size_t i = threadIdx.x; i < per_model; i += blockDim.x) spk[mm * mstride + i] = pk[mm * per_model + i];
+    __syncthreads();
+    const int pl = blockIdx.x * blockDim.x + threadIdx.x;   // pair index within the chunk
+    if (pl >= np) return;
+    const int p = p0 + pl;
+    const int u = order ? order[p] : p;
+    const int m = model_of_utt[u];
+    const R *spk_model = spk + (size_t)m * mstride;
+    R cst[NMAX], la[NMAX + 2], lb[NMAX + 2];
+#pragma unroll
+    for (int j = 0; j < NMAX; j++) cst[j] = (j < N) ? cst_g[(size_t)m * N + j] : R(0);
+#pragma unroll
+    for (int j = 0; j < NMAX + 2; j++) {
+        la[j] = (j < S) ? la_g[(size_t)m * S + j] : R(0);
+        lb[j] = (j < S) ? lb_g[(size_t)m * S + j] : R(0);
+    }
+    const R lbN = lb_g[(size_t)m * S + N];   // ln A[N, exit]
+    const int64_t off = offsets[u];
+    const int T = (int)(offsets[u + 1] - off);
+    const R NINF = Num<R>::ninf();
+    const int lane = pl & 31;
+    const size_t blk = (size_t)(pl >> 5) * maxT * N * 32;
+    R *sa = scr_alpha + blk + lane;
+    R *se = scr_e + blk + lane;
+
+    // ---------------- forward (custom_hmm.py:176-211) ----------------
+    R a[NMAX], e[NMAX];
+    R ax = NINF;          // alpha[t, exit]
+    double base = 0.0;    // alpha[t, j] = a[j] + base
+    double amax = 0.0;    // running max of alpha over all cells; alpha[0,0] = 0 (:184)
+    bool anan = false;
+    if (T > 0) {
+        emit_diag_e<R, NMAX>(X + (size_t)off * ldx, nchunk, N, spk_model, cst, e);
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) a[j] = NINF;
+        a[0] = lb[0] + e[0];
+        if (a[0] != a[0]) anan = true; else amax = fmax(amax, (double)a[0]);
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) if (j < N) { sa[(size_t)j * 32] = a[j]; se[(size_t)j * 32] = e[j]; }
+    }
+    for (int t = 1; t < T; t++) {
+        emit_diag_e<R, NMAX>(X + (size_t)(off + t) * ldx, nchunk, N, spk_model, cst, e);
+        R aN = NINF;                                   // alpha[t-1, N] without dynamic register indexing
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) if (j == N - 1) aN = a[j];
+        R nx = aN + lbN;                               // alpha[t, exit] = alpha[t-1, N] + ln A[N, exit]
+#pragma unroll
+        for (int j = NMAX - 1; j >= 1; j--)
+            if (j < N) a[j] = lae(a[j - 1] + lb[j], a[j] + la[j + 1]) + e[j];
+        {
+            R ent = (t == 1) ? (R)(R(0) - (R)base) + lb[0] : NINF;   // alpha[t-1, 0] is 0 at t == 1 only
+            a[0] = lae(ent, a[0] + la[1]) + e[0];
+        }
+        ax = nx;
+        R mx = ax;
+        bool nn = (ax != ax);
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) if (j < N) { mx = fmax(mx, a[j]); nn = nn || (a[j] != a[j]); }
+        if (nn) anan = true;
+        if (mx > NINF) amax = fmax(amax, (double)mx + base);
+        if (RENORM && mx > NINF && mx < R(INFINITY)) {
+#pragma unroll
+            for (int j = 0; j < NMAX; j++) if (j < N) a[j] -= mx;
+            ax -= mx;
+            base += (double)mx;
+        }
+        const size_t row = (size_t)t * N * 32;
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) if (j < N) { sa[row + (size_t)j * 32] = a[j]; se[row + (size_t)j * 32] = e[j]; }
+    }
+    // reported log-likelihood: logaddexp.reduce(alpha[T-1, :]) - max(alpha)
+    if (T > 0) {
+        R r = (T == 1) ? R(0) : NINF;                  // alpha[T-1, entry]
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) if (j < N) r = lae(r, a[j]);
+        r = lae(r, ax);
+        double scale = anan ? (double)NAN : amax;
+        loglik[u] = ((double)r + base) - scale;
+    }
+
+    // ---------------- backward + gamma + xi (custom_hmm.py:213-322) ----------------
+    R gG[NMAX], gO[NMAX], gX[NMAX];
+#pragma unroll
+    for (int j = 0; j < NMAX; j++) { gG[j] = R(0); gO[j] = R(0); gX[j] = R(0); }
+    R b[NMAX];           // beta-hat[t+1, j]
+#pragma unroll
+    for (int j = 0; j < NMAX; j++) b[j] = NINF;
+    R bx = R(0);         // beta[T-1, exit] = 0
+    // t = T-1: gamma row is one-hot on the exit state (emitting gammas are exactly 0) unless alpha[T-1, exit]
+    // is -inf, in which case the reference produces NaN for the whole row (:252-255).
+    if (T > 0) {
+        // T == 1 or alpha[T-1, exit] == -inf: every cell of the row is -inf -> NaN row
+        const R g_last = (T > 1 && ax > NINF) ? R(0) : R(NAN);
+        R *go = gamma_out ? gamma_out + (size_t)(off + T - 1) * N : nullptr;
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) if (j < N) { if (go) go[j] = g_last; gO[j] += g_last; }
+    }
+    for (int t = T - 2; t >= 0; t--) {
+        const size_t rown = (size_t)(t + 1) * N * 32, row = (size_t)t * N * 32;
+        R w[NMAX + 1], at[NMAX];
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) {
+            if (j < N) { w[j] = se[rown + (size_t)j * 32] + b[j]; at[j] = sa[row + (size_t)j * 32]; }
+            else { w[j] = NINF; at[j] = NINF; }
+        }
+        w[NMAX] = NINF;
+        // beta[t, i] (:219-242); self[i] = ln A_ii + e_{t+1}(i) + beta_{t+1}(i)
+        R self[NMAX], nb[NMAX];
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) {
+            if (j < N) {
+                self[j] = la[j + 1] + w[j];
+                R adv = (j < N - 1) ? lb[j + 1] + w[j + 1] : lbN + bx;
+                nb[j] = lae(self[j], adv);
+            } else { self[j] = NINF; nb[j] = NINF; }
+        }
+        R b0 = lb[0] + w[0];                          // beta[t, entry]
+        // normaliser: logaddexp over all states of alpha+beta; entry contributes at t == 0 only,
+        // exit never for t < T-1 (beta[t, exit] = -inf)
+        R lg[NMAX];
+        R nrm = (t == 0) ? (R)(R(0) + b0) : NINF;
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) if (j < N) { lg[j] = at[j] + nb[j]; nrm = lae(nrm, lg[j]); }
+        // xi normaliser (:319-320): sum over the arcs (0,1), (i,i), (i,i+1)_{i<N}; the (N,exit) arc is 0
+        R xn = (t == 0) ? (R)(R(0) + b0) : NINF;
+#pragma unroll
+        for (int j = 0; j < NMAX; j++)
+            if (j < N) xn = lae(xn, (j < N - 1) ? lg[j] : at[j] + self[j]);
+        R *go = gamma_out ? gamma_out + (size_t)(off + t) * N : nullptr;
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) {
+            if (j < N) {
+                R g = fexp(lg[j] - nrm);               // all -inf row -> NaN like the reference
+                gG[j] += g; gO[j] += g;
+                if (go) go[j] = g;
+                R xs = at[j] + self[j];
+                if (xn > NINF && xs > NINF) gX[j] += fexp(xs - xn);
+            }
+        }
+        // next beta, renormalised (offsets cancel in gamma / xi, so they are not kept)
+        R mx = NINF;
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) if (j < N) { b[j] = nb[j]; mx = fmax(mx, nb[j]); }
+        bx = NINF;
+        if (RENORM && mx > NINF && mx < R(INFINITY)) {
+#pragma unroll
+            for (int j = 0; j < NMAX; j++) if (j < N) b[j] -= mx;
+        }
+    }
+    R *us = ustats + (size_t)pl * 3 * N;
+#pragma unroll
+    for (int j = 0; j < NMAX; j++) if (j < N) { us[j] = gG[j]; us[N + j] = gX[j]; us[2 * N + j] = gO[j]; }
+}
+
+// ----------------------------------------------------------------------------------------------
+// grouping of utterances by model: order[] (stable) and model_start[M+1]
+__global__ void k_model_start(const int32_t *__restrict__ model_of_utt, const int32_t *__restrict__ order, int B, int M,
+                              int32_t *__restrict__ model_start) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m > M) return;
+    int lo = 0, hi = B;   // first p with model(order[p]) >= m
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (model_of_utt[order[mid]] >= m) hi = mid; else lo = mid + 1;
+    }
+    model_start[m] = lo;
+}
+
+// single-CTA stable counting sort (fallback when the caller gives no order[])
+__global__ void k_group_by_model(const int32_t *__restrict__ model_of_utt, int B, int M, int32_t *__restrict__ order) {
+    __shared__ int s_scan[1024];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int m = 0; m < M; m++) {
+        for (int b0 = 0; b0 < B; b0 += blockDim.x) {
+            int u = b0 + threadIdx.x;
+            int f = (u < B && model_of_utt[u] == m) ? 1 : 0;
+            s_scan[threadIdx.x] = f;
+            __syncthreads();
+            for (int d = 1; d < (int)blockDim.x; d <<= 1) {
+                int v = (threadIdx.x >= (unsigned)d) ? s_scan[threadIdx.x - d] : 0;
+                __syncthreads();
+                s_scan[threadIdx.x] += v;
+                __syncthreads();
+            }
+            if (f) order[s_base + s_scan[threadIdx.x] - 1] = u;
+            __syncthreads();
+            if (threadIdx.x == blockDim.x - 1) s_base += s_scan[threadIdx.x];
+            __syncthreads();
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+#define STATS_SLOTS 4  /* frame slots per feature dim */
+
+__device__ __forceinline__ int find_tile(const int32_t *model_start, int M, int upc, int tile, int *tile_in_model) {
+    int acc = 0;
+    for (int m = 0; m < M; m++) {
+        int cnt = model_start[m + 1] - model_start[m];
+        int nt = (cnt + upc - 1) / upc;
+        if (tile < acc + nt) { *tile_in_model = tile - acc; return m; }
+        acc += nt;
+    }
+    return -1;
+}
+
+// blockDim = (Dp, STATS_SLOTS).  partial[tile][2][N][Dp] float64.
+template <typename R, int NMAX>
+__global__ void k_stats_diag(const float *__restrict__ X, int ldx, const int64_t *__restrict__ offsets,
+                             const int32_t *__restrict__ order, const int32_t *__restrict__ model_start, int M, int N,
+                             int D, int Dp, int S, int upc, const double *__restrict__ mean,
+                             const R *__restrict__ gamma, double *__restrict__ partial) {
+    __shared__ int s_m, s_tim;
+    if (threadIdx.x == 0 && threadIdx.y == 0) s_m = find_tile(model_start, M, upc, blockIdx.x, &s_tim);
+    __syncthreads();
+    const int m = s_m;
+    const int d = threadIdx.x, slot = threadIdx.y;
+    double *out = partial + (size_t)blockIdx.x * 2 * N * Dp;
+    extern __shared__ double s_red[];   // [STATS_SLOTS][2][N][Dp]
+    double a1[NMAX], a2[NMAX];
+#pragma unroll
+    for (int j = 0; j < NMAX; j++) { a1[j] = 0.0; a2[j] = 0.0; }
+    if (m >= 0) {
+        R c[NMAX];
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) c[j] = (j < N && d < D) ? (R)mean[((size_t)m * S + j + 1) * D + d] : R(0);
+        const int pbeg = model_start[m] + s_tim * upc;
+        const int pend = min(pbeg + upc, model_start[m + 1]);
+        for (int p = pbeg; p < pend; p++) {
+            const int u = order[p];
+            const int64_t off = offsets[u];
+            const int T = (int)(offsets[u + 1] - off);
+            R f1[NMAX], f2[NMAX];
+#pragma unroll
+            for (int j = 0; j < NMAX; j++) { f1[j] = R(0); f2[j] = R(0); }
+            for (int t = slot; t < T; t += STATS_SLOTS) {
+                const R x = (d < D) ? (R)__ldg(X + (size_t)(off + t) * ldx + d) : R(0);
+                const R *g = gamma + (size_t)(off + t) * N;
+#pragma unroll
+                for (int j = 0; j < NMAX; j++) {
+                    if (j < N) {
+                        R gj = __ldg(g + j);
+                        R xc = x - c[j];
+                        R gx = gj * xc;
+                        f1[j] += gx;
+                        f2[j] = fma(gx, xc, f2[j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NMAX; j++) { a1[j] += (double)f1[j]; a2[j] += (double)f2[j]; }
+        }
+    }
+    // fixed-order reduction over the frame slots
+#pragma unroll
+    for (int j = 0; j < NMAX; j++)
+        if (j < N) {
+            s_red[((size_t)(slot * 2 + 0) * N + j) * Dp + d] = a1[j];
+            s_red[((size_t)(slot * 2 + 1) * N + j) * Dp + d] = a2[j];
+        }
+    __syncthreads();
+    if (slot == 0) {
+        for (int k = 0; k < 2; k++)
+            for (int j = 0; j < N; j++) {
+                double s = 0.0;
+                for (int sl = 0; sl < STATS_SLOTS; sl++) s += s_red[((size_t)(sl * 2 + k) * N + j) * Dp + d];
+                out[((size_t)k * N + j) * Dp + d] = s;
+            }
+    }
+}
+
+// fixed-order sum of the tile partials: one thread per (model, k, state, dim)
+__global__ void k_reduce_partials(const int32_t *__restrict__ model_start, int M, int N, int D, int Dp, int S, int upc,
+                                  const double *__restrict__ partial, double *__restrict__ stats, int64_t stride) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per_model = 2 * N * D;
+    if (idx >= M * per_model) return;
+    const int m = idx / per_model, i = idx % per_model;
+    const int k = i / (N * D), r = i % (N * D), j = r / D, d = r % D;
+    int tile0 = 0;
+    for (int q = 0; q < m; q++) tile0 += (model_start[q + 1] - model_start[q] + upc - 1) / upc;
+    const int ntile = (model_start[m + 1] - model_start[m] + upc - 1) / upc;
+    const double *src = partial + ((size_t)k * N + j) * Dp + d;
+    const size_t tstride = (size_t)2 * N * Dp;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int t = 0;
+    for (; t + 3 < ntile; t += 4) {
+        s0 += src[(size_t)(tile0 + t) * tstride];
+        s1 += src[(size_t)(tile0 + t + 1) * tstride];
+        s2 += src[(size_t)(tile0 + t + 2) * tstride];
+        s3 += src[(size_t)(tile0 + t + 3) * tstride];
+    }
+    for (; t < ntile; t++) s0 += src[(size_t)(tile0 + t) * tstride];
+    stats[(size_t)m * stride + (size_t)3 * S + (size_t)k * S * D + (size_t)(j + 1) * D + d] = (s0 + s1) + (s2 + s3);
+}
+
+// per-utterance (G, Xi, occ) triples of one chunk of pairs, added into stats in a fixed order:
+// grid = (3N, M), 256 threads, tree reduction.
+template <typename R>
+__global__ void k_reduce_triples(const int32_t *__restrict__ model_start, int N, int S, const R *__restrict__ ustats,
+                                 int p0, int np, double *__restrict__ stats, int64_t stride) {
+    const int m = blockIdx.y, q = blockIdx.x;
+    __shared__ double s_acc[256];
+    const int pb = max(model_start[m], p0), pe = min(model_start[m + 1], p0 + np);
+    double s = 0.0;
+    for (int p = pb + threadIdx.x; p < pe; p += blockDim.x) s += (double)ustats[(size_t)(p - p0) * 3 * N + q];
+    s_acc[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) s_acc[threadIdx.x] += s_acc[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int k = q / N, j = q % N;
+        stats[(size_t)m * stride + (size_t)k * S + j + 1] += s_acc[0];
+    }
+}
+
+extern "C" int64_t sapr_stats_stride(int N, int D) {
+    const int64_t S = N + 2;
+    return 3 * S + 2 * S * D;
+}
+
+template <typename R, int NMAX>
+static int launch_estep(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int B,
+                        int64_t total_frames, int max_T, const int32_t *model_of_utt, const int32_t *order_in,
+                        double *stats, double *loglik, void *gamma_out) {
+    const int N = m->N, M = m->M, D = m->D, Dp = m->Dp, S = m->S, nchunk = Dp / 4;
+    const int64_t stride = sapr_stats_stride(N, D);
+    int rc;
+    // grouping
+    if ((rc = sapr_ws_reserve(ctx, 2, sizeof(int32_t) * ((size_t)B + M + 2)))) return rc;
+    int32_t *order_ws = (int32_t *)ctx->ws[2];
+    int32_t *model_start = order_ws + B;
+    const int32_t *order = order_in;
+    if (!order) {
+        k_group_by_model<<<1, 1024, 0, ctx->stream>>>(model_of_utt, B, M, order_ws);
+        SAPR_LAUNCH_CHECK(ctx);
+        order = order_ws;
+    }
+    k_model_start<<<1, 64, 0, ctx->stream>>>(model_of_utt, order, B, M, model_start);
+    SAPR_LAUNCH_CHECK(ctx);
+    // gamma workspace (or the caller's debug buffer)
+    R *gamma = (R *)gamma_out;
+    if (!gamma) {
+        if ((rc = sapr_ws_reserve(ctx, 3, sizeof(R) * (size_t)total_frames * N))) return rc;
+        gamma = (R *)ctx->ws[3];
+    }
+    // forward/backward lattice scratch, chunked over pairs so it stays bounded (<= ~1 GB)
+    const size_t per_pair = (size_t)max_T * N * sizeof(R) * 2;
+    int chunk = (int)std::min<int64_t>(B, std::max<int64_t>(128, ((int64_t)1 << 30) / (int64_t)per_pair));
+    chunk = (chunk + 127) / 128 * 128;
+    if ((rc = sapr_ws_reserve(ctx, 0, per_pair * chunk))) return rc;
+    if ((rc = sapr_ws_reserve(ctx, 1, sizeof(R) * (size_t)chunk * 3 * N))) return rc;
+    R *scr_alpha = (R *)ctx->ws[0];
+    R *scr_e = scr_alpha + (size_t)chunk * max_T * N;
+    R *ustats = (R *)ctx->ws[1];
+    const int upc = std::max(8, std::min(256, B / (4 * ctx->sm_count)));
+    const int ntile_max = (B + upc - 1) / upc + M;
+    if ((rc = sapr_ws_reserve(ctx, 4, sizeof(double) * (size_t)ntile_max * 2 * N * Dp))) return rc;
+    double *partial = (double *)ctx->ws[4];
+
+    const R *pk = std::is_same<R, float>::value ? (const R *)m->pk32 : (const R *)m->pk64;
+    const R *cst = std::is_same<R, float>::value ? (const R *)m->cst32 : (const R *)m->cst64;
+    const R *la = std::is_same<R, float>::value ? (const R *)m->la32 : (const R *)m->la64;
+    const R *lb = std::is_same<R, float>::value ? (const R *)m->lb32 : (const R *)m->lb64;
+    auto kern = k_estep_fused<R, NMAX, std::is_same<R, float>::value>;
+    size_t smem = (size_t)M * model_stride<R>((size_t)nchunk * N * 8) * sizeof(R);
+    if (smem > 227 * 1024) SAPR_FAIL(ctx, SAPR_E_RANGE, "estep: model set does not fit in shared memory");
+    SAPR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int p0 = 0; p0 < B; p0 += chunk) {
+        const int np = std::min(chunk, B - p0);
+        {
+            ProfScope ps(ctx, 2);
+            kern<<<(np + 127) / 128, 128, smem, ctx->stream>>>(X, ldx, offsets, p0, np, M, N, nchunk, pk, cst, la, lb,
+                                                               model_of_utt, order, scr_alpha, scr_e, max_T, gamma,
+                                                               ustats, loglik);
+        }
+        SAPR_LAUNCH_CHECK(ctx);
+        // the small per-utterance triples are folded into stats chunk by chunk (fixed order)
+        k_reduce_triples<R><<<dim3(3 * N, M), 256, 0, ctx->stream>>>(model_start, N, S, ustats, p0, np, stats, stride);
+        SAPR_LAUNCH_CHECK(ctx);
+    }
+    // feature statistics over the whole batch
+    const int ntiles = ntile_max;
+    dim3 sb(Dp, STATS_SLOTS);
+    size_t ssm = sizeof(double) * STATS_SLOTS * 2 * N * Dp;
+    auto skern = k_stats_diag<R, NMAX>;
+    SAPR_CUDA(ctx, cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+    {
+        ProfScope ps(ctx, 3);
+        skern<<<ntiles, sb, ssm, ctx->stream>>>(X, ldx, offsets, order, model_start, M, N, D, Dp, S, upc, m->mean, gamma,
+                                                partial);
+    }
+    SAPR_LAUNCH_CHECK(ctx);
+    k_reduce_partials<<<(M * 2 * N * D + 127) / 128, 128, 0, ctx->stream>>>(model_start, M, N, D, Dp, S, upc, partial,
+                                                                            stats, stride);
+    SAPR_LAUNCH_CHECK(ctx);
+    return SAPR_OK;
+}
+
+extern "C" int sapr_estep(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int B,
+                          int64_t total_frames, int max_T, const int32_t *model_of_utt, const int32_t *order,
+                          int precision, double *stats, double *loglik, void *gamma_out) {
+    if (!ctx || !m || !X || !offsets || !model_of_utt || !stats || !loglik) return SAPR_E_INVALID;
+    if (!m->valid) SAPR_FAIL(ctx, SAPR_E_INVALID, "estep: model parameters not set");
+    if (m->emission != SAPR_EMIT_DIAG || m->topology != SAPR_TOPO_ENTRY_EXIT)
+        SAPR_FAIL(ctx, SAPR_E_INVALID, "estep: fused kernel needs DIAG emission + ENTRY_EXIT topology");
+    if (ldx % 4 || ldx < m->Dp) SAPR_FAIL(ctx, SAPR_E_INVALID, "estep: ldx must be a multiple of 4 and >= D padded");
+    if (m->Dp * STATS_SLOTS > 1024) SAPR_FAIL(ctx, SAPR_E_RANGE, "estep: D > 256 not supported");
+    SAPR_CUDA(ctx, cudaMemsetAsync(stats, 0, sizeof(double) * (size_t)m->M * sapr_stats_stride(m->N, m->D), ctx->stream));
+    if (B <= 0) return SAPR_OK;
+#define GO(R, NM) \
+    return launch_estep<R, NM>(ctx, m, X, ldx, offsets, B, total_frames, max_T, model_of_utt, order, stats, loglik, gamma_out)
+    if (precision == SAPR_FP32) {
+        if (m->N <= 8) GO(float, 8);
+        if (m->N <= 16) GO(float, 16);
+        if (m->N <= 31) GO(float, 31);
+    } else {
+        if (m->N <= 8) GO(double, 8);
+        if (m->N <= 16) GO(double, 16);
+        if (m->N <= 31) GO(double, 31);
+    }
+#undef GO
+    SAPR_FAIL(ctx, SAPR_E_RANGE, "estep: N > 31 emitting states not supported");
+}
+
+// ----------------------------------------------------------------------------------------------
+// M-step (custom_hmm.py:351-400) on the packed statistics; one thread per (model, state, dim).
+__global__ void k_mstep_diag(int M, int N, int D, int S, const double *__restrict__ stats, int64_t stride,
+                             const double *__restrict__ floor_var, double *__restrict__ mean, double *__restrict__ var,
+                             double *__restrict__ A) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = M * S * D;
+    if (idx < total) {
+        const int d = idx % D, j = (idx / D) % S, m = idx / (D * S);
+        const double *st = stats + (size_t)m * stride;
+        double nm = 0.0, nv = 0.0;
+        if (j >= 1 && j <= N) {
+            const double occ = st[2 * S + j];
+            if (occ > 0) {
+                const double c = mean[idx];
+                const double s1 = st[3 * S + (size_t)j * D + d], s2 = st[3 * S + (size_t)S * D + (size_t)j * D + d];
+                const double dm = s1 / occ;
+                nm = c + dm;
+                double v = s2 / occ - dm * dm;          // = sum gamma (x - mu_new)^2 / occ
+                const double fl = floor_var[m];
+                nv = (v != v) ? v : (v > fl ? v : fl);   // np.maximum keeps NaN (:397)
+            }
+        }
+        // defer the mean write until every thread of this (m, j) row has read its pivot: each thread only
+        // touches its own element, so writing in place is safe.
+        mean[idx] = nm;
+        var[idx] = nv;
+    }
+    if (idx < M * S) {   // transitions (:351-364)
+        const int j = idx % S, m = idx / S;
+        const double *st = stats + (size_t)m * stride;
+        double *Am = A + (size_t)m * S * S;
+        if (j == 0) Am[0 * S + 1] = 1.0;
+        else if (j == S - 1) Am[(size_t)j * S + j] = 1.0;
+        else if (st[j] > 0) {
+            const double aii = st[S + j] / st[j];
+            Am[(size_t)j * S + j] = aii;
+            Am[(size_t)j * S + j + 1] = 1.0 - aii;
+        }
+    }
+}
+
+extern "C" int sapr_mstep(sapr_ctx *ctx, sapr_models *m, const double *stats, const double *floor_var_host) {
+    if (!ctx || !m || !stats || !floor_var_host) return SAPR_E_INVALID;
+    if (m->emission != SAPR_EMIT_DIAG || m->topology != SAPR_TOPO_ENTRY_EXIT)
+        SAPR_FAIL(ctx, SAPR_E_INVALID, "mstep: needs DIAG emission + ENTRY_EXIT topology");
+    int rc = sapr_ws_reserve(ctx, 5, sizeof(double) * m->M);
+    if (rc) return rc;
+    SAPR_CUDA(ctx, cudaMemcpyAsync(ctx->ws[5], floor_var_host, sizeof(double) * m->M, cudaMemcpyHostToDevice, ctx->stream));
+    SAPR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // floor_var_host is pageable caller memory
+    const int total = m->M * m->S * m->D;
+    k_mstep_diag<<<(total + 255) / 256, 256, 0, ctx->stream>>>(m->M, m->N, m->D, m->S, stats, sapr_stats_stride(m->N, m->D),
+                                                               (const double *)ctx->ws[5], m->mean, m->cov, m->A);
+    SAPR_LAUNCH_CHECK(ctx);
+    return sapr_models_prepare(m);
+}

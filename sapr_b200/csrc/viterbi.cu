@@ -1,0 +1,277 @@
+// viterbi.cu -- batched max-product decoding with fused diagonal-Gaussian emission.
+//
+// Replaces custom_hmm.py:462-514 (HMM.decode) for every (utterance, model) pair and the
+// strict-'>' argmax over word models of decoder.py:42-47.
+//
+// Mapping: one thread per (utterance, model); a warp holds 32 utterances of the SAME model so the
+// model's packed (mu, 0.5/var) rows are shared-memory broadcasts, the N state scores and the exit
+// score live in registers, and the left-to-right transition needs no shuffles at all.  Features are
+// read once per CTA from HBM (the M model-warps of a CTA walk the same 32 utterances in lock step, so
+// M-1 of the M reads hit L1).  Back-pointers are one bit per (frame, state) -- "advanced from j-1" vs
+// "stayed in j" -- packed in one word per frame and kept in an L2-resident scratch laid out
+// [model][frame][utterance] so each warp store is one coalesced line.
+#include "common.cuh"
+
+template <typename R> struct alignas(16) Vec4 { R x, y, z, w; };
+
+template <typename R, int NMAX>
+__device__ __forceinline__ void emit_diag(const float *__restrict__ xrow, int nchunk, int N,
+                                          const R *__restrict__ spk_model, const R *cst, R *e) {
+    R acc[NMAX];
+#pragma unroll
+    for (int j = 0; j < NMAX; j++) acc[j] = R(0);
+    const float4 *xr = reinterpret_cast<const float4 *>(xrow);
+    for (int c = 0; c < nchunk; c++) {
+        float4 xv = __ldg(xr + c);
+        const R *p = spk_model + (size_t)c * N * 8;
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) {
+            if (j < N) {
+                Vec4<R> mu = *reinterpret_cast<const Vec4<R> *>(p + j * 8);
+                Vec4<R> h = *reinterpret_cast<const Vec4<R> *>(p + j * 8 + 4);
+                R d0 = R(xv.x) - mu.x, d1 = R(xv.y) - mu.y, d2 = R(xv.z) - mu.z, d3 = R(xv.w) - mu.w;
+                R a = acc[j];
+                a = fma(d0 * d0, h.x, a);
+                a = fma(d1 * d1, h.y, a);
+                a = fma(d2 * d2, h.z, a);
+                a = fma(d3 * d3, h.w, a);
+                acc[j] = a;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NMAX; j++) e[j] = (j < N) ? cst[j] - acc[j] : R(0);
+}
+
+// blockDim = (32 utterances, models-per-CTA).  all-models mode: slot = model; own-model mode
+// (model_of_utt != NULL): one slot, the model differs per lane.
+template <typename R, typename BP, int NMAX, bool RENORM>
+__global__ void __launch_bounds__(32 * 16)
+k_viterbi_fused(const float *__restrict__ X, int ldx, const int64_t *__restrict__ offsets, int u0, int nu, int M,
+                int N, int nchunk, const R *__restrict__ pk, const R *__restrict__ cst_g, const R *__restrict__ la_g,
+                const R *__restrict__ lb_g, const int32_t *__restrict__ model_of_utt, int first_frames,
+                BP *__restrict__ bp, int64_t Bpad, int maxT, int nslots, double *__restrict__ scores) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *spk = reinterpret_cast<R *>(smem_raw);
+    const int S = N + 2;
+    const size_t per_model = (size_t)nchunk * N * 8;
+    const bool own = (model_of_utt != nullptr);
+    const int m0 = own ? 0 : blockIdx.y * blockDim.y;
+    const int nm = own ? M : min((int)blockDim.y, M - m0);
+    {   // stage the packed emission parameters of this CTA's models
+        const int tid = threadIdx.y * 32 + threadIdx.x, nt = blockDim.x * blockDim.y;
+        const R *src = pk + (size_t)m0 * per_model;
+        for (size_t i = tid; i < (size_t)nm * per_model; i += nt) spk[i] = src[i];
+    }
+    __syncthreads();
+    const int ul = blockIdx.x * 32 + threadIdx.x;   // utterance within this chunk
+    const int slot = own ? 0 : m0 + threadIdx.y;
+    if (ul >= nu || slot >= nslots || (own && threadIdx.y > 0)) return;
+    const int u = u0 + ul;
+    const int m = own ? model_of_utt[u] : slot;
+    const R *spk_model = spk + (size_t)(m - m0) * per_model;
+
+    R cst[NMAX], la[NMAX + 2], lb[NMAX + 2];
+#pragma unroll
+    for (int j = 0; j < NMAX; j++) cst[j] = (j < N) ? cst_g[(size_t)m * N + j] : R(0);
+#pragma unroll
+    for (int j = 0; j < NMAX + 2; j++) {
+        la[j] = (j < S) ? la_g[(size_t)m * S + j] : R(0);
+        lb[j] = (j < S) ? lb_g[(size_t)m * S + j] : R(0);
+    }
+    const R lbN = lb_g[(size_t)m * S + N], laX = la_g[(size_t)m * S + S - 1];   // ln A[N, exit], ln A[exit, exit]
+    const int64_t off = offsets[u];
+    const int T = (int)(offsets[u + 1] - off);
+    const int Te = (first_frames > 0 && first_frames < T) ? first_frames : T;
+    const R NINF = Num<R>::ninf();
+
+    R V[NMAX + 1];   // V[j] = state j+1 (emitting), j < N;  exit kept separately
+    R e[NMAX];
+#pragma unroll
+    for (int j = 0; j <= NMAX; j++) V[j] = NINF;
+    R Vx = NINF;
+    double base = 0.0;
+    if (Te > 0) {
+        emit_diag<R, NMAX>(X + (size_t)off * ldx, nchunk, N, spk_model, cst, e);
+        V[0] = lb[0] + e[0];   // V[0,1] = ln A01 + E[0,1]   (custom_hmm.py:473)
+    }
+    BP *bpp = bp + ((size_t)slot * maxT) * Bpad + ul;
+    for (int t = 1; t < Te; t++) {
+        emit_diag<R, NMAX>(X + (size_t)(off + t) * ldx, nchunk, N, spk_model, cst, e);
+        unsigned bits = 0;
+        // exit state first (reads the old V[N-1]); open only for t >= N (custom_hmm.py:481-485)
+        R nx = NINF;
+        if (t >= N) {
+            R best = NINF;
+            R vN = NINF;   // V of the last emitting state, selected without dynamic register indexing
+#pragma unroll
+            for (int j = 0; j < NMAX; j++) if (j == N - 1) vN = V[j];
+            R c_adv = vN + lbN, c_stay = Vx + laX;
+            if (c_adv > best) { best = c_adv; bits |= (1u << N); }
+            if (c_stay > best) { best = c_stay; bits &= ~(1u << N); }
+            nx = best;
+        }
+        // emitting states, high to low so V[j-1] is still the previous frame's value
+#pragma unroll
+        for (int j = NMAX - 1; j >= 1; j--) {
+            if (j < N) {
+                R best = NINF;
+                R c_adv = V[j - 1] + lb[j], c_stay = V[j] + la[j + 1];
+                bool adv = false;
+                if (c_adv > best) { best = c_adv; adv = true; }     // first candidate: j-1 (:488)
+                if (c_stay > best) { best = c_stay; adv = false; }
+                if (adv) bits |= (1u << j);
+                V[j] = (best > NINF) ? best + e[j] : NINF;
+            }
+        }
+        {   // state 1: candidates [1] then, at t == 1 only, the entry state (:477-480)
+            R best = NINF;
+            R c_stay = V[0] + la[1];
+            bool adv = false;
+            if (c_stay > best) best = c_stay;
+            if (t == 1) {
+                R c_ent = R(0) + lb[0];   // V[0,0] = 0
+                if (c_ent > best) { best = c_ent; adv = true; }
+            }
+            if (adv) bits |= 1u;
+            V[0] = (best > NINF) ? best + e[0] : NINF;
+        }
+        Vx = nx;
+        if (RENORM) {
+            R mx = Vx;
+#pragma unroll
+            for (int j = 0; j < NMAX; j++) if (j < N) mx = fmax(mx, V[j]);
+            if (mx > NINF && mx < R(INFINITY)) {
+#pragma unroll
+                for (int j = 0; j < NMAX; j++) if (j < N) V[j] -= mx;
+                Vx -= mx;
+                base += (double)mx;
+            }
+        }
+        bpp[(size_t)t * Bpad] = (BP)bits;
+    }
+    double sc = (Vx > NINF || Vx != Vx) ? (double)Vx + base : (double)NINF;
+    if (Te <= 0) sc = (double)NINF;
+    scores[(size_t)ul * nslots + slot] = sc;
+}
+
+// argmax over models (strict '>' keeps the first best, decoder.py:44) + back-trace (custom_hmm.py:505-512)
+template <typename BP>
+__global__ void k_viterbi_finish(const int64_t *__restrict__ offsets, int u0, int nu, int N, int nslots,
+                                 const int32_t *__restrict__ model_of_utt, int first_frames,
+                                 const BP *__restrict__ bp, int64_t Bpad, int maxT,
+                                 const double *__restrict__ scores, int32_t *__restrict__ best_word,
+                                 double *__restrict__ best_score, double *__restrict__ scores_out, int M,
+                                 uint8_t *__restrict__ best_path, uint8_t *__restrict__ all_paths,
+                                 int64_t total_frames) {
+    const int ul = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ul >= nu) return;
+    const int u = u0 + ul;
+    const int S = N + 2;
+    const int64_t off = offsets[u];
+    const int T = (int)(offsets[u + 1] - off);
+    const int Te = (first_frames > 0 && first_frames < T) ? first_frames : T;
+    double bs = -INFINITY;
+    int bslot = -1;
+    for (int s = 0; s < nslots; s++) {
+        double sc = scores[(size_t)ul * nslots + s];
+        if (scores_out) scores_out[(size_t)u * nslots + s] = sc;
+        if (sc > bs) { bs = sc; bslot = s; }
+    }
+    if (best_word) best_word[u] = (bslot < 0) ? -1 : (model_of_utt ? model_of_utt[u] : bslot);
+    if (best_score) best_score[u] = bs;
+    for (int s = 0; s < nslots; s++) {
+        uint8_t *out = nullptr;
+        if (all_paths) out = all_paths + (size_t)s * total_frames + off;
+        else if (best_path && s == (bslot < 0 ? 0 : bslot)) out = best_path + off;
+        if (!out) continue;
+        const bool reachable = scores[(size_t)ul * nslots + s] != -INFINITY;
+        const BP *bpp = bp + ((size_t)s * maxT) * Bpad + ul;
+        int cur = S - 1;
+        for (int t = Te - 1; t >= 0; t--) {
+            out[t] = (uint8_t)cur;
+            if (!reachable) { cur = 0; continue; }     // unreachable cell: backpointer stays 0 (:470)
+            if (t == 0) break;
+            unsigned bits = (unsigned)bpp[(size_t)t * Bpad];
+            if (cur == S - 1) cur = ((bits >> N) & 1u) ? N : S - 1;
+            else if (cur >= 1) cur = ((bits >> (cur - 1)) & 1u) ? cur - 1 : cur;
+        }
+    }
+}
+
+template <typename R, typename BP, int NMAX>
+static int launch_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int B,
+                          int64_t total_frames, int max_T, const int32_t *model_of_utt, int first_frames,
+                          int32_t *best_word, double *best_score, double *scores, uint8_t *best_path,
+                          uint8_t *all_paths) {
+    const bool own = model_of_utt != nullptr;
+    const int nslots = own ? 1 : m->M;
+    const int nchunk = m->Dp / 4;
+    const int Tm = (first_frames > 0 && first_frames < max_T) ? first_frames : max_T;
+    // chunk the batch so the back-pointer scratch stays <= ~192 MB
+    int64_t per_utt = (int64_t)nslots * (Tm > 0 ? Tm : 1) * sizeof(BP);
+    int chunk = (int)std::min<int64_t>(B, std::max<int64_t>(32, ((int64_t)192 << 20) / per_utt));
+    chunk = (chunk + 31) / 32 * 32;
+    const int64_t Bpad = chunk;
+    int rc = sapr_ws_reserve(ctx, 0, (size_t)per_utt * Bpad);
+    if (rc) return rc;
+    rc = sapr_ws_reserve(ctx, 1, (size_t)chunk * nslots * sizeof(double));
+    if (rc) return rc;
+    BP *bp = (BP *)ctx->ws[0];
+    double *sc_ws = (double *)ctx->ws[1];
+    const int mpc = own ? 1 : std::min(m->M, 16);
+    const int nm_stage = own ? m->M : mpc;
+    size_t smem = (size_t)nm_stage * nchunk * m->N * 8 * sizeof(R);
+    auto kern = k_viterbi_fused<R, BP, NMAX, std::is_same<R, float>::value>;
+    if (smem > 227 * 1024) SAPR_FAIL(ctx, SAPR_E_RANGE, "viterbi: model set does not fit in shared memory");
+    SAPR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const R *pk = std::is_same<R, float>::value ? (const R *)m->pk32 : (const R *)m->pk64;
+    const R *cst = std::is_same<R, float>::value ? (const R *)m->cst32 : (const R *)m->cst64;
+    const R *la = std::is_same<R, float>::value ? (const R *)m->la32 : (const R *)m->la64;
+    const R *lb = std::is_same<R, float>::value ? (const R *)m->lb32 : (const R *)m->lb64;
+    for (int u0 = 0; u0 < B; u0 += chunk) {
+        const int nu = std::min(chunk, B - u0);
+        dim3 block(32, mpc), grid((nu + 31) / 32, own ? 1 : (m->M + mpc - 1) / mpc);
+        {
+            ProfScope ps(ctx, 0);
+            kern<<<grid, block, smem, ctx->stream>>>(X, ldx, offsets, u0, nu, m->M, m->N, nchunk, pk, cst, la, lb,
+                                                     model_of_utt, first_frames, bp, Bpad, Tm, nslots, sc_ws);
+        }
+        SAPR_LAUNCH_CHECK(ctx);
+        {
+            ProfScope ps(ctx, 1);
+            k_viterbi_finish<BP><<<(nu + 127) / 128, 128, 0, ctx->stream>>>(
+                offsets, u0, nu, m->N, nslots, model_of_utt, first_frames, bp, Bpad, Tm, sc_ws, best_word, best_score,
+                scores, m->M, best_path, all_paths, total_frames);
+        }
+        SAPR_LAUNCH_CHECK(ctx);
+    }
+    return SAPR_OK;
+}
+
+extern "C" int sapr_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int B,
+                            int64_t total_frames, int max_T, const int32_t *model_of_utt, int precision,
+                            int first_frames, int32_t *best_word, double *best_score, double *scores,
+                            uint8_t *best_path, uint8_t *all_paths) {
+    if (!ctx || !m || !X || !offsets) return SAPR_E_INVALID;
+    if (!m->valid) SAPR_FAIL(ctx, SAPR_E_INVALID, "viterbi: model parameters not set");
+    if (m->emission != SAPR_EMIT_DIAG || m->topology != SAPR_TOPO_ENTRY_EXIT)
+        SAPR_FAIL(ctx, SAPR_E_INVALID, "viterbi: fused kernel needs DIAG emission + ENTRY_EXIT topology");
+    if (ldx % 4 || ldx < m->Dp) SAPR_FAIL(ctx, SAPR_E_INVALID, "viterbi: ldx must be a multiple of 4 and >= D padded");
+    if (B <= 0) return SAPR_OK;
+    if (max_T <= 0) SAPR_FAIL(ctx, SAPR_E_INVALID, "viterbi: max_T must be positive");
+#define GO(R, BP, NM)                                                                                       \
+    return launch_viterbi<R, BP, NM>(ctx, m, X, ldx, offsets, B, total_frames, max_T, model_of_utt,        \
+                                     first_frames, best_word, best_score, scores, best_path, all_paths)
+    if (precision == SAPR_FP32) {
+        if (m->N <= 8) GO(float, uint16_t, 8);
+        if (m->N <= 15) GO(float, uint16_t, 15);
+        if (m->N <= 31) GO(float, uint32_t, 31);
+    } else {
+        if (m->N <= 8) GO(double, uint16_t, 8);
+        if (m->N <= 15) GO(double, uint16_t, 15);
+        if (m->N <= 31) GO(double, uint32_t, 31);
+    }
+#undef GO
+    SAPR_FAIL(ctx, SAPR_E_RANGE, "viterbi: N > 31 emitting states not supported by the left-to-right kernel");
+}

@@ -1,0 +1,273 @@
+"""Drop-in for the reference's ``assignment2/custom_hmm.py``: same class name, constructor, attributes,
+method names, argument meaning and error behaviour -- every number is computed by the CUDA kernels of
+libsaprb200 (no numpy arithmetic on the hot path, no CPU fallback).
+
+``semantics`` (constructor kwarg or ``SAPR_SEMANTICS`` env):
+
+* ``"sapr"`` (default) -- bug-compatible with the reference as written:
+  Gram-row-sum emission over full covariances, ``decode`` walks the first ``features.shape[0]`` frames.
+  Runs the float64 kernels of csrc/compat.cu.
+* ``"standard"`` -- true diagonal-Gaussian emission, ``decode`` walks every frame; Baum-Welch and
+  Viterbi run the fused kernels (csrc/estep.cu, csrc/viterbi.cu) in ``precision`` "fp32" (production)
+  or "fp64" (verification).  The entry/exit topology (D4, D5, D9) is kept in both modes.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from typing import List, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import EMIT_DIAG, EMIT_SAPR, FP32, FP64, TOPO_ENTRY_EXIT, ptr
+from .engine import PackedBatch, WordModels
+
+logging.basicConfig(level=logging.INFO)   # the reference does this at import (custom_hmm.py:6)
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class HMM:
+    def __init__(self, num_states: int, num_obs: int, feature_set: list = None, model_name: str = None,
+                 var_floor_factor: float = 0.001, semantics: str = None, precision: str = None):
+        assert num_states > 0, "Number of states must be greater than 0."
+        assert num_obs > 0, "Number of observations must be greater than 0."
+        self.model_name = model_name
+        self.num_states = num_states
+        self.num_obs = num_obs
+        self.var_floor_factor = var_floor_factor
+        self.total_states = num_states + 2
+        self.semantics = semantics or os.environ.get("SAPR_SEMANTICS", "sapr")
+        assert self.semantics in ("sapr", "standard")
+        self.precision = precision or ("fp64" if os.environ.get("SAPR_FP64_VERIFY", "0") == "1" else "fp32")
+        self.pi = np.zeros(self.total_states)
+        self.pi[0] = 1.0
+        self._dev = None
+        if feature_set is not None:
+            assert all(feature.shape[0] == num_obs for feature in feature_set), \
+                "All features must have the same dimension as the number of observations."
+            self.init_parameters(feature_set)
+
+    # ---- pickling: plain numpy state only (train.py:74-78 pickles the whole object) ----
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_dev"] = None
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._dev = None
+
+    # ---- device plumbing ----
+    def _prec(self):
+        return FP64 if self.precision == "fp64" else FP32
+
+    def _models(self) -> WordModels:
+        """Upload the (possibly caller-mutated) numpy parameters; tests edit A / B in place."""
+        emission = EMIT_SAPR if self.semantics == "sapr" else EMIT_DIAG
+        if self._dev is None or self._dev.emission != emission:
+            self._dev = WordModels(1, self.num_states, self.num_obs, emission, TOPO_ENTRY_EXIT)
+        cov = np.asarray(self.B["covariance"], dtype=np.float64)
+        if emission == EMIT_DIAG:
+            cov = np.ascontiguousarray(np.diagonal(cov, axis1=1, axis2=2)) if cov.ndim == 3 else cov
+        self._dev.set(self.B["mean"], cov, self.A)
+        return self._dev
+
+    def _pull(self):
+        means, cov, A, _ = self._dev.get()
+        self.A = A[0]
+        if self._dev.emission == EMIT_DIAG:
+            full = np.zeros((self.total_states, self.num_obs, self.num_obs))
+            idx = np.arange(self.num_obs)
+            full[:, idx, idx] = cov[0]
+            cov0 = full
+        else:
+            cov0 = cov[0]
+        self.B = {"mean": means[0], "covariance": cov0}
+
+    @staticmethod
+    def _pack(features_list) -> PackedBatch:
+        return PackedBatch.from_features(features_list)
+
+    # ---- initialisation (custom_hmm.py:35-116) ----
+    def init_parameters(self, feature_set) -> None:
+        from .engine import init_flat_start
+        batch = self._pack(feature_set)
+        gmean, var, A, _ = init_flat_start(batch, self.num_states, self.var_floor_factor)
+        self.global_mean = gmean
+        self.global_covariance = np.diag(var)
+        self.A = A
+        means = np.tile(self.global_mean, (self.total_states, 1))
+        covars = np.zeros((self.total_states, self.num_obs, self.num_obs))
+        for i in range(self.total_states):
+            covars[i] = self.global_covariance.copy()
+        self.B = {"mean": means, "covariance": covars}
+
+    def calculate_means(self, feature_set):
+        from .engine import init_flat_start
+        return init_flat_start(self._pack(feature_set), self.num_states, self.var_floor_factor)[0]
+
+    def initialize_transitions(self, feature_set, num_states):
+        from .engine import init_flat_start
+        return init_flat_start(self._pack(feature_set), num_states, self.var_floor_factor)[2]
+
+    # ---- per-step methods (float64 kernels on materialised matrices) ----
+    def compute_emission_matrix(self, features):
+        """(D, T) features -> (T, S) log-emissions; entry/exit columns are -inf (custom_hmm.py:146-174)."""
+        torch = _torch()
+        features = np.asarray(features)
+        if features.shape[0] != self.num_obs:
+            # the reference's broadcast `features - mean[:, newaxis]` raises for the wrong orientation
+            raise ValueError(f"operands could not be broadcast together with shapes {features.shape} ({self.num_obs},1)")
+        m = self._models()
+        batch = self._pack([features])
+        E = torch.empty((batch.total_frames, self.total_states), dtype=torch.float64, device=batch.X.device)
+        m.ctx.check(m.lib.sapr_emission(m.ctx.h, m.h, 0, ptr(batch.X), batch.ldx, batch.total_frames, ptr(E)))
+        return E.cpu().numpy()
+
+    def _dev_f64(self, a):
+        torch = _torch()
+        return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device="cuda")
+
+    def forward(self, emission_matrix):
+        torch = _torch()
+        m = self._models()
+        E = self._dev_f64(emission_matrix)
+        T = E.shape[0]
+        alpha = torch.empty_like(E)
+        scale = torch.zeros(1, dtype=torch.float64, device=E.device)
+        m.ctx.check(m.lib.sapr_forward(m.ctx.h, m.h, 0, ptr(E), T, ptr(alpha), ptr(scale)))
+        return alpha.cpu().numpy(), float(scale.item())
+
+    def backward(self, emission_matrix, scale_factor):
+        torch = _torch()
+        m = self._models()
+        E = self._dev_f64(emission_matrix)
+        beta = torch.empty_like(E)
+        scale = torch.tensor([scale_factor], dtype=torch.float64, device=E.device)
+        m.ctx.check(m.lib.sapr_backward(m.ctx.h, m.h, 0, ptr(E), E.shape[0], ptr(scale), ptr(beta)))
+        return beta.cpu().numpy()
+
+    def compute_gamma(self, alpha, beta):
+        torch = _torch()
+        ctx = _lib.default_context()
+        a, b = self._dev_f64(alpha), self._dev_f64(beta)
+        g = torch.empty_like(a)
+        ctx.check(ctx.lib.sapr_gamma(ctx.h, a.shape[1], ptr(a), ptr(b), a.shape[0], ptr(g)))
+        return g.cpu().numpy()
+
+    def compute_xi(self, alpha, beta, emission_matrix):
+        torch = _torch()
+        m = self._models()
+        a, b, E = self._dev_f64(alpha), self._dev_f64(beta), self._dev_f64(emission_matrix)
+        T, S = a.shape
+        xi = torch.zeros((max(T - 1, 0), S, S), dtype=torch.float64, device=a.device)
+        m.ctx.check(m.lib.sapr_xi(m.ctx.h, m.h, 0, ptr(a), ptr(b), ptr(E), T, ptr(xi)))
+        return xi.cpu().numpy()
+
+    def update_A(self, aggregated_xi, aggregated_gamma) -> None:
+        m = self._models()
+        ax, ag = self._dev_f64(aggregated_xi), self._dev_f64(aggregated_gamma)
+        m.ctx.check(m.lib.sapr_update_A(m.ctx.h, m.h, 0, ptr(ax), ptr(ag)))
+        self.A = m.get()[2][0]
+
+    def _floor(self):
+        return float(self.var_floor_factor * np.mean(np.diagonal(self.global_covariance)))
+
+    def update_B(self, features_list, gamma_per_seq) -> None:
+        m = self._models()
+        batch = self._pack(features_list)
+        g = self._dev_f64(np.concatenate([np.asarray(x) for x in gamma_per_seq], axis=0))
+        m.ctx.check(m.lib.sapr_update_B(m.ctx.h, m.h, 0, ptr(batch.X), batch.ldx, batch.total_frames, ptr(g), self._floor()))
+        self._pull()
+
+    # ---- training (custom_hmm.py:402-460) ----
+    def baum_welch(self, features_list, max_iter: int = 15, tol: float = 1e-4):
+        torch = _torch()
+        print(f"\nTraining `{self.model_name}` HMM using Baum-Welch algorithm...")
+        batch = self._pack(features_list)
+        m = self._models()
+        S = self.total_states
+        dev = batch.X.device
+        prev = float("-inf")
+        history = []
+        fused = self.semantics == "standard"
+        if fused:
+            labels = torch.zeros(batch.B, dtype=torch.int32, device=dev)
+        else:
+            gamma = torch.empty((batch.total_frames, S), dtype=torch.float64, device=dev)
+            agg_g = torch.empty(S, dtype=torch.float64, device=dev)
+            agg_x = torch.empty((S, S), dtype=torch.float64, device=dev)
+            ll = torch.empty(batch.B, dtype=torch.float64, device=dev)
+        for iteration in range(max_iter):
+            if fused:
+                stats, ll, _ = m.estep(batch, labels, None, self._prec())
+            else:
+                m.ctx.check(m.lib.sapr_estep_compat(m.ctx.h, m.h, 0, ptr(batch.X), batch.ldx, ptr(batch.offsets), batch.B,
+                                                    batch.total_frames, ptr(gamma), ptr(agg_g), ptr(agg_x), ptr(ll)))
+            total = float(ll.cpu().numpy().sum())   # utterance order, like the reference accumulation
+            history.append(total)
+            print(f"Iteration {iteration + 1}, Log-Likelihood: {total:.2f}")
+            if abs(total - prev) < tol:
+                print(f"Converged after {iteration + 1} iterations!")
+                break
+            prev = total
+            if fused:
+                m.mstep(stats, self._floor())
+            else:
+                m.ctx.check(m.lib.sapr_update_A(m.ctx.h, m.h, 0, ptr(agg_x), ptr(agg_g)))
+                m.ctx.check(m.lib.sapr_update_B(m.ctx.h, m.h, 0, ptr(batch.X), batch.ldx, batch.total_frames, ptr(gamma),
+                                                self._floor()))
+        self._pull()
+        print("Training complete!")
+        return history
+
+    # ---- decoding (custom_hmm.py:462-514) ----
+    def decode(self, features) -> Tuple[float, List[int]]:
+        """Returns (log_prob, path) -- the reference's annotation says the opposite order (:462 vs :514)."""
+        torch = _torch()
+        features = np.asarray(features)
+        if self.semantics == "sapr":
+            T_eff = features.shape[0]                     # custom_hmm.py:466
+            if features.shape[0] != self.num_obs:
+                raise ValueError(f"operands could not be broadcast together with shapes {features.shape} ({self.num_obs},1)")
+            T = features.shape[1]
+            if T < T_eff:
+                raise IndexError(f"index {T} is out of bounds for axis 0 with size {T}")
+            m = self._models()
+            batch = self._pack([features])
+            score = torch.zeros(1, dtype=torch.float64, device=batch.X.device)
+            path = torch.zeros(T_eff, dtype=torch.int32, device=batch.X.device)
+            m.ctx.check(m.lib.sapr_decode_compat(m.ctx.h, m.h, 0, ptr(batch.X), batch.ldx, T, T_eff, ptr(score), ptr(path)))
+            return float(score.item()), [int(p) for p in path.cpu().numpy()]
+        # standard: (D, T) in, every frame walked, fused kernel
+        if features.shape[0] != self.num_obs:
+            raise ValueError(f"operands could not be broadcast together with shapes {features.shape} ({self.num_obs},1)")
+        m = self._models()
+        batch = self._pack([features])
+        out = m.viterbi(batch, None, self._prec(), 0, want_scores=False, want_path=True)
+        return float(out["best_score"].item()), [int(p) for p in out["path"].cpu().numpy()]
+
+    # ---- printers (custom_hmm.py:118-144, :324-349); formatting only ----
+    def print_parameters(self):
+        print("HMM Parameters:")
+        print(f"\nN (states): {self.num_states}")
+        print(f"\nM (observation dim): {self.num_obs}")
+        print(f"\nπ (initial state distribution): {self.pi.round(3)}")
+        print("\nA (transition matrix):")
+        self.print_matrix(self.A, "Transition Matrix", col="To", idx="From")
+
+    def print_matrix(self, matrix, title, col="T", idx="State", start_idx=0, start_col=0) -> None:
+        matrix = np.asarray(matrix)
+        if matrix.ndim == 2:
+            import pandas as pd
+            print(f"\n{title}:")
+            df = pd.DataFrame(matrix, columns=[f"{col} {i + start_col}" for i in range(matrix.shape[1])],
+                              index=[f"{idx} {i + start_idx}" for i in range(matrix.shape[0])])
+            print(df)
+        else:
+            logging.warning("Method only supports 2D matrices.")

@@ -1,0 +1,243 @@
+"""Parity of the fused CUDA kernels (through the C ABI) against the reference-generated golden vectors and
+the CPU oracle.  Run with ``-m gpu`` on a B200."""
+import numpy as np
+import pytest
+
+from conftest import assert_close, split_features
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from sapr_b200 import engine
+    return engine
+
+
+def _models(eng, g, M=None):
+    A, means, var = g["A"], g["means"], g["var"]
+    M = M or means.shape[0]
+    m = eng.WordModels(M, int(g["N"]), int(g["D"]))
+    m.set(means[:M], var[:M], A[:M])
+    return m
+
+
+def path_score(E, A, path):
+    """Score of a given state path under the reference's decode rules (custom_hmm.py:469-503)."""
+    S = E.shape[1]
+    with np.errstate(divide="ignore"):
+        lA = np.log(A)
+    s = 0.0
+    prev = path[0]
+    s += 0.0 if prev == 0 else (lA[0, 1] + E[0, 1] if prev == 1 else -np.inf)
+    for t in range(1, len(path)):
+        j = path[t]
+        s += lA[prev, j] + (E[t, j] if 0 < j < S - 1 else 0.0)
+        prev = j
+    return s
+
+
+@pytest.mark.parametrize("name", ["rung1_d39", "rung1_d13"])
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_viterbi_all_models_vs_reference(eng, name, prec, request):
+    g = request.getfixturevalue(name)
+    feats = split_features(g)
+    m = _models(eng, g)
+    batch = eng.PackedBatch.from_features(feats)
+    P = eng.FP64 if prec == "fp64" else eng.FP32
+    out = m.viterbi(batch, None, P, 0, want_scores=True, want_path=True, all_paths=True)
+    sc = out["scores"].cpu().numpy(); bw = out["best_word"].cpu().numpy()
+    allp = out["all_paths"].cpu().numpy(); bp = out["path"].cpu().numpy()
+    offs = batch.offsets_host
+    # float64 verification mode: rel 1e-12; fp32 production mode: rel 1e-6 (stated tolerance)
+    assert_close(sc, g["dec_scores"], 1e-12 if prec == "fp64" else 1e-6, what="scores")
+    assert np.array_equal(bw, g["dec_best"])
+    assert_close(out["best_score"].cpu().numpy(), g["dec_scores"][np.arange(len(bw)), bw],
+                 1e-12 if prec == "fp64" else 1e-6, what="best_score")
+    near_ties = 0
+    for u in range(batch.B):
+        T = feats[u].shape[1]
+        assert np.array_equal(bp[offs[u]:offs[u + 1]], allp[bw[u], offs[u]:offs[u + 1]])
+        for w in range(m.M):
+            got = allp[w, offs[u]:offs[u + 1]].astype(np.int32)
+            ref = g["dec_paths"][u, w, :T].astype(np.int32)
+            if np.array_equal(got, ref):
+                continue
+            assert prec == "fp32", f"float64 path differs for utt {u} model {w}"
+            # documented near-tie policy: the fp32 path must score within 2e-3 of the optimum in float64
+            E = orc.emission_diag(feats[u], g["means"][w], g["var"][w])
+            assert abs(path_score(E, g["A"][w], got) - g["dec_scores"][u, w]) < 2e-3, (u, w)
+            near_ties += 1
+    assert near_ties <= 0.02 * batch.B * m.M
+
+
+def test_viterbi_first_frames_and_own_model(eng, rung1_d13):
+    """the reference walks only features.shape[0] = D frames; and the own-model mode."""
+    import torch
+    g = rung1_d13
+    feats = split_features(g)
+    m = _models(eng, g)
+    batch = eng.PackedBatch.from_features(feats)
+    D = int(g["D"])
+    out = m.viterbi(batch, None, eng.FP64, D, want_scores=True, want_path=True)
+    X, offs = orc.pack(feats)
+    bw, bs, sc, bp = orc.viterbi_batch(X, offs, g["A"], g["means"], g["var"], first_frames=D)
+    assert np.array_equal(out["best_word"].cpu().numpy(), bw)
+    assert_close(out["scores"].cpu().numpy(), sc, 1e-12, what="scores")
+    p = out["path"].cpu().numpy()
+    for u in range(batch.B):
+        assert np.array_equal(p[offs[u]:offs[u] + D], bp[offs[u]:offs[u] + D])
+    # own-model mode: each utterance against its label's model only
+    lab = torch.as_tensor(g["labels"].astype(np.int32), device="cuda")
+    out2 = m.viterbi(batch, lab, eng.FP64, 0, want_scores=True, want_path=True)
+    assert np.array_equal(out2["best_word"].cpu().numpy(), g["labels"])
+    assert_close(out2["best_score"].cpu().numpy(), g["dec_scores"][np.arange(batch.B), g["labels"]], 1e-12, what="own")
+    p2 = out2["path"].cpu().numpy()
+    for u in range(batch.B):
+        T = feats[u].shape[1]
+        assert np.array_equal(p2[offs[u]:offs[u + 1]], g["dec_paths"][u, g["labels"][u], :T])
+    with pytest.raises(IndexError):
+        m.viterbi(batch, None, eng.FP64, 10 ** 6)
+
+
+@pytest.mark.parametrize("T", [2, 5, 8, 9, 10])
+def test_viterbi_short_utterances(eng, edge, T):
+    """T <= N: the exit state is never reachable -> score -inf, path = zeros + [S-1] (custom_hmm.py:505-512)."""
+    x = edge[f"T{T}_x"].astype(np.float64).T
+    m = eng.WordModels(2, 8, 13)
+    m.set(edge["means"], edge["var"], edge["A"])
+    batch = eng.PackedBatch.from_features([x])
+    for P in (eng.FP64, eng.FP32):
+        out = m.viterbi(batch, None, P, 0, want_scores=True, want_path=True, all_paths=True)
+        assert np.array_equal(out["all_paths"].cpu().numpy()[0], edge[f"T{T}_dec_path"])
+        assert_close(out["scores"].cpu().numpy()[0, 0], edge[f"T{T}_dec_score"], 1e-12 if P == eng.FP64 else 1e-6, what="score")
+
+
+@pytest.mark.parametrize("name", ["rung1_d39", "rung1_d13"])
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_estep_vs_reference(eng, name, prec, request):
+    import torch
+    g = request.getfixturevalue(name)
+    feats = split_features(g)
+    m = _models(eng, g)
+    batch = eng.PackedBatch.from_features(feats)
+    lab = torch.as_tensor(g["labels"].astype(np.int32), device="cuda")
+    P = eng.FP64 if prec == "fp64" else eng.FP32
+    for order in (None, eng.group_by_model(lab)):
+        stats, ll, gamma = m.estep(batch, lab, order, P, want_gamma=True)
+        st = m.unpack_stats(stats)
+        rl, ra = (1e-12, 1e-10) if prec == "fp64" else (1e-6, 1e-5)
+        assert_close(ll.cpu().numpy(), g["es_loglik"], rl, what="loglik")
+        assert_close(gamma.cpu().numpy(), g["es_gamma"][:, 1:-1], 0, ra, what="gamma")
+        S = m.S
+        emit = (np.arange(S) > 0) & (np.arange(S) < S - 1)
+        for w in range(m.M):
+            sel = g["labels"] == w
+            n = max(1, int(sel.sum()))
+            assert_close(st["G"][w], g["es_G"][sel].sum(0) * emit, 0, ra * 50 * n, what="G")
+            assert_close(st["Xi"][w], g["es_xi_self"][sel].sum(0) * emit, 0, ra * 50 * n, what="Xi")
+            assert_close(st["occ"][w], g["es_occ"][sel].sum(0) * emit, 0, ra * 50 * n, what="occ")
+        # feature sums against the oracle's batched leg (same pivot = current mean)
+        X, offs = orc.pack(feats)
+        ost, _ = orc.estep_batch(X, offs, g["labels"], g["A"], g["means"], g["var"])
+        D = m.D
+        o1 = ost[:, 3 * S:3 * S + S * D].reshape(m.M, S, D); o2 = ost[:, 3 * S + S * D:].reshape(m.M, S, D)
+        scale = np.sqrt(g["var"])                       # per-dim sigma: sums scale with it
+        tol = 1e-9 if prec == "fp64" else 2e-4
+        assert np.max(np.abs(st["s1"] - o1) / scale) < tol * 60
+        assert np.max(np.abs(st["s2"] - o2) / scale ** 2) < tol * 60 * 10
+
+
+@pytest.mark.parametrize("name", ["rung1_d39", "rung1_d13"])
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_mstep_vs_reference_baum_welch_iteration(eng, name, prec, request):
+    """One E-step + M-step for all words at once == the reference's baum_welch(max_iter=1) per word
+    (Rung-1 ladder): A, means and the DIAGONAL of the reference's full covariances."""
+    import torch
+    g = request.getfixturevalue(name)
+    feats = split_features(g)
+    m = _models(eng, g)
+    batch = eng.PackedBatch.from_features(feats)
+    lab = torch.as_tensor(g["labels"].astype(np.int32), device="cuda")
+    floor_v = 0.001 * float(np.mean(np.diag(g["global_cov"])))
+    hist = eng.train_words(m, batch, lab, 1, floor_v, eng.FP64 if prec == "fp64" else eng.FP32)
+    means, var, A, _ = m.get()
+    rt = 1e-10 if prec == "fp64" else 1e-5
+    assert_close(hist[0], g["bw1_hist"], 1e-12 if prec == "fp64" else 1e-6, what="hist")
+    assert_close(A, g["bw1_A"], rt, atol=rt, what="A")
+    sig = np.sqrt(g["var"])
+    assert np.max(np.abs(means - g["bw1_mean"]) / sig) < (1e-9 if prec == "fp64" else 1e-4), "means"
+    ref_var = np.diagonal(g["bw1_cov"], axis1=2, axis2=3)
+    emit = slice(1, m.S - 1)
+    assert np.max(np.abs(var[:, emit] - ref_var[:, emit]) / g["var"][:, emit]) < (1e-8 if prec == "fp64" else 1e-3), "variances"
+    assert np.all(var[:, 0] == 0) and np.all(var[:, -1] == 0) and np.all(means[:, 0] == 0)
+
+
+def test_moderate_batch_against_oracle(eng):
+    """2048 ragged utterances x 11 models (seconds on the oracle): words/paths bit-exact in float64,
+    near-tie accounting in fp32; E-step statistics; host-buffer call equals the device call."""
+    import torch
+    from sapr_b200 import synth
+    feats, labels, mu, sd = synth.make_corpus(2048, 11, 8, 39, 60, 90, seed=7)
+    A, means, var = synth.truth_models(mu, sd, 0.9)
+    m = eng.WordModels(11, 8, 39)
+    m.set(means, var, A)
+    batch = eng.PackedBatch.from_features(feats)
+    X, offs = orc.pack(feats)
+    bw, bs, sc, bp = orc.viterbi_batch(X, offs, A, means, var)
+    o64 = m.viterbi(batch, None, eng.FP64, 0, want_scores=True)
+    assert np.array_equal(o64["best_word"].cpu().numpy(), bw)
+    assert np.array_equal(o64["path"].cpu().numpy().astype(np.int32), bp)
+    assert_close(o64["scores"].cpu().numpy(), sc, 1e-12, what="scores64")
+    o32 = m.viterbi(batch, None, eng.FP32, 0, want_scores=True)
+    assert_close(o32["scores"].cpu().numpy(), sc, 1e-6, what="scores32")
+    w32 = o32["best_word"].cpu().numpy()
+    bad = np.nonzero(w32 != bw)[0]
+    for u in bad:   # a different word is only acceptable on a float64 near-tie between the two words
+        assert abs(sc[u, w32[u]] - sc[u, bw[u]]) < 1e-5 * abs(sc[u, bw[u]]), u
+    assert len(bad) <= 2
+    pm = np.mean(o32["path"].cpu().numpy().astype(np.int32) == bp)
+    assert pm > 0.9995, f"fp32 path agreement {pm}"
+    # host-buffer entry: same answers
+    Xh, offh = synth.pack_frame_major(feats)
+    oh = m.viterbi_host(Xh, offh, eng.FP32, 0, chunk_utts=500)
+    assert np.array_equal(oh["best_word"], w32)
+    assert np.array_equal(oh["path"], o32["path"].cpu().numpy())
+    assert np.array_equal(oh["best_score"], o32["best_score"].cpu().numpy())
+    # E-step
+    lab = torch.as_tensor(labels, device="cuda")
+    ost, oll = orc.estep_batch(X, offs, labels, A, means, var)
+    for P, rl, ra in ((eng.FP64, 1e-12, 1e-9), (eng.FP32, 1e-6, 3e-5)):
+        stats, ll, _ = m.estep(batch, lab, None, P)
+        assert_close(ll.cpu().numpy(), oll, rl, what="loglik")
+        st = stats.cpu().numpy()
+        S = 10
+        occ = ost[:, 2 * S:3 * S]
+        assert np.max(np.abs(st[:, :3 * S] - ost[:, :3 * S])) < ra * 200 * 10
+        d1 = np.abs(st[:, 3 * S:] - ost[:, 3 * S:])
+        assert np.max(d1) < ra * 200 * 50
+    # 1-vs-2 shard equality of the reduced statistics (what the NCCL all-reduce sums)
+    from sapr_b200.dist import shard_bounds
+    tot = None
+    for (a, b) in shard_bounds(offh, 2):
+        sub = eng.PackedBatch.from_features(feats[a:b])
+        s, _, _ = m.estep(sub, torch.as_tensor(labels[a:b], device="cuda"), None, eng.FP64)
+        tot = s if tot is None else tot + s
+    full, _, _ = m.estep(batch, lab, None, eng.FP64)
+    assert_close(tot.cpu().numpy(), full.cpu().numpy(), 1e-12, atol=1e-9, what="sharded stats")
+
+
+def test_launch_counter_and_errors(eng):
+    from sapr_b200 import _lib
+    ctx = _lib.default_context()
+    n0 = ctx.launches()
+    m = eng.WordModels(1, 8, 13)
+    with pytest.raises(_lib.SaprError):
+        m.viterbi(eng.PackedBatch.from_features([np.zeros((13, 20), dtype=np.float32)]))   # parameters not set
+    assert ctx.launches() >= n0
+    with pytest.raises(_lib.SaprError):
+        eng.WordModels(1, 0, 13)

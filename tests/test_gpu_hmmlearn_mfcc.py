@@ -1,0 +1,112 @@
+"""hmmlearn-style class and the MFCC kernel against the CPU oracle restatements (both PARITY UNPINNED by
+the reference: hmmlearn / librosa are not vendored and cannot be installed here)."""
+import numpy as np
+import pytest
+
+from conftest import assert_close, split_features
+from oracle import oracle as orc
+from oracle import mfcc_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _setup(g, w=0):
+    from sapr_b200.hmmlearn_hmm import GaussianHMM
+    feats = [f for f, l in zip(split_features(g), g["labels"]) if l == w]
+    S = 10
+    rng = np.random.default_rng(3)
+    means = g["means"][w].copy()
+    means[0] = means[1] + 0.1 * rng.standard_normal(means.shape[1])
+    means[-1] = means[-2] + 0.1 * rng.standard_normal(means.shape[1])
+    var = g["var"][w].copy()
+    var[0] = var[1]; var[-1] = var[-2]
+    tm = g["A"][w].copy()
+    sp = np.zeros(S); sp[0] = 1.0
+    model = GaussianHMM(n_components=S, covariance_type="diag", n_iter=3, params="stmc", implementation="log",
+                        min_covar=0.01, init_params="")
+    model.means_, model.covars_, model.transmat_, model.startprob_ = means, var, tm, sp
+    X = np.concatenate([f.T for f in feats], axis=0)
+    lengths = [f.shape[1] for f in feats]
+    return model, X, lengths, (means, var, tm, sp)
+
+
+def test_score_decode_vs_oracle(cuda, rung1_d13):
+    model, X, lengths, (means, var, tm, sp) = _setup(rung1_d13)
+    offs = np.concatenate([[0], np.cumsum(lengths)])
+    tot, tot_v, paths = 0.0, 0.0, []
+    for a, b in zip(offs[:-1], offs[1:]):
+        lf = orc.emission_diag(X[a:b].T, means, var, all_emit=True)
+        tot += orc.hl_forward(lf, sp, tm)[0]
+        lp, p = orc.hl_viterbi(lf, sp, tm)
+        tot_v += lp; paths.append(p)
+    assert abs(model.score(X, lengths) - tot) <= 1e-10 * abs(tot)
+    lp, path = model.decode(X, lengths)
+    assert abs(lp - tot_v) <= 1e-10 * abs(tot_v)
+    assert np.array_equal(path, np.concatenate(paths))
+    assert np.array_equal(model.predict(X, lengths), path)
+    assert model.covars_.shape == (10, 13, 13)      # hmmlearn getter expands 'diag' to full matrices
+
+
+def test_fit_vs_oracle(cuda, rung1_d13):
+    model, X, lengths, (means, var, tm, sp) = _setup(rung1_d13, w=2)
+    offs = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+    hist = []
+    for _ in range(3):
+        st = orc.hl_estep(X, offs, sp, tm, means, var)
+        hist.append(st["logprob"])
+        sp, tm, means, var = orc.hl_mstep(st, sp, tm)
+    model.tol = -np.inf                        # run all three iterations
+    model.fit(X, lengths)
+    assert_close(np.array(model.monitor_.history), np.array(hist), 1e-10, what="history")
+    assert_close(model.means_, means, 1e-9, what="means")
+    assert_close(model._covars, var, 1e-8, what="covars")
+    assert_close(model.transmat_, tm, 1e-9, atol=1e-12, what="transmat")
+    assert_close(model.startprob_, sp, 1e-12, what="startprob")
+
+
+def test_hmmlearn_wrapper(cuda):
+    from sapr_b200 import synth
+    from sapr_b200.hmmlearn_hmm import HMMLearnModel
+    feats, labels, _, _ = synth.make_corpus(22, 11, 8, 13, 40, 60, seed=11)
+    w = HMMLearnModel(num_states=8, model_name="heed", n_iter=2, feature_set=feats)
+    X = np.concatenate([f.T for f in feats], axis=0)
+    assert_close(w.global_mean, X.mean(axis=0), 1e-10, what="global mean")
+    assert_close(w.global_cov, X.astype(np.float64).var(axis=0), 1e-9, what="global var")
+    model, ll = w.fit([f for f, l in zip(feats, labels) if l == 0])
+    assert np.isfinite(ll) and len(model.monitor_.history) == 2
+
+
+@pytest.mark.parametrize("which", ["librosa", "cfg5"])
+def test_mfcc_vs_oracle(cuda, which):
+    from sapr_b200 import mfcc_extract as mx
+    rng = np.random.default_rng(0)
+    sr = 22050 if which == "librosa" else 16000
+    p = mx.librosa_params(sr) if which == "librosa" else mx.cfg5_params()
+    sigs = []
+    for n in (sr, int(0.37 * sr), 5000):
+        t = np.arange(n) / sr
+        y = sum(a * np.sin(2 * np.pi * f * t + ph) for a, f, ph in zip((0.5, 0.3, 0.2), rng.uniform(200, 3000, 3), rng.uniform(0, 6, 3)))
+        sigs.append((y + 0.01 * rng.standard_normal(n)).astype(np.float32))
+    audio = cuda.as_tensor(np.concatenate(sigs), device="cuda")
+    so = np.concatenate([[0], np.cumsum([len(s) for s in sigs])]).astype(np.int64)
+    feats, fo = mx.mfcc_batch(audio, so, p)
+    F = feats.cpu().numpy()
+    for u, y in enumerate(sigs):
+        ref = mfcc_oracle.mfcc(y, p.sample_rate, p.n_fft, p.win_length, p.hop_length, p.n_mels, p.n_mfcc, p.center,
+                               p.mel_slaney, p.log_db, p.top_db, p.preemph, p.fmin, p.fmax)
+        got = F[fo[u]:fo[u + 1], :p.n_mfcc].T
+        assert got.shape == ref.shape
+        if which == "librosa":
+            assert ref.shape == (13, 1 + len(y) // 220)          # tests/test_mfcc_extract.py:31-34 + Appendix C
+        # fp32 FFT/log vs float64: absolute tolerance on dB/log-scaled cepstra
+        assert np.max(np.abs(got - ref)) < (5e-2 if which == "librosa" else 5e-3), np.max(np.abs(got - ref))
+    one = mx.mfcc_from_samples(sigs[0], sr, p)
+    assert one.shape[0] == 13 and one.dtype == np.float32
