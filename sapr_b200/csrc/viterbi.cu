@@ -180,16 +180,18 @@ __global__ void k_viterbi_finish(const int64_t *__restrict__ offsets, int u0, in
     }
     if (best_word) best_word[u] = (bslot < 0) ? -1 : (model_of_utt ? model_of_utt[u] : bslot);
     if (best_score) best_score[u] = bs;
+    const int wslot = bslot < 0 ? 0 : bslot;
     for (int s = 0; s < nslots; s++) {
-        uint8_t *out = nullptr;
-        if (all_paths) out = all_paths + (size_t)s * total_frames + off;
-        else if (best_path && s == (bslot < 0 ? 0 : bslot)) out = best_path + off;
+        uint8_t *out = all_paths ? all_paths + (size_t)s * total_frames + off : nullptr;
+        uint8_t *out2 = (best_path && s == wslot) ? best_path + off : nullptr;
+        if (!out) { out = out2; out2 = nullptr; }
         if (!out) continue;
         const bool reachable = scores[(size_t)ul * nslots + s] != -INFINITY;
         const BP *bpp = bp + ((size_t)s * maxT) * Bpad + ul;
         int cur = S - 1;
         for (int t = Te - 1; t >= 0; t--) {
             out[t] = (uint8_t)cur;
+            if (out2) out2[t] = (uint8_t)cur;
             if (!reachable) { cur = 0; continue; }     // unreachable cell: backpointer stays 0 (:470)
             if (t == 0) break;
             unsigned bits = (unsigned)bpp[(size_t)t * Bpad];

@@ -78,7 +78,7 @@ def test_hmmlearn_wrapper(cuda):
     feats, labels, _, _ = synth.make_corpus(22, 11, 8, 13, 40, 60, seed=11)
     w = HMMLearnModel(num_states=8, model_name="heed", n_iter=2, feature_set=feats)
     X = np.concatenate([f.T for f in feats], axis=0)
-    assert_close(w.global_mean, X.mean(axis=0), 1e-10, what="global mean")
+    assert_close(w.global_mean, X.astype(np.float64).mean(axis=0), 1e-10, what="global mean")
     assert_close(w.global_cov, X.astype(np.float64).var(axis=0), 1e-9, what="global var")
     model, ll = w.fit([f for f, l in zip(feats, labels) if l == 0])
     assert np.isfinite(ll) and len(model.monitor_.history) == 2
