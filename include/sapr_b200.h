@@ -42,6 +42,7 @@ extern "C" {
 /* precision of the fused kernels */
 #define SAPR_FP32 0           /* production: fp32 emission + per-frame renormalised fp32 recursions */
 #define SAPR_FP64 1           /* verification: float64 end to end, same summation order as the oracle */
+#define SAPR_FP32_SIMT 2      /* fp32 with the SIMT emission forced (A/B against the tensor-core emission) */
 
 /* emission model */
 #define SAPR_EMIT_DIAG 0      /* true diagonal Gaussian (north_star; hmmlearn "diag") */
@@ -97,6 +98,12 @@ int sapr_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const i
                  int64_t total_frames, int max_T, const int32_t *model_of_utt, int precision,
                  int first_frames, int32_t *best_word, double *best_score, double *scores,
                  uint8_t *best_path, uint8_t *all_paths);
+
+/* Parity/debug: the tensor-core emission tile of the fused Viterbi kernel written out, E_out float32
+ * [sum_T][*ncols_out], column m*8 + (j-1) = state j of model m (compute_emission_matrix, custom_hmm.py:146-174,
+ * for all models at once).  Only for model sets the tensor-core path accepts (N == 8, M <= 12, D < 64). */
+int sapr_debug_tc_emission(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int B,
+                           int64_t total_frames, int max_T, float *E_out, int *ncols_out);
 
 /* Same call with HOST buffers: features are staged through pinned memory and streamed to the GPU in
  * utterance chunks (copy/compute overlap), results come back to host arrays.  This is the call a

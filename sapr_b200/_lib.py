@@ -13,7 +13,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libsaprb200.so")
 
-FP32, FP64 = 0, 1
+FP32, FP64, FP32_SIMT = 0, 1, 2
 EMIT_DIAG, EMIT_SAPR = 0, 1
 TOPO_ENTRY_EXIT, TOPO_DENSE = 0, 1
 E_SHORT = -5
@@ -44,6 +44,7 @@ SIGNATURES = {
     "sapr_models_get": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "sapr_init_stats": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp]),
     "sapr_viterbi": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "sapr_debug_tc_emission": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _i64, _i32, _vp, C.POINTER(_i32)]),
     "sapr_viterbi_host": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "sapr_stats_stride": (_i64, [_i32, _i32]),
     "sapr_estep": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),

@@ -138,6 +138,11 @@ extern "C" int sapr_models_create(sapr_ctx *ctx, int M, int N, int D, int emissi
         rc |= dalloc(ctx, &m->P, (size_t)M * S * D * D);
         rc |= dalloc(ctx, &m->cstS, (size_t)M * S);
     }
+    if (!rc && sapr_tc_eligible(m)) {
+        unsigned char *img = nullptr;
+        rc |= dalloc(ctx, &img, sapr_tc_image_bytes(m, nullptr, nullptr));
+        m->tc_image = img;
+    }
     if (rc) { sapr_models_destroy(m); return SAPR_E_CUDA; }
     *out = m;
     return SAPR_OK;
@@ -147,7 +152,7 @@ extern "C" int sapr_models_destroy(sapr_models *m) {
     if (!m) return SAPR_OK;
     cudaStreamSynchronize(m->ctx->stream);
     void *ptrs[] = {m->mean, m->cov, m->A, m->pi, m->logA, m->logpi, m->la64, m->lb64, m->la32, m->lb32,
-                    m->pk64, m->pk32, m->cst64, m->cst32, m->P, m->cstS};
+                    m->pk64, m->pk32, m->cst64, m->cst32, m->P, m->cstS, m->tc_image};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete m;
     return SAPR_OK;
@@ -287,6 +292,10 @@ int sapr_models_prepare(sapr_models *m) {
         k_prepare_diag<<<(M * m->n_emit + 63) / 64, 64, 0, ctx->stream>>>(M, S, D, m->Dp, m->n_emit, first, m->mean,
                                                                           m->cov, m->pk64, m->pk32, m->cst64, m->cst32);
         SAPR_LAUNCH_CHECK(ctx);
+        if (m->tc_image) {
+            int rc = sapr_tc_prepare(m);
+            if (rc) return rc;
+        }
     } else {
         int rc = sapr_ws_reserve(ctx, 6, sizeof(double) * (size_t)M * S * D * D);
         if (rc) return rc;

@@ -82,6 +82,9 @@ struct sapr_models {
     // SAPR emission: P = inv(cov + 1e-6 I) [M][S][D][D], cstS = -0.5 (D ln 2pi + logdet) [M][S]
     double *P = nullptr;
     double *cstS = nullptr;
+    // tensor-core Viterbi image (viterbi_tc.cu): fp16 hi/lo weights in shared-memory layout + (g, s) + transitions
+    void *tc_image = nullptr;
+    int tc_ctas_per_sm = 1;
     bool valid = false;
 };
 
@@ -114,6 +117,12 @@ int sapr_ws_reserve(sapr_ctx *ctx, int slot, size_t bytes);   // grows ctx->ws[s
 int sapr_pin_reserve(sapr_ctx *ctx, int slot, size_t bytes);  // grows ctx->pin[slot]
 int sapr_models_prepare(sapr_models *m);                      // recompute the derived arrays on device
 // float64 emission matrix E[total_frames][S] of model mi for a batch (DIAG or SAPR emission)
+bool sapr_tc_eligible(const sapr_models *m);
+size_t sapr_tc_image_bytes(const sapr_models *m, int *nck_out, int *ncols_out);
+int sapr_tc_prepare(sapr_models *m);
+int sapr_viterbi_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int B,
+                           int64_t total_frames, int max_T, int first_frames, int32_t *best_word, double *best_score,
+                           double *scores, uint8_t *best_path, uint8_t *all_paths, float *dbgE);
 int sapr_emission_into(sapr_ctx *ctx, sapr_models *m, int mi, const float *X, int ldx, const int64_t *offsets, int B,
                        int64_t total_frames, double *E);
 

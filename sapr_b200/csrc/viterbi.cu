@@ -10,6 +10,8 @@
 // M-1 of the M reads hit L1).  Back-pointers are one bit per (frame, state) -- "advanced from j-1" vs
 // "stayed in j" -- packed in one word per frame and kept in an L2-resident scratch laid out
 // [model][frame][utterance] so each warp store is one coalesced line.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 template <typename R> struct alignas(16) Vec4 { R x, y, z, w; };
@@ -201,6 +203,20 @@ __global__ void k_viterbi_finish(const int64_t *__restrict__ offsets, int u0, in
     }
 }
 
+int sapr_viterbi_finish_u16(sapr_ctx *ctx, const int64_t *offsets, int u0, int nu, int N, int nslots, int first_frames,
+                            const uint16_t *bp, int64_t Bpad, int maxT, const double *scores, int32_t *best_word,
+                            double *best_score, double *scores_out, int M, uint8_t *best_path, uint8_t *all_paths,
+                            int64_t total_frames) {
+    {
+        ProfScope ps(ctx, 1);
+        k_viterbi_finish<uint16_t><<<(nu + 127) / 128, 128, 0, ctx->stream>>>(offsets, u0, nu, N, nslots, nullptr, first_frames, bp,
+                                                                              Bpad, maxT, scores, best_word, best_score,
+                                                                              scores_out, M, best_path, all_paths, total_frames);
+    }
+    SAPR_LAUNCH_CHECK(ctx);
+    return SAPR_OK;
+}
+
 template <typename R, typename BP, int NMAX>
 static int launch_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int B,
                           int64_t total_frames, int max_T, const int32_t *model_of_utt, int first_frames,
@@ -251,6 +267,19 @@ static int launch_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx
     return SAPR_OK;
 }
 
+// debug / parity entry: the tensor-core emission tile written out as E[sum_T][ncols] float32
+// (ncols = M*8 rounded up to 16; column m*8 + j-1 = state j of model m) -- compute_emission_matrix, custom_hmm.py:146-174
+extern "C" int sapr_debug_tc_emission(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int B,
+                                      int64_t total_frames, int max_T, float *E_out, int *ncols_out) {
+    if (!ctx || !m || !X || !offsets || !E_out) return SAPR_E_INVALID;
+    if (!m->valid || !m->tc_image || !sapr_tc_eligible(m)) SAPR_FAIL(ctx, SAPR_E_RANGE, "tc emission: model set not eligible");
+    int ncols = 0;
+    sapr_tc_image_bytes(m, nullptr, &ncols);
+    if (ncols_out) *ncols_out = ncols;
+    return sapr_viterbi_tc_launch(ctx, m, X, ldx, offsets, B, total_frames, max_T, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                  E_out);
+}
+
 extern "C" int sapr_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int B,
                             int64_t total_frames, int max_T, const int32_t *model_of_utt, int precision,
                             int first_frames, int32_t *best_word, double *best_score, double *scores,
@@ -265,7 +294,13 @@ extern "C" int sapr_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int l
 #define GO(R, BP, NM)                                                                                       \
     return launch_viterbi<R, BP, NM>(ctx, m, X, ldx, offsets, B, total_frames, max_T, model_of_utt,        \
                                      first_frames, best_word, best_score, scores, best_path, all_paths)
-    if (precision == SAPR_FP32) {
+    if (precision == SAPR_FP32 && !model_of_utt && m->tc_image && sapr_tc_eligible(m)) {
+        const char *env = getenv("SAPR_TC");
+        if (!env || env[0] != '0')
+            return sapr_viterbi_tc_launch(ctx, m, X, ldx, offsets, B, total_frames, max_T, first_frames, best_word, best_score,
+                                          scores, best_path, all_paths, nullptr);
+    }
+    if (precision == SAPR_FP32 || precision == SAPR_FP32_SIMT) {
         if (m->N <= 8) GO(float, uint16_t, 8);
         if (m->N <= 15) GO(float, uint16_t, 15);
         if (m->N <= 31) GO(float, uint32_t, 31);

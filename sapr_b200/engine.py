@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import EMIT_DIAG, EMIT_SAPR, FP32, FP64, TOPO_DENSE, TOPO_ENTRY_EXIT, ptr
+from ._lib import EMIT_DIAG, EMIT_SAPR, FP32, FP32_SIMT, FP64, TOPO_DENSE, TOPO_ENTRY_EXIT, ptr
 
 
 def _torch():
@@ -125,6 +125,17 @@ class WordModels:
                                              batch.total_frames, batch.max_T, ptr(model_of_utt), precision, first_frames,
                                              ptr(best_word), ptr(best_score), ptr(scores), ptr(path), ptr(allp)))
         return dict(best_word=best_word, best_score=best_score, scores=scores, path=path, all_paths=allp)
+
+    def tc_emission(self, batch: PackedBatch):
+        """Debug/parity: the tensor-core emission tile, float32 [sum_T, ncols] (column m*8 + j-1)."""
+        torch = _torch()
+        ncols = (self.M * 8 + 15) // 16 * 16
+        E = torch.zeros((batch.total_frames, ncols), dtype=torch.float32, device=batch.X.device)
+        nc = C.c_int(0)
+        self.ctx.check(self.lib.sapr_debug_tc_emission(self.ctx.h, self.h, ptr(batch.X), batch.ldx, ptr(batch.offsets), batch.B,
+                                                       batch.total_frames, batch.max_T, ptr(E), C.byref(nc)))
+        assert nc.value == ncols
+        return E
 
     def viterbi_host(self, X_host, offsets_host, precision=FP32, first_frames=0, chunk_utts=8192, want_path=True,
                      out=None):

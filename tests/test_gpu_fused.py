@@ -41,14 +41,37 @@ def path_score(E, A, path):
     return s
 
 
+def _P(eng, prec):
+    return {"fp64": eng.FP64, "fp32": eng.FP32, "fp32_simt": eng.FP32_SIMT}[prec]
+
+
 @pytest.mark.parametrize("name", ["rung1_d39", "rung1_d13"])
-@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_tensor_core_emission_tile(eng, name, request):
+    """The tcgen05 emission (fp16 hi/lo split operands, fp32 TMEM accumulate) against the float64 oracle
+    emission of every model: absolute error of the log-density."""
+    g = request.getfixturevalue(name)
+    feats = split_features(g)
+    m = _models(eng, g)
+    batch = eng.PackedBatch.from_features(feats)
+    E = m.tc_emission(batch).cpu().numpy()
+    offs = batch.offsets_host
+    worst = 0.0
+    for u in range(batch.B):
+        for w in range(m.M):
+            ref = orc.emission_diag(feats[u], g["means"][w], g["var"][w])[:, 1:-1]
+            got = E[offs[u]:offs[u + 1], w * 8:(w + 1) * 8]
+            worst = max(worst, float(np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref) * 1e-3))))
+    assert worst < 2e-4, worst      # stated tolerance: 2e-4 absolute (or 2e-7 relative for |E| > 1000)
+
+
+@pytest.mark.parametrize("name", ["rung1_d39", "rung1_d13"])
+@pytest.mark.parametrize("prec", ["fp64", "fp32", "fp32_simt"])
 def test_viterbi_all_models_vs_reference(eng, name, prec, request):
     g = request.getfixturevalue(name)
     feats = split_features(g)
     m = _models(eng, g)
     batch = eng.PackedBatch.from_features(feats)
-    P = eng.FP64 if prec == "fp64" else eng.FP32
+    P = _P(eng, prec)
     out = m.viterbi(batch, None, P, 0, want_scores=True, want_path=True, all_paths=True)
     sc = out["scores"].cpu().numpy(); bw = out["best_word"].cpu().numpy()
     allp = out["all_paths"].cpu().numpy(); bp = out["path"].cpu().numpy()
@@ -67,7 +90,7 @@ def test_viterbi_all_models_vs_reference(eng, name, prec, request):
             ref = g["dec_paths"][u, w, :T].astype(np.int32)
             if np.array_equal(got, ref):
                 continue
-            assert prec == "fp32", f"float64 path differs for utt {u} model {w}"
+            assert prec != "fp64", f"float64 path differs for utt {u} model {w}"
             # documented near-tie policy: the fp32 path must score within 2e-3 of the optimum in float64
             E = orc.emission_diag(feats[u], g["means"][w], g["var"][w])
             assert abs(path_score(E, g["A"][w], got) - g["dec_scores"][u, w]) < 2e-3, (u, w)
@@ -111,10 +134,17 @@ def test_viterbi_short_utterances(eng, edge, T):
     m = eng.WordModels(2, 8, 13)
     m.set(edge["means"], edge["var"], edge["A"])
     batch = eng.PackedBatch.from_features([x])
-    for P in (eng.FP64, eng.FP32):
+    for P in (eng.FP64, eng.FP32, eng.FP32_SIMT):
         out = m.viterbi(batch, None, P, 0, want_scores=True, want_path=True, all_paths=True)
         assert np.array_equal(out["all_paths"].cpu().numpy()[0], edge[f"T{T}_dec_path"])
         assert_close(out["scores"].cpu().numpy()[0, 0], edge[f"T{T}_dec_score"], 1e-12 if P == eng.FP64 else 1e-6, what="score")
+    # ragged tile: the same short utterance next to longer ones in one 128-row tensor-core tile
+    long_x = np.tile(x, (1, 20))[:, :37]
+    b2 = eng.PackedBatch.from_features([long_x, x, long_x[:, :21]])
+    o_tc = m.viterbi(b2, None, eng.FP32, 0, want_scores=True, all_paths=True)
+    o_64 = m.viterbi(b2, None, eng.FP64, 0, want_scores=True, all_paths=True)
+    assert_close(o_tc["scores"].cpu().numpy(), o_64["scores"].cpu().numpy(), 1e-6, what="ragged scores")
+    assert np.array_equal(o_tc["all_paths"].cpu().numpy()[0, 37:37 + T], edge[f"T{T}_dec_path"])
 
 
 @pytest.mark.parametrize("name", ["rung1_d39", "rung1_d13"])
@@ -193,15 +223,16 @@ def test_moderate_batch_against_oracle(eng):
     assert np.array_equal(o64["best_word"].cpu().numpy(), bw)
     assert np.array_equal(o64["path"].cpu().numpy().astype(np.int32), bp)
     assert_close(o64["scores"].cpu().numpy(), sc, 1e-12, what="scores64")
-    o32 = m.viterbi(batch, None, eng.FP32, 0, want_scores=True)
-    assert_close(o32["scores"].cpu().numpy(), sc, 1e-6, what="scores32")
-    w32 = o32["best_word"].cpu().numpy()
-    bad = np.nonzero(w32 != bw)[0]
-    for u in bad:   # a different word is only acceptable on a float64 near-tie between the two words
-        assert abs(sc[u, w32[u]] - sc[u, bw[u]]) < 1e-5 * abs(sc[u, bw[u]]), u
-    assert len(bad) <= 2
-    pm = np.mean(o32["path"].cpu().numpy().astype(np.int32) == bp)
-    assert pm > 0.9995, f"fp32 path agreement {pm}"
+    for P in (eng.FP32_SIMT, eng.FP32):          # SIMT emission, then the tensor-core emission (kept as o32)
+        o32 = m.viterbi(batch, None, P, 0, want_scores=True)
+        assert_close(o32["scores"].cpu().numpy(), sc, 1e-6, what="scores32")
+        w32 = o32["best_word"].cpu().numpy()
+        bad = np.nonzero(w32 != bw)[0]
+        for u in bad:   # a different word is only acceptable on a float64 near-tie between the two words
+            assert abs(sc[u, w32[u]] - sc[u, bw[u]]) < 1e-5 * abs(sc[u, bw[u]]), u
+        assert len(bad) <= 2
+        pm = np.mean(o32["path"].cpu().numpy().astype(np.int32) == bp)
+        assert pm > 0.9995, f"fp32 path agreement {pm}"
     # host-buffer entry: same answers
     Xh, offh = synth.pack_frame_major(feats)
     oh = m.viterbi_host(Xh, offh, eng.FP32, 0, chunk_utts=500)
