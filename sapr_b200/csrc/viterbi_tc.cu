@@ -3,28 +3,39 @@
 // Same contract as k_viterbi_fused (custom_hmm.py:462-514 x all models + decoder.py:42-47), different
 // machine mapping.  The emission of one frame against all M*8 states is the dense contraction
 //      E[r, n] = sum_k A[r, k] * W[n, k],   A[r, :] = [x', x'^2, 1] of utterance r at frame t,
-// where x' = (x - g) * s is the feature standardised by a per-dimension centre/scale derived from the
-// model set (keeps the expanded quadratic well conditioned) and W[n, :] = [2 mu' h', -h', c - sum mu'^2 h'].
+// where x' = x * s + b is the feature standardised by a per-dimension centre/scale derived from the model
+// set (keeps the expanded quadratic well conditioned) and W[n, :] = [2 mu' h', -h', c - sum mu'^2 h' + ln a_nn].
 // One MMA tile = 128 utterances AT THE SAME FRAME INDEX: tcgen05.mma writes row r to TMEM lane r, and
-// tcgen05.ld.32x32b hands thread r exactly the emissions of ITS utterance -- no transposition between the
-// tensor-core tile and the register-resident left-to-right recursion.
+// tcgen05.ld.32x32b hands the threads of row r exactly the emissions of THEIR utterance -- no transposition
+// between the tensor-core tile and the register-resident left-to-right recursion.
 //
-// Precision: operands are fp16 hi/lo splits (x' = hi + lo exactly to 22 bits, likewise W); the three products
-// hi*Whi + lo*Whi + hi*Wlo are one K = 3*Kh accumulation chain in fp32 TMEM (Kh = 80 for D = 39): emission
-// error ~1e-5 absolute, the same class as the fp32 SIMT kernel.
+// Data movement (per CTA = one SM, persistent over 128-utterance tiles):
+//   HBM --cp.async.bulk (one copy per utterance: F consecutive frames, contiguous)--> shared-memory ring
+//   shared --LDS.128 (row r, conflict-free padded stride)--> registers: standardise, square, fp16 hi/lo split
+//   registers --tcgen05.st--> TMEM: the A operand lives in tensor memory (row r = lane r), never in shared memory
+//   tcgen05.mma (A from TMEM, W from shared memory, fp32 accumulators in TMEM, double buffered)
+//   TMEM --tcgen05.ld--> registers: max-product recursion, 1-bit back-pointers --> HBM scratch
 //
-// CTA = 9 warps: warps 0-7 are workers (thread = (row r, column group g): converts half of row r's next
-// frame into the A tile, then runs the recursion for its half of the models), warp 8 issues the MMAs.
-// Pipeline per frame f (stage = f & 1):  workers write A[f+1] -> mbarrier A_full -> MMA warp issues
-// 3*nck/2 tcgen05.mma into TMEM buffer (f+1)&1 -> tcgen05.commit -> mbarrier acc_full -> workers tcgen05.ld,
-// recursion, mbarrier acc_empty.  The MMAs of frame f+1 overlap the recursion of frame f.
+// Precision: operands are fp16 hi/lo splits (x' = hi + lo to 22 bits, likewise W); the three products
+// hi*Whi + lo*Whi + hi*Wlo are one K = 3*Kh accumulation chain in fp32 TMEM (Kh = 80 for D = 39).
+//
+// CTA = 18 warps: warps 0-15 are workers (thread = (row r, group g): converts a quarter of row r's next frame
+// into the A operand, then runs the recursion for a quarter of the models), warp 16 issues the MMAs, warp 17
+// issues the bulk copies.  Pipeline per frame f (stage = f & 1): workers write A[f+1] -> mbarrier A_full ->
+// MMA warp issues 3*nck/2 tcgen05.mma into accumulator (f+1)&1 -> tcgen05.commit -> mbarrier acc_full ->
+// workers tcgen05.ld, recursion, mbarrier acc_empty.  The MMAs of frame f+1 overlap the recursion of frame f.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
-#define TC_WORKERS 256
-#define TC_THREADS 288
 #define TC_ROWS 128
+#define TC_GROUPS 4
+#define TC_WORKERS (TC_ROWS * TC_GROUPS)
+#define TC_WORKER_WARPS (TC_WORKERS / 32)
+#define TC_LOADERS 3
+#define TC_THREADS (TC_WORKERS + 32 + 32 * TC_LOADERS)    /* + MMA warp + bulk-copy warps */
+#define TC_MAX_STAGES 4
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -36,22 +47,47 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
 }
-// bounded wait: a protocol bug traps (error to the host) instead of hanging the GPU
+__device__ __forceinline__ void mbar_arrive_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+// bounded wait: a protocol bug traps (error to the host) instead of hanging the GPU.  try_wait suspends the
+// thread in hardware up to the time hint, so a waiting warp costs almost no issue slots.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t spin = 0; !done; spin++) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1u << 26)) __trap();
-    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.gt.u32 p, n, 4000000;\n\t"
+        "@p trap;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t}"
+        ::"r"(bar), "r"(parity), "r"(2000u) : "memory");
+}
+// keeps a per-thread constant in its register (stops the compiler from re-deriving it from %tid in the hot loop)
+__device__ __forceinline__ uint32_t pin_reg(uint32_t v) {
+    asm volatile("mov.u32 %0, %0;" : "+r"(v));
+    return v;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -63,13 +99,13 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::f16, fp32 accumulate
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem desc]^T, kind::f16, fp32 accumulate
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *v) {
@@ -78,6 +114,42 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *v) {
                  : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 issue two lanes per instruction)
+__device__ __forceinline__ unsigned long long f2_as_u64(float2 a) { return *reinterpret_cast<unsigned long long *>(&a); }
+__device__ __forceinline__ float2 u64_as_f2(unsigned long long a) { return *reinterpret_cast<float2 *>(&a); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)), "l"(f2_as_u64(c)));
+    return u64_as_f2(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
+    return u64_as_f2(d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
+    return u64_as_f2(d);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
+    return u64_as_f2(d);
+}
+// (lo16, hi16) = (fp16(a.x), fp16(a.y)), saturating to the largest finite half instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_h2(float2 a) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a.y), "f"(a.x));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t h) { return __half22float2(*reinterpret_cast<__half2 *>(&h)); }
 
 // K-major, no-swizzle ("interleave") shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // core matrix = 8 rows x 16 bytes stored contiguously (128 B); LBO = byte distance between the two core
@@ -92,16 +164,23 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 // ------------------------------------------------------------------------------------------------
-// model-set preparation: standardisation (g, s) and the fp16 hi/lo weight image in its shared-memory layout
-//   wimg[2][ncols/8][nck][8][8] halves  (hi plane, lo plane); n = m*8 + state, k = 2*dim (x') / 2*dim+1 (x'^2)
-//   gs[4*nck] float2 (g, s) for real dims;  trp[M][5] float4 transition block
+// model-set preparation: standardisation (s, b) and the fp16 hi/lo weight image in its shared-memory layout
+//   wimg[2][ncols/8][nck][8][8] halves (hi plane, lo plane); n = m*8 + state.  A chunk is 4 feature dims =
+//   8 K elements ordered [x'_0 .. x'_3, x'^2_0 .. x'^2_3] (so a packed pair of one kind is one TMEM column).
+//   Dim index D is the constant slot: x' = 1 there; its x' weight carries the constant and its (otherwise
+//   unused) x'^2 weight the part of the constant the fp16 hi/lo pair of the first cannot represent.
+//   sb[2][4*nck] float (scale s, offset b: x' = x*s + b);  trp[M][5] float4 transition block:
+//     [0] = (c1, c2, c3, c4)  [1] = (c5, c6, c7, cx)   c_j = ln A[j-1,j] - ln A[j-1,j-1] (advance minus stay),
+//                                                      cx = ln A[N,exit] - ln A[N,N]
+//     [2] = (ln A[exit,exit], ln A[0,1], 0, 0)   [3], [4] = stay_1 .. stay_8 = ln A[j,j] (folded into W's constant)
 __global__ void k_prepare_tc(int M, int S, int D, int nck, int ncols, const double *__restrict__ mean,
                              const double *__restrict__ var, const double *__restrict__ la, const double *__restrict__ lb,
-                             __half *__restrict__ wimg, float2 *__restrict__ gs, float4 *__restrict__ trp) {
-    extern __shared__ double s_gs[];   // [2][4*nck]
+                             __half *__restrict__ wimg, float *__restrict__ sb, float4 *__restrict__ trp) {
+    extern __shared__ double s_gs[];   // [2][4*nck]: effective centre g, scale s
     const int N = S - 2, nd = 4 * nck;
     for (int d = threadIdx.x; d < nd; d += blockDim.x) {
-        double g = 0.0, sc = 1.0;
+        double g = 0.0, sc = 0.0;
+        float sf = 0.f, bf = 0.f;
         if (d < D) {
             double sm = 0.0;
             for (int m = 0; m < M; m++) for (int j = 1; j <= N; j++) sm += mean[((size_t)m * S + j) * D + d];
@@ -114,10 +193,13 @@ __global__ void k_prepare_tc(int M, int S, int D, int nck, int ncols, const doub
                 }
             v /= (M * N);
             sc = (v > 0 && v < 1e300) ? 4.0 / sqrt(v) : 1.0;
-            g = (double)(float)g; sc = (double)(float)sc;   // the kernel standardises in fp32 with exactly these values
+            sf = (float)sc; bf = (float)(-g * sc);
+            sc = (double)sf; g = -(double)bf / sc;   // the kernel standardises in fp32 with exactly (sf, bf)
+        } else if (d == D) {
+            sf = 0.f; bf = 1.f;                       // constant slot: x' = 1
         }
         s_gs[d] = g; s_gs[nd + d] = sc;
-        gs[d] = make_float2((float)g, (float)sc);
+        sb[d] = sf; sb[nd + d] = bf;
     }
     __syncthreads();
     const size_t plane = (size_t)(ncols / 8) * nck * 64;
@@ -131,29 +213,34 @@ __global__ void k_prepare_tc(int M, int S, int D, int nck, int ncols, const doub
                 const double g = s_gs[d], sc = s_gs[nd + d];
                 const double hp = 0.5 / vr[d] / (sc * sc), mp = (mu[d] - g) * sc;
                 wx = 2.0 * mp * hp; wx2 = -hp;
-            } else if (d == D) {   // constant slot: A carries x' = 1 here
+            } else if (d == D) {   // constant slot: A carries x' = 1 and x'^2 = 1 here
                 double ld = 0.0, c2 = 0.0;
                 for (int q = 0; q < D; q++) {
                     const double g = s_gs[q], sc = s_gs[nd + q];
                     const double hp = 0.5 / vr[q] / (sc * sc), mp = (mu[q] - g) * sc;
                     ld += log(vr[q]); c2 += mp * mp * hp;
                 }
-                wx = -0.5 * (D * SAPR_LOG2PI + ld) - c2; wx2 = 0.0;
+                const double cst = -0.5 * (D * SAPR_LOG2PI + ld) - c2 + la[(size_t)m * S + j];   // + ln A[j,j]
+                const __half ch = __double2half(cst);
+                const double r1 = cst - (double)__half2float(ch);
+                const __half cl = __double2half(r1);
+                wx = cst; wx2 = r1 - (double)__half2float(cl);   // third-order piece of the constant
             }
         }
-        // element (n, k) of the image: group n/8, chunk k/8, row n%8, elem k%8; k = 2d, 2d+1
-        const size_t o = ((size_t)(n / 8) * nck + d / 4) * 64 + (size_t)(n % 8) * 8 + (d % 4) * 2;
+        // element (n, k) of the image: group n/8, chunk d/4, row n%8, elem (d%4) for x', 4 + (d%4) for x'^2
+        const size_t o = ((size_t)(n / 8) * nck + d / 4) * 64 + (size_t)(n % 8) * 8 + (d % 4);
         const __half hx = __double2half(wx), hx2 = __double2half(wx2);
-        wimg[o] = hx; wimg[o + 1] = hx2;
+        wimg[o] = hx; wimg[o + 4] = hx2;
         wimg[plane + o] = __double2half(wx - (double)__half2float(hx));
-        wimg[plane + o + 1] = __double2half(wx2 - (double)__half2float(hx2));
+        wimg[plane + o + 4] = __double2half(wx2 - (double)__half2float(hx2));
     }
     for (int m = threadIdx.x; m < M; m += blockDim.x) {
         const double *a = la + (size_t)m * S, *b = lb + (size_t)m * S;
-        // (stay_j, adv_j) pairs for states 1..8: adv_j = ln A[j-1, j] = lb[j-1], stay_j = ln A[j, j] = la[j]
         float v[20];
-        for (int j = 1; j <= 8; j++) { v[2 * (j - 1)] = (j <= N) ? (float)a[j] : -INFINITY; v[2 * (j - 1) + 1] = (j <= N) ? (float)b[j - 1] : -INFINITY; }
-        v[16] = (float)a[S - 1]; v[17] = (float)b[N]; v[18] = (float)b[0]; v[19] = 0.f;
+        for (int j = 1; j <= 7; j++) v[j - 1] = (j + 1 <= N) ? (float)(b[j] - a[j]) : -INFINITY;   // c_{j+1}: into state j+1
+        v[7] = (float)(b[N] - a[N]);                                                              // cx (N == 8)
+        v[8] = (float)a[S - 1]; v[9] = (float)b[0]; v[10] = 0.f; v[11] = 0.f;
+        for (int j = 1; j <= 8; j++) v[11 + j] = (j <= N) ? (float)a[j] : 0.f;
         for (int q = 0; q < 5; q++) trp[(size_t)m * 5 + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
 }
@@ -161,256 +248,434 @@ __global__ void k_prepare_tc(int M, int S, int D, int nck, int ncols, const doub
 // ------------------------------------------------------------------------------------------------
 struct TcParams {
     const float *X; int ldx; const int64_t *offsets; int u0, nu, M, D, nck, ncols, first_frames;
-    const __half *wimg; const float2 *gs; const float4 *trp;
+    const __half *wimg; const float *sb; const float4 *trp;
     uint16_t *bp; int64_t Bpad; int maxT; double *scores; float *dbgE;   // dbgE: [sum_T][ncols] or null
+    long long *trace;           // [TC_TRACE_ROLES][TC_TRACE_FRAMES][TC_TRACE_EVENTS] or null
+    int Fshift, nst_shift;      // raw ring: 2^Fshift frames per stage, 2^nst_shift stages
+    uint32_t rstride;           // bytes per row per stage (F * row bytes + pad, an odd multiple of 16)
 };
 
-template <int MG>
+struct TcSmem {   // byte offsets into dynamic shared memory
+    uint32_t w, raw, tr, sb, base, bar, total;
+};
+__host__ __device__ inline TcSmem tc_smem_layout(int M, int nck, int ncols, int nst, uint32_t rstride) {
+    TcSmem L;
+    L.w = 0;
+    L.raw = (uint32_t)2 * (ncols / 8) * nck * 128;
+    L.tr = L.raw + (uint32_t)nst * TC_ROWS * rstride;
+    L.sb = L.tr + (uint32_t)M * 5 * 16;
+    L.base = (L.sb + (uint32_t)8 * nck * 4 + 15u) & ~15u;            // float64 renormalisation offsets [3][TC_WORKERS]
+    L.bar = L.base + 3u * TC_WORKERS * 8u;
+    L.total = L.bar + (2 * TC_MAX_STAGES + 6) * 8 + 16;
+    return L;
+}
+
+// one frame of the max-product recursion of one model (custom_hmm.py:476-503) on U_j = V[t, j] + ln A[j, j]:
+//   U_j <- max(U_{j-1} + c_j, U_j) + e'_j,  e'_j = E[t, j] + ln A[j, j] straight from the tensor core.
+// Returns the 9 "advanced" bits (bit j-1 = state j took its predecessor j-1, bit 8 = the exit state took state N;
+// the first candidate wins ties, :488-497).  EARLY = frames 1..8: entry state alive at t == 1, exit closed for t < N.
+template <bool EARLY>
+__device__ __forceinline__ uint32_t vit_step(float2 (&U)[4], float &Ux, const float4 c03, const float4 c47, const float a_exit,
+                                             const float b0, const uint32_t (&ev)[8], int t) {
+    const float2 P01 = add2(U[0], make_float2(c03.x, c03.y));   // advance candidates P_j = U_j + c_{j+1}
+    const float2 P23 = add2(U[1], make_float2(c03.z, c03.w));
+    const float2 P45 = add2(U[2], make_float2(c47.x, c47.y));
+    const float2 P67 = add2(U[3], make_float2(c47.z, c47.w));   // P67.y feeds the exit state
+    const float xs = Ux + a_exit;                               // exit self-loop
+    uint32_t sb;                                                // "stayed" bits, exit first
+    float nx;
+    if (!EARLY || t >= 8) {                                     // exit opens at t >= N (custom_hmm.py:481-485)
+        sb = __float_as_uint(P67.y - xs) >> 31;
+        nx = fmaxf(P67.y, xs);
+    } else {
+        sb = 1; nx = -INFINITY;
+    }
+    sb = __funnelshift_l(__float_as_uint(P67.x - U[3].y), sb, 1);   // state 8
+    sb = __funnelshift_l(__float_as_uint(P45.y - U[3].x), sb, 1);
+    sb = __funnelshift_l(__float_as_uint(P45.x - U[2].y), sb, 1);
+    sb = __funnelshift_l(__float_as_uint(P23.y - U[2].x), sb, 1);
+    sb = __funnelshift_l(__float_as_uint(P23.x - U[1].y), sb, 1);
+    sb = __funnelshift_l(__float_as_uint(P01.y - U[1].x), sb, 1);
+    sb = __funnelshift_l(__float_as_uint(P01.x - U[0].y), sb, 1);   // state 2
+    float n0;
+    if (EARLY) {                                                    // state 1: the entry state is alive at t == 1 only
+        const float ent = (t == 1) ? b0 : -INFINITY;
+        sb = __funnelshift_l(__float_as_uint(ent - U[0].x), sb, 1);
+        n0 = fmaxf(ent, U[0].x);
+    } else {
+        sb = (sb << 1) | 1u;
+        n0 = U[0].x;
+    }
+    const float2 n01 = make_float2(n0, fmaxf(P01.x, U[0].y));
+    const float2 n23 = make_float2(fmaxf(P01.y, U[1].x), fmaxf(P23.x, U[1].y));
+    const float2 n45 = make_float2(fmaxf(P23.y, U[2].x), fmaxf(P45.x, U[2].y));
+    const float2 n67 = make_float2(fmaxf(P45.y, U[3].x), fmaxf(P67.x, U[3].y));
+    U[0] = add2(n01, make_float2(__uint_as_float(ev[0]), __uint_as_float(ev[1])));
+    U[1] = add2(n23, make_float2(__uint_as_float(ev[2]), __uint_as_float(ev[3])));
+    U[2] = add2(n45, make_float2(__uint_as_float(ev[4]), __uint_as_float(ev[5])));
+    U[3] = add2(n67, make_float2(__uint_as_float(ev[6]), __uint_as_float(ev[7])));
+    Ux = nx;
+    return (~sb) & 0x1FFu;
+}
+
+// renormalise (fp32 stays at O(1) magnitudes); the offset is accumulated in float64 in shared memory
+__device__ __forceinline__ void vit_renorm(float2 (&U)[4], float &Ux, uint32_t base_addr) {
+    float mx = fmaxf(fmaxf(U[0].x, U[0].y), Ux);
+    mx = fmaxf(fmaxf(U[1].x, U[1].y), mx);
+    mx = fmaxf(fmaxf(U[2].x, U[2].y), mx);
+    mx = fmaxf(fmaxf(U[3].x, U[3].y), mx);
+    if (mx > -INFINITY && mx < INFINITY) {
+        const float2 m2 = make_float2(mx, mx);
+        U[0] = sub2(U[0], m2);
+        U[1] = sub2(U[1], m2);
+        U[2] = sub2(U[2], m2);
+        U[3] = sub2(U[3], m2);
+        Ux -= mx;
+        double b;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b) : "r"(base_addr));
+        b += (double)mx;
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(base_addr), "d"(b) : "memory");
+    }
+}
+
+// TRACE: CTA 0 records clock64() at its pipeline events for the first TC_TRACE_FRAMES frames (tuning aid, SAPR_TC_TRACE=file)
+#define TC_TRACE_FRAMES 96
+#define TC_TRACE_EVENTS 6
+#define TC_TRACE_ROLES 5
+template <int MG, int NKS, bool DBG, bool TRACE = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int nck = p.nck, ncols = p.ncols, M = p.M;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // ---- shared memory carve-up ----
+    const int F = 1 << p.Fshift, nst = 1 << p.nst_shift;
+    const uint32_t rowbytes = (uint32_t)p.ldx * 4u, rstride = p.rstride, stage_bytes = TC_ROWS * rstride;
+    const TcSmem L = tc_smem_layout(M, nck, ncols, nst, rstride);
     const uint32_t w_plane = (uint32_t)(ncols / 8) * nck * 128;            // bytes per W plane
-    const uint32_t a_stage = 16u * 2u * nck * 128u;                         // 128 rows x (2*nck chunks) x 16 B
-    unsigned char *sW = smem;                                               // hi plane, lo plane
-    unsigned char *sA = sW + 2 * w_plane;                                   // 2 stages
-    float4 *sTr = reinterpret_cast<float4 *>(sA + 2 * a_stage);             // [M][5]
-    float2 *sGs = reinterpret_cast<float2 *>(sTr + (size_t)M * 5);          // [4*nck]
-    uint64_t *sBar = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(sGs + 4 * nck) + 15) & ~(uintptr_t)15);
-    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 8);
-    const uint32_t barA_full = smem_u32(sBar + 0), barAcc_full = smem_u32(sBar + 2), barAcc_empty = smem_u32(sBar + 4);
+    unsigned char *sW = smem + L.w;
+    unsigned char *sRaw = smem + L.raw;
+    const float4 *sTr = reinterpret_cast<const float4 *>(smem + L.tr);     // [M][5]
+    const float4 *sS = reinterpret_cast<const float4 *>(smem + L.sb);      // [nck] scales, then [nck] offsets
+    uint64_t *sBar = reinterpret_cast<uint64_t *>(smem + L.bar);
+    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 2 * TC_MAX_STAGES + 6);
+    const uint32_t barRaw_full = smem_u32(sBar), barRaw_empty = barRaw_full + 8 * TC_MAX_STAGES;
+    const uint32_t barA_full = barRaw_empty + 8 * TC_MAX_STAGES, barAcc_full = barA_full + 16;
 
     {   // stage the constant images
         const uint4 *src = reinterpret_cast<const uint4 *>(p.wimg);
         uint4 *dst = reinterpret_cast<uint4 *>(sW);
         for (uint32_t i = tid; i < 2 * w_plane / 16; i += TC_THREADS) dst[i] = src[i];
-        for (int i = tid; i < M * 5; i += TC_THREADS) sTr[i] = p.trp[i];
-        for (int i = tid; i < 4 * nck; i += TC_THREADS) sGs[i] = p.gs[i];
+        float4 *dtr = reinterpret_cast<float4 *>(smem + L.tr);
+        for (int i = tid; i < M * 5; i += TC_THREADS) dtr[i] = p.trp[i];
+        float *dsb = reinterpret_cast<float *>(smem + L.sb);
+        for (int i = tid; i < 8 * nck; i += TC_THREADS) dsb[i] = p.sb[i];
     }
     if (tid == 0) {
+        for (int s = 0; s < nst; s++) {
+            mbar_init(barRaw_full + 8 * s, 32 * TC_LOADERS);
+            mbar_init(barRaw_empty + 8 * s, TC_WORKER_WARPS);
+        }
         for (int s = 0; s < 2; s++) {
-            mbar_init(barA_full + 8 * s, TC_WORKERS);
+            mbar_init(barA_full + 8 * s, TC_WORKER_WARPS);
             mbar_init(barAcc_full + 8 * s, 1);
-            mbar_init(barAcc_empty + 8 * s, TC_WORKERS);
         }
         fence_barrier_init();
     }
-    // TMEM: two accumulator buffers of ncols columns
+    // TMEM: two accumulator buffers of ncols columns, two A-operand buffers of 8*nck columns (hi 4*nck | lo 4*nck)
+    const uint32_t a_cols = 8u * nck;
     uint32_t tcols = 32;
-    while (tcols < 2u * ncols) tcols <<= 1;
-    if (warp == 8) tmem_alloc(smem_u32(sTmem), tcols);
+    while (tcols < 2u * ncols + 2u * a_cols) tcols <<= 1;
+    if (warp == TC_WORKER_WARPS) tmem_alloc(smem_u32(sTmem), tcols);
     fence_proxy_async();            // W image written with generic stores, read by the tensor core
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *sTmem;
+    const uint32_t tmem_acc = tmem_base, tmem_a = tmem_base + 2u * ncols;
 
     const int ntiles = (p.nu + TC_ROWS - 1) / TC_ROWS;
-    uint32_t f = 0;                 // running frame counter of this CTA (pipeline stage / phase bookkeeping)
-    __shared__ int s_Tt[2];         // per-tile frame count, ping-pong by tile iteration
+    uint32_t f = 0;                 // running frame counter of this CTA (A / accumulator stage and phase)
+    uint32_t sg = 0;                // running raw-stage counter of this CTA (ring slot and phase)
 
-    if (warp == 8) {
+    // frames a row walks; every role derives the tile length (max over the 128 rows) with one warp reduction
+    auto row_frames = [&](int ul, int64_t &off) -> int {
+        off = 0;
+        if (ul >= p.nu) return 0;
+        off = p.offsets[p.u0 + ul];
+        const int T = (int)(p.offsets[p.u0 + ul + 1] - off);
+        return (p.first_frames > 0 && p.first_frames < T) ? p.first_frames : T;
+    };
+    auto tile_frames = [&](int tile) -> int {
+        int Tt = 0;
+        for (int r = lane; r < TC_ROWS; r += 32) {
+            int64_t o;
+            Tt = max(Tt, row_frames(tile * TC_ROWS + r, o));
+        }
+        for (int o = 16; o > 0; o >>= 1) Tt = max(Tt, __shfl_xor_sync(0xffffffffu, Tt, o));
+        return Tt;
+    };
+
+    auto trace = [&](int role, uint32_t frame, int ev) {
+        if (TRACE && blockIdx.x == 0 && lane == 0 && frame < TC_TRACE_FRAMES)
+            p.trace[((size_t)role * TC_TRACE_FRAMES + frame) * TC_TRACE_EVENTS + ev] = clock64();
+    };
+    if (warp >= TC_WORKER_WARPS) {
+    if (warp > TC_WORKER_WARPS) {
+        // ===================== bulk-copy producers =====================
+        // loader warp lw owns rows [lw*RPL, (lw+1)*RPL) of the tile; a lane issues at most two copies per stage
+        constexpr int RPL = (TC_ROWS + TC_LOADERS - 1) / TC_LOADERS;
+        const int lw = warp - TC_WORKER_WARPS - 1;
+        const int rlo = lw * RPL, rhi = min(rlo + RPL, TC_ROWS);
+        const int r0 = rlo + lane, r1 = rlo + lane + 32;
+        const uint32_t dst0 = smem_u32(sRaw) + (uint32_t)r0 * rstride, dst1 = smem_u32(sRaw) + (uint32_t)r1 * rstride;
+        const uint32_t stage_adv = (uint32_t)F * rowbytes;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int Tt = tile_frames(tile);
+            const int nsg = (Tt + F - 1) >> p.Fshift;
+            int64_t o0 = 0, o1 = 0;
+            const int Te0 = (r0 < rhi) ? row_frames(tile * TC_ROWS + r0, o0) : 0;
+            const int Te1 = (r1 < rhi) ? row_frames(tile * TC_ROWS + r1, o1) : 0;
+            const char *src0 = reinterpret_cast<const char *>(p.X + (size_t)o0 * p.ldx);
+            const char *src1 = reinterpret_cast<const char *>(p.X + (size_t)o1 * p.ldx);
+            int rem0 = Te0, rem1 = Te1;                      // frames not yet requested
+            for (int k = 0; k < nsg; k++, sg++) {
+                const uint32_t slot = sg & (uint32_t)(nst - 1), ph = (sg >> p.nst_shift) & 1u;
+                const uint32_t nb0 = (uint32_t)min(max(rem0, 0), F) * rowbytes, nb1 = (uint32_t)min(max(rem1, 0), F) * rowbytes;
+                const uint32_t bar = barRaw_full + 8 * slot;
+                mbar_wait(barRaw_empty + 8 * slot, ph ^ 1u);
+                if (lw == 0) trace(1, sg, 0);
+                mbar_arrive_tx(bar, nb0 + nb1);
+                if (nb0) bulk_g2s(dst0 + slot * stage_bytes, src0, nb0, bar);
+                if (nb1) bulk_g2s(dst1 + slot * stage_bytes, src1, nb1, bar);
+                src0 += stage_adv; src1 += stage_adv; rem0 -= F; rem1 -= F;
+                if (lw == 0) trace(1, sg, 1);
+                if (TRACE && lw == 0) { mbar_wait(bar, ph); trace(1, sg, 2); }
+            }
+        }
+    } else if (warp == TC_WORKER_WARPS) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = (1u << 4) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
-        const uint32_t sW_hi = smem_u32(sW), sW_lo = sW_hi + w_plane, sA0 = smem_u32(sA);
-        const uint32_t sboA = 2u * nck * 128u, sboW = (uint32_t)nck * 128u;
+        const uint32_t sW_hi = smem_u32(sW), sW_lo = sW_hi + w_plane;
+        const uint32_t sboW = (uint32_t)nck * 128u;
+        const uint64_t dW_hi = make_desc(sW_hi, 128, sboW), dW_lo = make_desc(sW_lo, 128, sboW);
+        const int nks = nck / 2;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            // frames this tile walks = max over its rows (computed identically by the workers)
-            int Tt = 0;
-            for (int r = lane; r < TC_ROWS; r += 32) {
-                const int ul = tile * TC_ROWS + r;
-                if (ul < p.nu) {
-                    const int T = (int)(p.offsets[p.u0 + ul + 1] - p.offsets[p.u0 + ul]);
-                    Tt = max(Tt, (p.first_frames > 0 && p.first_frames < T) ? p.first_frames : T);
-                }
-            }
-            for (int o = 16; o > 0; o >>= 1) Tt = max(Tt, __shfl_xor_sync(0xffffffffu, Tt, o));
+            const int Tt = tile_frames(tile);
             for (int t = 0; t < Tt; t++, f++) {
                 const uint32_t s = f & 1, ph = (f >> 1) & 1;
+                trace(0, f, 0);
                 mbar_wait(barA_full + 8 * s, ph);
-                mbar_wait(barAcc_empty + 8 * s, ph ^ 1);
+                trace(0, f, 1);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t d_tmem = tmem_base + s * (uint32_t)ncols;
-                    const uint32_t aBase = sA0 + s * a_stage;
-                    uint32_t acc = 0;
-                    for (int ks = 0; ks < nck / 2; ks++) {      // (hi + lo) * W_hi ... hi block
-                        umma_f16(d_tmem, make_desc(aBase + ks * 256, 128, sboA), make_desc(sW_hi + ks * 256, 128, sboW), idesc, acc);
-                        acc = 1;
+                    const uint32_t d_tmem = tmem_acc + s * (uint32_t)ncols;
+                    const uint32_t a_hi = tmem_a + s * a_cols, a_lo = a_hi + 4u * nck;
+                    // the two small correction products first: the tensor core truncates the fp32 accumulator on
+                    // every step, so the large hi * W_hi partial sums should see as few steps as possible.
+                    // One K = 16 step advances A by 8 TMEM columns and the W descriptor by 256 B (16 in its address field).
+                    if (NKS > 0) {
+#pragma unroll
+                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_lo + ks * 8, dW_hi + (uint64_t)(16 * ks), idesc, ks > 0);
+#pragma unroll
+                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 8, dW_lo + (uint64_t)(16 * ks), idesc, 1);
+#pragma unroll
+                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 8, dW_hi + (uint64_t)(16 * ks), idesc, 1);
+                    } else {
+                        uint64_t dh = dW_hi, dl = dW_lo;
+                        uint32_t a = a_lo;
+                        for (int ks = 0; ks < nks; ks++, a += 8, dh += 16) umma_f16_ts(d_tmem, a, dh, idesc, ks > 0);   // lo * W_hi
+                        a = a_hi;
+                        for (int ks = 0; ks < nks; ks++, a += 8, dl += 16) umma_f16_ts(d_tmem, a, dl, idesc, 1);        // hi * W_lo
+                        a = a_hi; dh = dW_hi;
+                        for (int ks = 0; ks < nks; ks++, a += 8, dh += 16) umma_f16_ts(d_tmem, a, dh, idesc, 1);        // hi * W_hi
                     }
-                    for (int ks = 0; ks < nck / 2; ks++)        // lo block of A against W_hi
-                        umma_f16(d_tmem, make_desc(aBase + (nck + 2 * ks) * 128, 128, sboA), make_desc(sW_hi + ks * 256, 128, sboW), idesc, 1);
-                    for (int ks = 0; ks < nck / 2; ks++)        // hi block of A against W_lo
-                        umma_f16(d_tmem, make_desc(aBase + ks * 256, 128, sboA), make_desc(sW_lo + ks * 256, 128, sboW), idesc, 1);
                     umma_commit(barAcc_full + 8 * s);
                 }
                 __syncwarp();
+                trace(0, f, 2);
+                if (TRACE) { mbar_wait(barAcc_full + 8 * s, ph); trace(0, f, 3); }
             }
         }
+    }
     } else {
         // ===================== workers =====================
-        const int g = warp >> 2;                     // column group (which half of the models)
-        const int r = (warp & 3) * 32 + lane;        // row of the tile = TMEM lane
-        const int mg0 = (M + 1) / 2;
-        const int mbeg = g == 0 ? 0 : mg0, mcnt = g == 0 ? mg0 : M - mg0;
-        const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        const int cbeg = g == 0 ? 0 : (nck + 1) / 2, cend = g == 0 ? (nck + 1) / 2 : nck;   // chunks this thread converts
-        int it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-            const int ul = tile * TC_ROWS + r;
-            const bool live = ul < p.nu;
-            int64_t off = 0;
-            int Te = 0;
-            if (live) {
-                off = p.offsets[p.u0 + ul];
-                const int T = (int)(p.offsets[p.u0 + ul + 1] - off);
-                Te = (p.first_frames > 0 && p.first_frames < T) ? p.first_frames : T;
+        const int q = warp & 3;                      // TMEM lane quadrant this warp may access
+        const int g = warp >> 2;                     // group: which models / which feature chunks
+        const int r = q * 32 + lane;                 // row of the tile = TMEM lane
+        const int mbase = M / TC_GROUPS, mrem = M % TC_GROUPS;
+        const int mbeg = g * mbase + min(g, mrem), mcnt = mbase + (g < mrem ? 1 : 0);
+        int c0 = 0, c1 = 0;                          // feature chunks: the groups with fewer models take the extra ones
+        {
+            const int cbase = nck / TC_GROUPS, crem = nck % TC_GROUPS;
+            int acc = 0;
+            for (int gg = 0; gg < TC_GROUPS; gg++) {
+                const int cnt = cbase + ((TC_GROUPS - 1 - gg) < crem ? 1 : 0);
+                if (gg == g) { c0 = acc; c1 = acc + cnt; }
+                acc += cnt;
             }
-            // tile length = max Te over the 128 rows: every worker thread needs it (barrier counts);
-            // named barrier over the 256 workers only (the MMA warp does not take part)
-            if (tid == 0) s_Tt[it & 1] = 0;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (g == 0) atomicMax(&s_Tt[it & 1], Te);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const int Tt = s_Tt[it & 1];
+        }
+        const int nch = c1 - c0;                                       // 0..3 chunks per thread
+        int nrd = 0;                                                   // chunks whose 16 bytes lie inside the feature row
+        for (int c = 0; c < nch; c++) if (4 * (c0 + c) < p.ldx) nrd = c + 1;
+        const int trole = (warp == 0) ? 2 : (warp == 6) ? 3 : (warp == 15) ? 4 : -1;   // traced worker warps
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        // per-thread addresses, pinned in registers
+        const uint32_t ta_hi0 = pin_reg(tmem_a + lane_sel + 4u * c0);              // A hi, stage 0 (stage 1: + a_cols)
+        const uint32_t acc0 = pin_reg(tmem_acc + lane_sel + (uint32_t)mbeg * 8u);  // accumulators, stage 0 (stage 1: + ncols)
+        const uint32_t raw0 = pin_reg(smem_u32(sRaw) + (uint32_t)r * rstride + 16u * c0);
+        const uint32_t lo_off = 4u * nck;
+        const uint32_t trS = pin_reg(smem_u32(sTr) + (uint32_t)mbeg * 80u);
+        const uint32_t sbS = pin_reg(smem_u32(sS) + 16u * c0);
+        const uint32_t sbB = sbS + 16u * nck;
+        const size_t bp_model = (size_t)p.maxT * p.Bpad;                 // elements between consecutive models
+        const size_t bp_frame = (size_t)p.Bpad;
+        const uint32_t baseS = pin_reg(smem_u32(smem + L.base) + (uint32_t)tid * 8u);   // [k][tid] float64
 
-            float V[MG][8], Vx[MG];
-            double base[MG];
+        auto lds4 = [](uint32_t a) -> float4 {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+            return v;
+        };
+
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int Tt = tile_frames(tile);
+            const int ul = tile * TC_ROWS + r;
+            int64_t off;
+            const int Te = row_frames(ul, off);
+            const bool live = ul < p.nu;
+            const uint32_t sg0 = sg;
+
+            float2 U[MG][4];
+            float Ux[MG];
+            uint16_t *bpt = p.bp + (size_t)mbeg * bp_model + ul;       // back-pointer word of (first model, frame t, this row)
 #pragma unroll
             for (int k = 0; k < MG; k++) {
-                Vx[k] = -INFINITY; base[k] = 0.0;
+                Ux[k] = -INFINITY;
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"(baseS + (uint32_t)k * (TC_WORKERS * 8u)), "d"(0.0) : "memory");
 #pragma unroll
-                for (int j = 0; j < 8; j++) V[k][j] = -INFINITY;
+                for (int j = 0; j < 4; j++) U[k][j] = make_float2(-INFINITY, -INFINITY);
             }
-            // raw feature prefetch registers: up to 8 chunks per thread
-            float4 xr[8];
-            auto load_row = [&](int t) {
-                const bool ok = live && t < Te;
-                const float4 *row = reinterpret_cast<const float4 *>(p.X + (size_t)(off + t) * p.ldx);
+
+            // frame t of this tile -> standardise, square, split, store into A-operand stage fr & 1
+            auto convert = [&](int t, uint32_t fr) {
+                const int kk = t >> p.Fshift, fi = t & (F - 1);
+                const uint32_t sgk = sg0 + (uint32_t)kk, slot = sgk & (uint32_t)(nst - 1);
+                if (TRACE && trole >= 0) trace(trole, fr, 0);
+                if (fi == 0) mbar_wait(barRaw_full + 8 * slot, (sgk >> p.nst_shift) & 1u);
+                if (TRACE && trole >= 0) trace(trole, fr, 1);
+                const uint32_t rowp = raw0 + slot * stage_bytes + (uint32_t)fi * rowbytes;
+                const bool ok = t < Te;                      // Te == 0 for rows beyond the batch
+                const uint32_t ta = ta_hi0 + (fr & 1u) * a_cols;
 #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    const int ch = cbeg + c;
-                    xr[c] = (ok && ch < cend && 4 * ch < p.ldx) ? __ldg(row + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            };
-            auto convert_row = [&](uint32_t fr) {      // write this thread's chunks of frame fr into stage fr & 1
-                unsigned char *aS = sA + (fr & 1) * a_stage + (size_t)(r >> 3) * (2 * nck * 128) + (r & 7) * 16;
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    const int ch = cbeg + c;
-                    if (ch < cend) {
-                        const float xv[4] = {xr[c].x, xr[c].y, xr[c].z, xr[c].w};
-                        uint32_t hi[4], lo[4];
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const int d = 4 * ch + q;
-                            const float2 gsd = sGs[d];
-                            float xs = (xv[q] - gsd.x) * gsd.y;
-                            xs = fminf(fmaxf(xs, -250.f), 250.f);
-                            if (d >= p.D) xs = (d == p.D) ? 1.f : 0.f;      // constant slot / zero padding
-                            const float x2 = xs * xs;
-                            const __half2 h = __floats2half2_rn(xs, x2);
-                            const float2 hf = __half22float2(h);
-                            const __half2 l = __floats2half2_rn(xs - hf.x, x2 - hf.y);
-                            hi[q] = *reinterpret_cast<const uint32_t *>(&h);
-                            lo[q] = *reinterpret_cast<const uint32_t *>(&l);
-                        }
-                        *reinterpret_cast<uint4 *>(aS + (size_t)ch * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4 *>(aS + (size_t)(nck + ch) * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                for (int c = 0; c < 3; c++) {
+                    if (c < nch) {
+                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok && c < nrd) x = lds4(rowp + 16u * c);
+                        const float4 sc = lds4(sbS + 16u * c), of = lds4(sbB + 16u * c);
+                        const float2 a01 = fma2(make_float2(x.x, x.y), make_float2(sc.x, sc.y), make_float2(of.x, of.y));
+                        const float2 a23 = fma2(make_float2(x.z, x.w), make_float2(sc.z, sc.w), make_float2(of.z, of.w));
+                        const float2 q01 = mul2(a01, a01), q23 = mul2(a23, a23);
+                        const uint32_t h0 = pack_h2(a01), h1 = pack_h2(a23), h2 = pack_h2(q01), h3 = pack_h2(q23);
+                        const uint32_t l0 = pack_h2(sub2(a01, unpack_h2(h0))), l1 = pack_h2(sub2(a23, unpack_h2(h1)));
+                        const uint32_t l2 = pack_h2(sub2(q01, unpack_h2(h2))), l3 = pack_h2(sub2(q23, unpack_h2(h3)));
+                        tmem_st4(ta + 4u * c, h0, h1, h2, h3);
+                        tmem_st4(ta + lo_off + 4u * c, l0, l1, l2, l3);
                     }
                 }
-                fence_proxy_async();
-                mbar_arrive(barA_full + 8 * (fr & 1));
-            };
-
-            if (Tt > 0) {
-                load_row(0);
-                convert_row(f);
-                load_row(1);
-            }
-            uint16_t *bpp = p.bp + ul;
-            for (int t = 0; t < Tt; t++, f++) {
-                if (t + 1 < Tt) {
-                    convert_row(f + 1);
-                    load_row(t + 2);
-                }
-                const uint32_t s = f & 1, ph = (f >> 1) & 1;
-                mbar_wait(barAcc_full + 8 * s, ph);
-                tc_fence_after();
-                uint32_t ev[MG][8];
-#pragma unroll
-                for (int k = 0; k < MG; k++)
-                    if (k < mcnt) tmem_ld8(tmem_lane + s * (uint32_t)ncols + (uint32_t)(mbeg + k) * 8, ev[k]);
-                tmem_ld_wait();
+                tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(barAcc_empty + 8 * s);
-                if (p.dbgE && live && t < Te) {
-#pragma unroll
-                    for (int k = 0; k < MG; k++)
-                        if (k < mcnt)
-#pragma unroll
-                            for (int j = 0; j < 8; j++) p.dbgE[(size_t)(off + t) * ncols + (mbeg + k) * 8 + j] = __uint_as_float(ev[k][j]);
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(barA_full + 8 * (fr & 1u));
+                    if (fi == F - 1 || t == Tt - 1) mbar_arrive(barRaw_empty + 8 * slot);
                 }
-                if (live && t < Te) {
+                if (TRACE && trole >= 0) trace(trole, fr, 2);
+            };
+            // accumulators of frame fr ready?  (their release needs no barrier: a warp signals A_full(fr + 2) only after
+            // its last tcgen05.ld of frame fr, and the MMAs of frame fr + 2 wait for every warp's A_full(fr + 2))
+            auto acc_ready = [&](uint32_t fr) -> uint32_t {
+                const uint32_t s = fr & 1u;
+                if (TRACE && trole >= 0) trace(trole, fr, 3);
+                mbar_wait(barAcc_full + 8 * s, (fr >> 1) & 1u);
+                if (TRACE && trole >= 0) trace(trole, fr, 4);
+                tc_fence_after();
+                return acc0 + s * (uint32_t)ncols;
+            };
+            if (Tt > 0) convert(0, f);
+            const int Tearly = min(Tt, 9);
+            int t = 0;
+            // ---- frames 0 .. 8: entry state, closed exit (generic step) ----
+            for (; t < Tearly; t++, f++) {
+                if (t + 1 < Tt) convert(t + 1, f + 1);
+                const uint32_t tacc = acc_ready(f);
+                const bool act = t < Te;
 #pragma unroll
-                    for (int k = 0; k < MG; k++) {
-                        if (k < mcnt) {
-                            const float4 *tr = sTr + (size_t)(mbeg + k) * 5;
-                            const float4 t0 = tr[0], t1 = tr[1], t2 = tr[2], t3 = tr[3], t4 = tr[4];
-                            const float stay[8] = {t0.x, t0.z, t1.x, t1.z, t2.x, t2.z, t3.x, t3.z};
-                            const float adv[8] = {t0.y, t0.w, t1.y, t1.w, t2.y, t2.w, t3.y, t3.w};
-                            float e[8];
+                for (int k = 0; k < MG; k++) {
+                    if (k < mcnt) {
+                        uint32_t ev[8];
+                        tmem_ld8(tacc + 8u * k, ev);
+                        tmem_ld_wait();
+                        if (DBG && p.dbgE && act) {
+                            const float4 st0 = lds4(trS + 80u * k + 48u), st1 = lds4(trS + 80u * k + 64u);
+                            const float st[8] = {st0.x, st0.y, st0.z, st0.w, st1.x, st1.y, st1.z, st1.w};
 #pragma unroll
-                            for (int j = 0; j < 8; j++) e[j] = __uint_as_float(ev[k][j]);
+                            for (int j = 0; j < 8; j++)
+                                p.dbgE[(size_t)(off + t) * ncols + (mbeg + k) * 8 + j] = __uint_as_float(ev[j]) - st[j];
+                        }
+                        if (act) {
+                            const float4 cm = lds4(trS + 80u * k + 32u);
                             if (t == 0) {
-                                V[k][0] = t4.z + e[0];                       // V[0,1] = ln A01 + E[0,1]
+                                U[k][0].x = cm.y + __uint_as_float(ev[0]);   // U_1 = ln A01 + E[0,1] + ln A11
                             } else {
-                                uint32_t sb = 0;                             // "stayed" bits, exit first
-                                float nx = -INFINITY;
-                                if (t >= 8) {                                // exit opens at t >= N (custom_hmm.py:481-485)
-                                    const float ca = V[k][7] + t4.y, cs = Vx[k] + t4.x;
-                                    sb = __funnelshift_l(__float_as_uint(ca - cs), sb, 1);
-                                    nx = fmaxf(ca, cs);
-                                } else {
-                                    sb = 1;
-                                }
-#pragma unroll
-                                for (int j = 7; j >= 1; j--) {
-                                    const float ca = V[k][j - 1] + adv[j], cs = V[k][j] + stay[j];
-                                    sb = __funnelshift_l(__float_as_uint(ca - cs), sb, 1);   // sign(ca - cs) = 1 -> stayed
-                                    V[k][j] = fmaxf(ca, cs) + e[j];
-                                }
-                                {
-                                    const float ca = (t == 1) ? t4.z : -INFINITY;            // entry only at t == 1
-                                    const float cs = V[k][0] + stay[0];
-                                    sb = __funnelshift_l(__float_as_uint(ca - cs), sb, 1);
-                                    V[k][0] = fmaxf(ca, cs) + e[0];
-                                }
-                                Vx[k] = nx;
-                                // after 9 shifts: bit 8 = exit, bit j = state j+1; advanced = !stayed
-                                bpp[((size_t)(mbeg + k) * p.maxT + t) * p.Bpad] = (uint16_t)((~sb) & 0x1FFu);
-                                if ((t & 3) == 0) {                          // renormalise, offset kept in float64
-                                    float mx = Vx[k];
-#pragma unroll
-                                    for (int j = 0; j < 8; j++) mx = fmaxf(mx, V[k][j]);
-                                    if (mx > -INFINITY && mx < INFINITY) {
-#pragma unroll
-                                        for (int j = 0; j < 8; j++) V[k][j] -= mx;
-                                        Vx[k] -= mx;
-                                        base[k] += (double)mx;
-                                    }
-                                }
+                                const float4 c03 = lds4(trS + 80u * k), c47 = lds4(trS + 80u * k + 16u);
+                                const uint32_t bits = vit_step<true>(U[k], Ux[k], c03, c47, cm.x, cm.y, ev, t);
+                                bpt[(size_t)k * bp_model] = (uint16_t)bits;
+                                if ((t & 3) == 0) vit_renorm(U[k], Ux[k], baseS + (uint32_t)k * (TC_WORKERS * 8u));
                             }
                         }
                     }
                 }
+                tc_fence_before();
+                bpt += bp_frame;
             }
+            // ---- steady state: no entry arc, exit open ----
+            for (; t < Tt; t++, f++) {
+                if (t + 1 < Tt) convert(t + 1, f + 1);
+                const uint32_t tacc = acc_ready(f);
+                const bool act = t < Te;
+                const bool rn = (t & 3) == 0;
+#pragma unroll
+                for (int k = 0; k < MG; k++) {
+                    if (k < mcnt) {
+                        uint32_t ev[8];
+                        tmem_ld8(tacc + 8u * k, ev);
+                        tmem_ld_wait();
+                        if (DBG && p.dbgE && act) {
+                            const float4 st0 = lds4(trS + 80u * k + 48u), st1 = lds4(trS + 80u * k + 64u);
+                            const float st[8] = {st0.x, st0.y, st0.z, st0.w, st1.x, st1.y, st1.z, st1.w};
+#pragma unroll
+                            for (int j = 0; j < 8; j++)
+                                p.dbgE[(size_t)(off + t) * ncols + (mbeg + k) * 8 + j] = __uint_as_float(ev[j]) - st[j];
+                        }
+                        if (act) {
+                            const float4 c03 = lds4(trS + 80u * k), c47 = lds4(trS + 80u * k + 16u), cm = lds4(trS + 80u * k + 32u);
+                            const uint32_t bits = vit_step<false>(U[k], Ux[k], c03, c47, cm.x, cm.y, ev, t);
+                            bpt[(size_t)k * bp_model] = (uint16_t)bits;
+                            if (rn) vit_renorm(U[k], Ux[k], baseS + (uint32_t)k * (TC_WORKERS * 8u));
+                        }
+                    }
+                }
+                tc_fence_before();
+                if (TRACE && trole >= 0) trace(trole, f, 5);
+                bpt += bp_frame;
+            }
+            sg = sg0 + (uint32_t)((Tt + F - 1) >> p.Fshift);
             if (live) {
 #pragma unroll
                 for (int k = 0; k < MG; k++)
                     if (k < mcnt) {
-                        const double sc = (Te > 0 && Vx[k] > -INFINITY) ? (double)Vx[k] + base[k] : -INFINITY;
+                        double b;
+                        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b) : "r"(baseS + (uint32_t)k * (TC_WORKERS * 8u)));
+                        const double sc = (Te > 0 && Ux[k] > -INFINITY) ? (double)Ux[k] + b : -INFINITY;
                         p.scores[(size_t)ul * M + mbeg + k] = sc;
                     }
             }
@@ -418,57 +683,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, tcols);
+    if (warp == TC_WORKER_WARPS) tmem_dealloc(tmem_base, tcols);
 }
 
 // ------------------------------------------------------------------------------------------------
 bool sapr_tc_eligible(const sapr_models *m) {
     return m->emission == SAPR_EMIT_DIAG && m->topology == SAPR_TOPO_ENTRY_EXIT && m->N == 8 && m->M <= 12 &&
-           m->D + 1 <= 64;
+           m->D + 1 <= 48;
 }
 
-size_t sapr_tc_image_bytes(const sapr_models *m, int *nck_out, int *ncols_out) {
+static void tc_geometry(const sapr_models *m, int *nck_out, int *ncols_out) {
     int nck = (m->D + 1 + 3) / 4;
     nck = (nck + 1) / 2 * 2;
     const int ncols = (m->M * 8 + 15) / 16 * 16;
     if (nck_out) *nck_out = nck;
     if (ncols_out) *ncols_out = ncols;
-    size_t w = (size_t)2 * (ncols / 8) * nck * 64 * sizeof(__half);
-    w = (w + 255) / 256 * 256;
-    size_t g = ((size_t)4 * nck * sizeof(float2) + 255) / 256 * 256;
-    size_t t = ((size_t)m->M * 5 * sizeof(float4) + 255) / 256 * 256;
-    return w + g + t;
+}
+
+static inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+
+size_t sapr_tc_image_bytes(const sapr_models *m, int *nck_out, int *ncols_out) {
+    int nck, ncols;
+    tc_geometry(m, &nck, &ncols);
+    if (nck_out) *nck_out = nck;
+    if (ncols_out) *ncols_out = ncols;
+    return al256((size_t)2 * (ncols / 8) * nck * 64 * sizeof(__half)) + al256((size_t)8 * nck * sizeof(float)) +
+           al256((size_t)m->M * 5 * sizeof(float4));
 }
 
 int sapr_tc_prepare(sapr_models *m) {
     sapr_ctx *ctx = m->ctx;
     int nck, ncols;
-    sapr_tc_image_bytes(m, &nck, &ncols);
-    const size_t w = ((size_t)2 * (ncols / 8) * nck * 64 * sizeof(__half) + 255) / 256 * 256;
-    const size_t g = ((size_t)4 * nck * sizeof(float2) + 255) / 256 * 256;
+    tc_geometry(m, &nck, &ncols);
+    const size_t w = al256((size_t)2 * (ncols / 8) * nck * 64 * sizeof(__half));
+    const size_t g = al256((size_t)8 * nck * sizeof(float));
     __half *wimg = (__half *)m->tc_image;
-    float2 *gs = (float2 *)((char *)m->tc_image + w);
+    float *sb = (float *)((char *)m->tc_image + w);
     float4 *trp = (float4 *)((char *)m->tc_image + w + g);
-    {
-        const size_t smem = (size_t)2 * (ncols / 8) * nck * 128 + (size_t)2 * 16 * 2 * nck * 128 + (size_t)m->M * 5 * 16 +
-                            (size_t)4 * nck * 8 + 16 + 64 + 16;
-        const int MG = (m->M + 1) / 2;
-        int nb = 1;
-        cudaError_t e;
-        if (MG <= 2) { cudaFuncSetAttribute(k_viterbi_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_viterbi_tc<2>, TC_THREADS, smem); }
-        else if (MG <= 4) { cudaFuncSetAttribute(k_viterbi_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_viterbi_tc<4>, TC_THREADS, smem); }
-        else { cudaFuncSetAttribute(k_viterbi_tc<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-               e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_viterbi_tc<6>, TC_THREADS, smem); }
-        if (e != cudaSuccess) { cudaGetLastError(); nb = 1; }
-        int tcols = 32;
-        while (tcols < 2 * ncols) tcols <<= 1;
-        nb = std::max(1, std::min(nb, 512 / tcols));     // TMEM: 512 columns per SM
-        m->tc_ctas_per_sm = nb;
-    }
     k_prepare_tc<<<1, 256, sizeof(double) * 2 * 4 * nck, ctx->stream>>>(m->M, m->S, m->D, nck, ncols, m->mean, m->cov, m->la64,
-                                                                         m->lb64, wimg, gs, trp);
+                                                                         m->lb64, wimg, sb, trp);
     SAPR_LAUNCH_CHECK(ctx);
     return SAPR_OK;
 }
@@ -483,9 +736,9 @@ int sapr_viterbi_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
                            int64_t total_frames, int max_T, int first_frames, int32_t *best_word, double *best_score,
                            double *scores, uint8_t *best_path, uint8_t *all_paths, float *dbgE) {
     int nck, ncols;
-    sapr_tc_image_bytes(m, &nck, &ncols);
-    const size_t w = ((size_t)2 * (ncols / 8) * nck * 64 * sizeof(__half) + 255) / 256 * 256;
-    const size_t g = ((size_t)4 * nck * sizeof(float2) + 255) / 256 * 256;
+    tc_geometry(m, &nck, &ncols);
+    const size_t w = al256((size_t)2 * (ncols / 8) * nck * 64 * sizeof(__half));
+    const size_t g = al256((size_t)8 * nck * sizeof(float));
     const int M = m->M;
     const int Tm = (first_frames > 0 && first_frames < max_T) ? first_frames : max_T;
     int64_t per_utt = (int64_t)M * (Tm > 0 ? Tm : 1) * sizeof(uint16_t);
@@ -497,9 +750,25 @@ int sapr_viterbi_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
     if ((rc = sapr_ws_reserve(ctx, 1, (size_t)chunk * M * sizeof(double)))) return rc;
     uint16_t *bp = (uint16_t *)ctx->ws[0];
     double *sc_ws = (double *)ctx->ws[1];
-    const size_t smem = (size_t)2 * (ncols / 8) * nck * 128 + (size_t)2 * 16 * 2 * nck * 128 + (size_t)M * 5 * 16 +
-                        (size_t)4 * nck * 8 + 16 + 64 + 16;
-    const int MG = (M + 1) / 2;
+
+    // raw-feature ring: largest power-of-two frames per stage (<= 8) such that two stages fit beside the W image
+    const uint32_t rowbytes = (uint32_t)ldx * 4u;
+    const size_t budget = 225 * 1024;
+    int Fshift = 3, nst = 2, nst_shift = 1;
+    uint32_t rstride = 0;
+    TcSmem L;
+    for (;; Fshift--) {
+        const uint32_t F = 1u << Fshift;
+        rstride = F * rowbytes + 16u;
+        if (((rstride >> 4) & 1u) == 0) rstride += 16u;     // odd multiple of 16 B: conflict-free LDS.128 across rows
+        L = tc_smem_layout(M, nck, ncols, nst, rstride);
+        if (L.total <= budget) break;
+        if (Fshift == 0) SAPR_FAIL(ctx, SAPR_E_RANGE, "viterbi (tensor core): feature rows too wide for the shared-memory ring");
+    }
+    if (Fshift <= 1 && tc_smem_layout(M, nck, ncols, 4, rstride).total <= budget) { nst = 4; nst_shift = 2; }
+    L = tc_smem_layout(M, nck, ncols, nst, rstride);
+    const size_t smem = L.total;
+    const int MG = (M + TC_GROUPS - 1) / TC_GROUPS;
     auto launch = [&](auto kern, const TcParams &prm, int grid) -> int {
         SAPR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
@@ -514,13 +783,43 @@ int sapr_viterbi_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
         TcParams prm;
         prm.X = X; prm.ldx = ldx; prm.offsets = offsets; prm.u0 = u0; prm.nu = nu; prm.M = M; prm.D = m->D; prm.nck = nck;
         prm.ncols = ncols; prm.first_frames = first_frames; prm.wimg = (const __half *)m->tc_image;
-        prm.gs = (const float2 *)((const char *)m->tc_image + w); prm.trp = (const float4 *)((const char *)m->tc_image + w + g);
+        prm.sb = (const float *)((const char *)m->tc_image + w); prm.trp = (const float4 *)((const char *)m->tc_image + w + g);
         prm.bp = bp; prm.Bpad = Bpad; prm.maxT = Tm; prm.scores = sc_ws; prm.dbgE = dbgE;
+        prm.Fshift = Fshift; prm.nst_shift = nst_shift; prm.rstride = rstride; prm.trace = nullptr;
+        const char *trace_path = getenv("SAPR_TC_TRACE");
+        if (trace_path && MG == 3 && !dbgE && u0 == 0) {      // tuning aid: one traced launch, timestamps to a text file
+            const size_t nrec = (size_t)TC_TRACE_ROLES * TC_TRACE_FRAMES * TC_TRACE_EVENTS;
+            long long *dtr = nullptr;
+            SAPR_CUDA(ctx, cudaMalloc(&dtr, nrec * sizeof(long long)));
+            SAPR_CUDA(ctx, cudaMemsetAsync(dtr, 0, nrec * sizeof(long long), ctx->stream));
+            prm.trace = dtr;
+            const int ntl = (nu + TC_ROWS - 1) / TC_ROWS;
+            rc = (nck == 10) ? launch(k_viterbi_tc<3, 5, false, true>, prm, std::min(ntl, ctx->sm_count))
+                             : launch(k_viterbi_tc<3, 0, false, true>, prm, std::min(ntl, ctx->sm_count));
+            std::vector<long long> h(nrec);
+            cudaMemcpyAsync(h.data(), dtr, nrec * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(dtr);
+            if (FILE *fp = fopen(trace_path, "w")) {
+                for (int ro = 0; ro < TC_TRACE_ROLES; ro++)
+                    for (int fr = 0; fr < TC_TRACE_FRAMES; fr++) {
+                        fprintf(fp, "%d %d", ro, fr);
+                        for (int e = 0; e < TC_TRACE_EVENTS; e++) fprintf(fp, " %lld", h[((size_t)ro * TC_TRACE_FRAMES + fr) * TC_TRACE_EVENTS + e]);
+                        fprintf(fp, "\n");
+                    }
+                fclose(fp);
+            }
+            prm.trace = nullptr;
+            if (rc) return rc;
+        }
         const int ntiles = (nu + TC_ROWS - 1) / TC_ROWS;
-        const int grid = std::min(ntiles, ctx->sm_count * m->tc_ctas_per_sm);
-        if (MG <= 2) rc = launch(k_viterbi_tc<2>, prm, grid);
-        else if (MG <= 4) rc = launch(k_viterbi_tc<4>, prm, grid);
-        else rc = launch(k_viterbi_tc<6>, prm, grid);
+        const int grid = std::min(ntiles, ctx->sm_count);
+        if (dbgE) rc = launch(k_viterbi_tc<3, 0, true>, prm, grid);
+        else if (MG <= 1) rc = launch(k_viterbi_tc<1, 0, false>, prm, grid);
+        else if (MG <= 2) rc = launch(k_viterbi_tc<2, 0, false>, prm, grid);
+        else if (nck == 10) rc = launch(k_viterbi_tc<3, 5, false>, prm, grid);     // D = 36..39 (cfg 2/3)
+        else if (nck == 4) rc = launch(k_viterbi_tc<3, 2, false>, prm, grid);      // D = 12..15 (cfg 1)
+        else rc = launch(k_viterbi_tc<3, 0, false>, prm, grid);
         if (rc) return rc;
         if ((rc = sapr_viterbi_finish_u16(ctx, offsets, u0, nu, m->N, M, first_frames, bp, Bpad, Tm, sc_ws, best_word, best_score,
                                           scores, M, best_path, all_paths, total_frames)))
