@@ -203,15 +203,86 @@ __global__ void k_viterbi_finish(const int64_t *__restrict__ offsets, int u0, in
     }
 }
 
+// Fast path of the above for the production call (winner's path only): a warp owns 32 utterances (lane = utterance).
+// Back-pointer words of a 32-frame chunk are fetched with 32 independent loads per lane (the address does not depend
+// on the state being traced), the traced states are staged in shared memory and written out row by row so every
+// store instruction covers 32 consecutive bytes of one utterance's path.
+template <typename BP>
+__global__ void __launch_bounds__(128)
+k_viterbi_finish_fast(const int64_t *__restrict__ offsets, int u0, int nu, int N, int nslots,
+                      const int32_t *__restrict__ model_of_utt, int first_frames, const BP *__restrict__ bp, int64_t Bpad,
+                      int maxT, const double *__restrict__ scores, int32_t *__restrict__ best_word,
+                      double *__restrict__ best_score, double *__restrict__ scores_out, uint8_t *__restrict__ best_path) {
+    constexpr int CH = 32;
+    __shared__ uint8_t sp[4][32][CH + 4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int ul = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = ul < nu;
+    const int u = u0 + ul;
+    const int S = N + 2;
+    int64_t off = 0;
+    int Te = 0;
+    double bs = -INFINITY;
+    int bslot = -1;
+    if (live) {
+        off = offsets[u];
+        const int T = (int)(offsets[u + 1] - off);
+        Te = (first_frames > 0 && first_frames < T) ? first_frames : T;
+        for (int s = 0; s < nslots; s++) {
+            const double sc = scores[(size_t)ul * nslots + s];
+            if (scores_out) scores_out[(size_t)u * nslots + s] = sc;
+            if (sc > bs) { bs = sc; bslot = s; }
+        }
+        if (best_word) best_word[u] = (bslot < 0) ? -1 : (model_of_utt ? model_of_utt[u] : bslot);
+        if (best_score) best_score[u] = bs;
+    }
+    if (!best_path) return;
+    const int wslot = bslot < 0 ? 0 : bslot;
+    const bool reachable = live && scores[(size_t)ul * nslots + wslot] != -INFINITY;
+    const BP *bpp = bp + ((size_t)wslot * maxT) * Bpad + ul;
+    int Tm = Te;
+    for (int o = 16; o > 0; o >>= 1) Tm = max(Tm, __shfl_xor_sync(0xffffffffu, Tm, o));
+    int cur = S - 1;
+    for (int t0 = (Tm - 1) / CH * CH; t0 >= 0; t0 -= CH) {
+        unsigned bits[CH];
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            const int t = t0 + j;
+            bits[j] = (reachable && t >= 1 && t < Te) ? (unsigned)bpp[(size_t)t * Bpad] : 0u;
+        }
+#pragma unroll
+        for (int j = CH - 1; j >= 0; j--) {
+            const int t = t0 + j;
+            if (t < Te) {
+                sp[w][lane][j] = (uint8_t)cur;
+                if (!reachable) cur = 0;                                   // unreachable cell: back-pointer stays 0 (:470)
+                else if (cur >= 1 && t >= 1) cur -= (int)((bits[j] >> (cur - 1)) & 1u);   // exit (S-1) -> N uses bit N
+            }
+        }
+        __syncwarp();
+        for (int row = 0; row < 32; row++) {
+            const int Te_r = __shfl_sync(0xffffffffu, Te, row);
+            const int64_t off_r = __shfl_sync(0xffffffffu, off, row);
+            if (t0 + lane < Te_r) best_path[off_r + t0 + lane] = sp[w][row][lane];
+        }
+        __syncwarp();
+    }
+}
+
 int sapr_viterbi_finish_u16(sapr_ctx *ctx, const int64_t *offsets, int u0, int nu, int N, int nslots, int first_frames,
                             const uint16_t *bp, int64_t Bpad, int maxT, const double *scores, int32_t *best_word,
                             double *best_score, double *scores_out, int M, uint8_t *best_path, uint8_t *all_paths,
                             int64_t total_frames) {
     {
         ProfScope ps(ctx, 1);
-        k_viterbi_finish<uint16_t><<<(nu + 127) / 128, 128, 0, ctx->stream>>>(offsets, u0, nu, N, nslots, nullptr, first_frames, bp,
-                                                                              Bpad, maxT, scores, best_word, best_score,
-                                                                              scores_out, M, best_path, all_paths, total_frames);
+        if (!all_paths)
+            k_viterbi_finish_fast<uint16_t><<<(nu + 127) / 128, 128, 0, ctx->stream>>>(offsets, u0, nu, N, nslots, nullptr, first_frames,
+                                                                                       bp, Bpad, maxT, scores, best_word, best_score,
+                                                                                       scores_out, best_path);
+        else
+            k_viterbi_finish<uint16_t><<<(nu + 127) / 128, 128, 0, ctx->stream>>>(offsets, u0, nu, N, nslots, nullptr, first_frames, bp,
+                                                                                  Bpad, maxT, scores, best_word, best_score,
+                                                                                  scores_out, M, best_path, all_paths, total_frames);
     }
     SAPR_LAUNCH_CHECK(ctx);
     return SAPR_OK;
@@ -258,9 +329,14 @@ static int launch_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx
         SAPR_LAUNCH_CHECK(ctx);
         {
             ProfScope ps(ctx, 1);
-            k_viterbi_finish<BP><<<(nu + 127) / 128, 128, 0, ctx->stream>>>(
-                offsets, u0, nu, m->N, nslots, model_of_utt, first_frames, bp, Bpad, Tm, sc_ws, best_word, best_score,
-                scores, m->M, best_path, all_paths, total_frames);
+            if (!all_paths)
+                k_viterbi_finish_fast<BP><<<(nu + 127) / 128, 128, 0, ctx->stream>>>(
+                    offsets, u0, nu, m->N, nslots, model_of_utt, first_frames, bp, Bpad, Tm, sc_ws, best_word, best_score,
+                    scores, best_path);
+            else
+                k_viterbi_finish<BP><<<(nu + 127) / 128, 128, 0, ctx->stream>>>(
+                    offsets, u0, nu, m->N, nslots, model_of_utt, first_frames, bp, Bpad, Tm, sc_ws, best_word, best_score,
+                    scores, m->M, best_path, all_paths, total_frames);
         }
         SAPR_LAUNCH_CHECK(ctx);
     }
