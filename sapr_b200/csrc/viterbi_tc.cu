@@ -27,6 +27,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 #define TC_ROWS 128
@@ -73,6 +75,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE:\n\t}"
         ::"r"(bar), "r"(parity), "r"(2000u) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t e;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(e));
+    return e != 0;
+}
 // keeps a per-thread constant in its register (stops the compiler from re-deriving it from %tid in the hot loop)
 __device__ __forceinline__ uint32_t pin_reg(uint32_t v) {
     asm volatile("mov.u32 %0, %0;" : "+r"(v));
@@ -117,6 +124,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
                  : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+                 "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -252,6 +264,7 @@ struct TcParams {
     uint16_t *bp; int64_t Bpad; int maxT; double *scores; float *dbgE;   // dbgE: [sum_T][ncols] or null
     long long *trace;           // [TC_TRACE_ROLES][TC_TRACE_FRAMES][TC_TRACE_EVENTS] or null
     int Fshift, nst_shift;      // raw ring: 2^Fshift frames per stage, 2^nst_shift stages
+    int mod0[TC_GROUPS], nmod[TC_GROUPS], pair0[TC_GROUPS], npair[TC_GROUPS];   // per worker group: models, chunk pairs
     uint32_t rstride;           // bytes per row per stage (F * row bytes + pad, an odd multiple of 16)
 };
 
@@ -264,8 +277,8 @@ __host__ __device__ inline TcSmem tc_smem_layout(int M, int nck, int ncols, int 
     L.raw = (uint32_t)2 * (ncols / 8) * nck * 128;
     L.tr = L.raw + (uint32_t)nst * TC_ROWS * rstride;
     L.sb = L.tr + (uint32_t)M * 5 * 16;
-    L.base = (L.sb + (uint32_t)8 * nck * 4 + 15u) & ~15u;            // float64 renormalisation offsets [3][TC_WORKERS]
-    L.bar = L.base + 3u * TC_WORKERS * 8u;
+    L.base = 0;
+    L.bar = (L.sb + (uint32_t)8 * nck * 4 + 15u) & ~15u;
     L.total = L.bar + (2 * TC_MAX_STAGES + 6) * 8 + 16;
     return L;
 }
@@ -318,24 +331,21 @@ __device__ __forceinline__ uint32_t vit_step(float2 (&U)[4], float &Ux, const fl
     return (~sb) & 0x1FFu;
 }
 
-// renormalise (fp32 stays at O(1) magnitudes); the offset is accumulated in float64 in shared memory
-__device__ __forceinline__ void vit_renorm(float2 (&U)[4], float &Ux, uint32_t base_addr) {
+// renormalise (fp32 stays at O(1) magnitudes).  The shift is the maximum rounded to an integer, so the running offset
+// is an integer-valued float that accumulates exactly (|offset| < 2^24) -- no float64 in the hot loop.
+__device__ __forceinline__ void vit_renorm(float2 (&U)[4], float &Ux, float &base) {
     float mx = fmaxf(fmaxf(U[0].x, U[0].y), Ux);
     mx = fmaxf(fmaxf(U[1].x, U[1].y), mx);
     mx = fmaxf(fmaxf(U[2].x, U[2].y), mx);
     mx = fmaxf(fmaxf(U[3].x, U[3].y), mx);
-    if (mx > -INFINITY && mx < INFINITY) {
-        const float2 m2 = make_float2(mx, mx);
-        U[0] = sub2(U[0], m2);
-        U[1] = sub2(U[1], m2);
-        U[2] = sub2(U[2], m2);
-        U[3] = sub2(U[3], m2);
-        Ux -= mx;
-        double b;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b) : "r"(base_addr));
-        b += (double)mx;
-        asm volatile("st.shared.f64 [%0], %1;" ::"r"(base_addr), "d"(b) : "memory");
-    }
+    mx = rintf(fminf(fmaxf(mx, -4194304.f), 4194304.f));      // -inf (nothing reachable yet) shifts by a finite amount
+    const float2 m2 = make_float2(mx, mx);
+    U[0] = sub2(U[0], m2);
+    U[1] = sub2(U[1], m2);
+    U[2] = sub2(U[2], m2);
+    U[3] = sub2(U[3], m2);
+    Ux -= mx;
+    base += mx;
 }
 
 // TRACE: CTA 0 records clock64() at its pipeline events for the first TC_TRACE_FRAMES frames (tuning aid, SAPR_TC_TRACE=file)
@@ -358,7 +368,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
     uint64_t *sBar = reinterpret_cast<uint64_t *>(smem + L.bar);
     uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 2 * TC_MAX_STAGES + 6);
     const uint32_t barRaw_full = smem_u32(sBar), barRaw_empty = barRaw_full + 8 * TC_MAX_STAGES;
-    const uint32_t barA_full = barRaw_empty + 8 * TC_MAX_STAGES, barAcc_full = barA_full + 16;
+    const uint32_t barA_full = barRaw_empty + 8 * TC_MAX_STAGES, barAcc_full = barA_full + 24;   // A_full[3], acc_full[2]
 
     {   // stage the constant images
         const uint4 *src = reinterpret_cast<const uint4 *>(p.wimg);
@@ -374,16 +384,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
             mbar_init(barRaw_full + 8 * s, 32 * TC_LOADERS);
             mbar_init(barRaw_empty + 8 * s, TC_WORKER_WARPS);
         }
-        for (int s = 0; s < 2; s++) {
-            mbar_init(barA_full + 8 * s, TC_WORKER_WARPS);
-            mbar_init(barAcc_full + 8 * s, 1);
-        }
+        for (int s = 0; s < 3; s++) mbar_init(barA_full + 8 * s, TC_WORKER_WARPS);
+        for (int s = 0; s < 2; s++) mbar_init(barAcc_full + 8 * s, 1);
         fence_barrier_init();
     }
-    // TMEM: two accumulator buffers of ncols columns, two A-operand buffers of 8*nck columns (hi 4*nck | lo 4*nck)
+    // TMEM: two accumulator buffers of ncols columns, three A-operand buffers of 8*nck columns (per K step: hi 8 | lo 8)
     const uint32_t a_cols = 8u * nck;
     uint32_t tcols = 32;
-    while (tcols < 2u * ncols + 2u * a_cols) tcols <<= 1;
+    while (tcols < 2u * ncols + 3u * a_cols) tcols <<= 1;
     if (warp == TC_WORKER_WARPS) tmem_alloc(smem_u32(sTmem), tcols);
     fence_proxy_async();            // W image written with generic stores, read by the tensor core
     tc_fence_before();
@@ -458,39 +466,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
         const uint32_t sboW = (uint32_t)nck * 128u;
         const uint64_t dW_hi = make_desc(sW_hi, 128, sboW), dW_lo = make_desc(sW_lo, 128, sboW);
         const int nks = nck / 2;
+        uint32_t a3 = 0, aph = 0;      // A-operand stage (frame counter mod 3) and its barrier phase
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int Tt = tile_frames(tile);
             for (int t = 0; t < Tt; t++, f++) {
                 const uint32_t s = f & 1, ph = (f >> 1) & 1;
                 trace(0, f, 0);
-                mbar_wait(barA_full + 8 * s, ph);
+                mbar_wait(barA_full + 8 * a3, aph);
                 trace(0, f, 1);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {      // one elected lane, provably uniform operands: no per-lane issue loop around UTCHMMA
                     const uint32_t d_tmem = tmem_acc + s * (uint32_t)ncols;
-                    const uint32_t a_hi = tmem_a + s * a_cols, a_lo = a_hi + 4u * nck;
+                    const uint32_t a_hi = tmem_a + a3 * a_cols, a_lo = a_hi + 8u;   // K step ks: hi at +16 ks, lo at +16 ks + 8
                     // the two small correction products first: the tensor core truncates the fp32 accumulator on
                     // every step, so the large hi * W_hi partial sums should see as few steps as possible.
                     // One K = 16 step advances A by 8 TMEM columns and the W descriptor by 256 B (16 in its address field).
                     if (NKS > 0) {
 #pragma unroll
-                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_lo + ks * 8, dW_hi + (uint64_t)(16 * ks), idesc, ks > 0);
+                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_lo + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, ks > 0);
 #pragma unroll
-                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 8, dW_lo + (uint64_t)(16 * ks), idesc, 1);
+                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_lo + (uint64_t)(16 * ks), idesc, 1);
 #pragma unroll
-                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 8, dW_hi + (uint64_t)(16 * ks), idesc, 1);
+                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, 1);
                     } else {
                         uint64_t dh = dW_hi, dl = dW_lo;
                         uint32_t a = a_lo;
-                        for (int ks = 0; ks < nks; ks++, a += 8, dh += 16) umma_f16_ts(d_tmem, a, dh, idesc, ks > 0);   // lo * W_hi
+                        for (int ks = 0; ks < nks; ks++, a += 16, dh += 16) umma_f16_ts(d_tmem, a, dh, idesc, ks > 0);   // lo * W_hi
                         a = a_hi;
-                        for (int ks = 0; ks < nks; ks++, a += 8, dl += 16) umma_f16_ts(d_tmem, a, dl, idesc, 1);        // hi * W_lo
+                        for (int ks = 0; ks < nks; ks++, a += 16, dl += 16) umma_f16_ts(d_tmem, a, dl, idesc, 1);        // hi * W_lo
                         a = a_hi; dh = dW_hi;
-                        for (int ks = 0; ks < nks; ks++, a += 8, dh += 16) umma_f16_ts(d_tmem, a, dh, idesc, 1);        // hi * W_hi
+                        for (int ks = 0; ks < nks; ks++, a += 16, dh += 16) umma_f16_ts(d_tmem, a, dh, idesc, 1);        // hi * W_hi
                     }
                     umma_commit(barAcc_full + 8 * s);
                 }
                 __syncwarp();
+                if (++a3 == 3) { a3 = 0; aph ^= 1u; }
                 trace(0, f, 2);
                 if (TRACE) { mbar_wait(barAcc_full + 8 * s, ph); trace(0, f, 3); }
             }
@@ -499,187 +509,192 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
     } else {
         // ===================== workers =====================
         const int q = warp & 3;                      // TMEM lane quadrant this warp may access
-        const int g = warp >> 2;                     // group: which models / which feature chunks
+        const int g = warp >> 2;                     // group: which models / which feature chunk pairs
         const int r = q * 32 + lane;                 // row of the tile = TMEM lane
-        const int mbase = M / TC_GROUPS, mrem = M % TC_GROUPS;
-        const int mbeg = g * mbase + min(g, mrem), mcnt = mbase + (g < mrem ? 1 : 0);
-        int c0 = 0, c1 = 0;                          // feature chunks: the groups with fewer models take the extra ones
-        {
-            const int cbase = nck / TC_GROUPS, crem = nck % TC_GROUPS;
-            int acc = 0;
-            for (int gg = 0; gg < TC_GROUPS; gg++) {
-                const int cnt = cbase + ((TC_GROUPS - 1 - gg) < crem ? 1 : 0);
-                if (gg == g) { c0 = acc; c1 = acc + cnt; }
-                acc += cnt;
-            }
-        }
-        const int nch = c1 - c0;                                       // 0..3 chunks per thread
-        int nrd = 0;                                                   // chunks whose 16 bytes lie inside the feature row
-        for (int c = 0; c < nch; c++) if (4 * (c0 + c) < p.ldx) nrd = c + 1;
+        const int mbeg = p.mod0[g], mcnt = p.nmod[g];                 // this thread's models
+        const int pr0 = p.pair0[g], npr = p.npair[g];                 // this thread's chunk pairs (8 feature dims each)
         const int trole = (warp == 0) ? 2 : (warp == 6) ? 3 : (warp == 15) ? 4 : -1;   // traced worker warps
+        // Phase mixing: groups 0-1 convert frame t+1 and then recurse frame t; groups 2-3 recurse frame t first and
+        // convert frame t+2 (one more A stage ahead).  At any time half of an SM sub-partition's warps are in the
+        // fma-heavy conversion and half in the alu-heavy recursion.
+        const bool rec_first = g >= 2;
+        uint32_t c3 = 0;              // A stage of the next frame this warp converts (frame counter mod 3)
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         // per-thread addresses, pinned in registers
-        const uint32_t ta_hi0 = pin_reg(tmem_a + lane_sel + 4u * c0);              // A hi, stage 0 (stage 1: + a_cols)
+        const uint32_t ta0 = pin_reg(tmem_a + lane_sel + 16u * pr0);               // A operand, stage 0 (stage 1: + a_cols)
         const uint32_t acc0 = pin_reg(tmem_acc + lane_sel + (uint32_t)mbeg * 8u);  // accumulators, stage 0 (stage 1: + ncols)
-        const uint32_t raw0 = pin_reg(smem_u32(sRaw) + (uint32_t)r * rstride + 16u * c0);
-        const uint32_t lo_off = 4u * nck;
+        const uint32_t raw0 = pin_reg(smem_u32(sRaw) + (uint32_t)r * rstride + 32u * pr0);
         const uint32_t trS = pin_reg(smem_u32(sTr) + (uint32_t)mbeg * 80u);
-        const uint32_t sbS = pin_reg(smem_u32(sS) + 16u * c0);
+        const uint32_t sbS = pin_reg(smem_u32(sS) + 32u * pr0);
         const uint32_t sbB = sbS + 16u * nck;
         const size_t bp_model = (size_t)p.maxT * p.Bpad;                 // elements between consecutive models
         const size_t bp_frame = (size_t)p.Bpad;
-        const uint32_t baseS = pin_reg(smem_u32(smem + L.base) + (uint32_t)tid * 8u);   // [k][tid] float64
+        // float4 index (within the row) from which a pair's chunks lie outside the feature row (never read)
+        const int nrd4 = p.ldx / 4 - 2 * pr0;
 
         auto lds4 = [](uint32_t a) -> float4 {
             float4 v;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
             return v;
         };
+        // 4 feature dims: standardise, square, split into fp16 hi / lo.  out[0..3] = hi (x'01, x'23, x'^2 01, x'^2 23), out2 = lo
+        auto split4 = [&](const float4 x, const float4 sc, const float4 of, uint32_t *hi, uint32_t *lo) {
+            const float2 a01 = fma2(make_float2(x.x, x.y), make_float2(sc.x, sc.y), make_float2(of.x, of.y));
+            const float2 a23 = fma2(make_float2(x.z, x.w), make_float2(sc.z, sc.w), make_float2(of.z, of.w));
+            const float2 q01 = mul2(a01, a01), q23 = mul2(a23, a23);
+            hi[0] = pack_h2(a01); hi[1] = pack_h2(a23); hi[2] = pack_h2(q01); hi[3] = pack_h2(q23);
+            lo[0] = pack_h2(sub2(a01, unpack_h2(hi[0]))); lo[1] = pack_h2(sub2(a23, unpack_h2(hi[1])));
+            lo[2] = pack_h2(sub2(q01, unpack_h2(hi[2]))); lo[3] = pack_h2(sub2(q23, unpack_h2(hi[3])));
+        };
 
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int Tt = tile_frames(tile);
-            const int ul = tile * TC_ROWS + r;
-            int64_t off;
-            const int Te = row_frames(ul, off);
-            const bool live = ul < p.nu;
-            const uint32_t sg0 = sg;
+        // NPc / MCc: compile-time pair and model counts of this group (0 = run-time counts, generic model sets)
+        auto run = [&](auto NPc, auto MCc) {
+            constexpr int NPT = decltype(NPc)::value, MCT = decltype(MCc)::value;
+            constexpr int NPMAX = NPT > 0 ? NPT : 2, MCMAX = MCT > 0 ? MCT : MG;
+            const int np = NPT > 0 ? NPT : npr, mc = MCT > 0 ? MCT : mcnt;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int Tt = tile_frames(tile);
+                const int ul = tile * TC_ROWS + r;
+                int64_t off;
+                const int Te = row_frames(ul, off);
+                const bool live = ul < p.nu;
+                const uint32_t sg0 = sg;
 
-            float2 U[MG][4];
-            float Ux[MG];
-            uint16_t *bpt = p.bp + (size_t)mbeg * bp_model + ul;       // back-pointer word of (first model, frame t, this row)
+                float2 U[MCMAX][4];
+                float Ux[MCMAX], base[MCMAX];
+                uint16_t *bpt = p.bp + (size_t)mbeg * bp_model + ul;       // back-pointer word of (first model, frame t, this row)
 #pragma unroll
-            for (int k = 0; k < MG; k++) {
-                Ux[k] = -INFINITY;
-                asm volatile("st.shared.f64 [%0], %1;" ::"r"(baseS + (uint32_t)k * (TC_WORKERS * 8u)), "d"(0.0) : "memory");
+                for (int k = 0; k < MCMAX; k++) {
+                    Ux[k] = -INFINITY; base[k] = 0.f;
 #pragma unroll
-                for (int j = 0; j < 4; j++) U[k][j] = make_float2(-INFINITY, -INFINITY);
-            }
-
-            // frame t of this tile -> standardise, square, split, store into A-operand stage fr & 1
-            auto convert = [&](int t, uint32_t fr) {
-                const int kk = t >> p.Fshift, fi = t & (F - 1);
-                const uint32_t sgk = sg0 + (uint32_t)kk, slot = sgk & (uint32_t)(nst - 1);
-                if (TRACE && trole >= 0) trace(trole, fr, 0);
-                if (fi == 0) mbar_wait(barRaw_full + 8 * slot, (sgk >> p.nst_shift) & 1u);
-                if (TRACE && trole >= 0) trace(trole, fr, 1);
-                const uint32_t rowp = raw0 + slot * stage_bytes + (uint32_t)fi * rowbytes;
-                const bool ok = t < Te;                      // Te == 0 for rows beyond the batch
-                const uint32_t ta = ta_hi0 + (fr & 1u) * a_cols;
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    if (c < nch) {
-                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (ok && c < nrd) x = lds4(rowp + 16u * c);
-                        const float4 sc = lds4(sbS + 16u * c), of = lds4(sbB + 16u * c);
-                        const float2 a01 = fma2(make_float2(x.x, x.y), make_float2(sc.x, sc.y), make_float2(of.x, of.y));
-                        const float2 a23 = fma2(make_float2(x.z, x.w), make_float2(sc.z, sc.w), make_float2(of.z, of.w));
-                        const float2 q01 = mul2(a01, a01), q23 = mul2(a23, a23);
-                        const uint32_t h0 = pack_h2(a01), h1 = pack_h2(a23), h2 = pack_h2(q01), h3 = pack_h2(q23);
-                        const uint32_t l0 = pack_h2(sub2(a01, unpack_h2(h0))), l1 = pack_h2(sub2(a23, unpack_h2(h1)));
-                        const uint32_t l2 = pack_h2(sub2(q01, unpack_h2(h2))), l3 = pack_h2(sub2(q23, unpack_h2(h3)));
-                        tmem_st4(ta + 4u * c, h0, h1, h2, h3);
-                        tmem_st4(ta + lo_off + 4u * c, l0, l1, l2, l3);
-                    }
+                    for (int j = 0; j < 4; j++) U[k][j] = make_float2(-INFINITY, -INFINITY);
                 }
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(barA_full + 8 * (fr & 1u));
-                    if (fi == F - 1 || t == Tt - 1) mbar_arrive(barRaw_empty + 8 * slot);
-                }
-                if (TRACE && trole >= 0) trace(trole, fr, 2);
-            };
-            // accumulators of frame fr ready?  (their release needs no barrier: a warp signals A_full(fr + 2) only after
-            // its last tcgen05.ld of frame fr, and the MMAs of frame fr + 2 wait for every warp's A_full(fr + 2))
-            auto acc_ready = [&](uint32_t fr) -> uint32_t {
-                const uint32_t s = fr & 1u;
-                if (TRACE && trole >= 0) trace(trole, fr, 3);
-                mbar_wait(barAcc_full + 8 * s, (fr >> 1) & 1u);
-                if (TRACE && trole >= 0) trace(trole, fr, 4);
-                tc_fence_after();
-                return acc0 + s * (uint32_t)ncols;
-            };
-            if (Tt > 0) convert(0, f);
-            const int Tearly = min(Tt, 9);
-            int t = 0;
-            // ---- frames 0 .. 8: entry state, closed exit (generic step) ----
-            for (; t < Tearly; t++, f++) {
-                if (t + 1 < Tt) convert(t + 1, f + 1);
-                const uint32_t tacc = acc_ready(f);
-                const bool act = t < Te;
+
+                // frame t of this tile -> standardise, square, split, store into A-operand stage fr & 1
+                auto convert = [&](int t, uint32_t fr) {      // frames are converted in order: c3 tracks fr % 3
+                    const int kk = t >> p.Fshift, fi = t & (F - 1);
+                    const uint32_t sgk = sg0 + (uint32_t)kk, slot = sgk & (uint32_t)(nst - 1);
+                    if (TRACE && trole >= 0) trace(trole, fr, 0);
+                    if (fi == 0) mbar_wait(barRaw_full + 8 * slot, (sgk >> p.nst_shift) & 1u);
+                    if (TRACE && trole >= 0) trace(trole, fr, 1);
+                    const uint32_t rowp = raw0 + slot * stage_bytes + (uint32_t)fi * rowbytes;
+                    const bool ok = t < Te;                      // Te == 0 for rows beyond the batch
+                    const uint32_t ta = ta0 + c3 * a_cols;
 #pragma unroll
-                for (int k = 0; k < MG; k++) {
-                    if (k < mcnt) {
-                        uint32_t ev[8];
-                        tmem_ld8(tacc + 8u * k, ev);
-                        tmem_ld_wait();
-                        if (DBG && p.dbgE && act) {
-                            const float4 st0 = lds4(trS + 80u * k + 48u), st1 = lds4(trS + 80u * k + 64u);
-                            const float st[8] = {st0.x, st0.y, st0.z, st0.w, st1.x, st1.y, st1.z, st1.w};
-#pragma unroll
-                            for (int j = 0; j < 8; j++)
-                                p.dbgE[(size_t)(off + t) * ncols + (mbeg + k) * 8 + j] = __uint_as_float(ev[j]) - st[j];
+                    for (int c = 0; c < NPMAX; c++) {
+                        if (c < np) {
+                            float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+                            if (ok && 2 * c < nrd4) x0 = lds4(rowp + 32u * c);
+                            if (ok && 2 * c + 1 < nrd4) x1 = lds4(rowp + 32u * c + 16u);
+                            uint32_t v[16];      // [hi chunk 0 | hi chunk 1 | lo chunk 0 | lo chunk 1] = 16 consecutive TMEM columns
+                            split4(x0, lds4(sbS + 32u * c), lds4(sbB + 32u * c), v, v + 8);
+                            split4(x1, lds4(sbS + 32u * c + 16u), lds4(sbB + 32u * c + 16u), v + 4, v + 12);
+                            tmem_st16(ta + 16u * c, v);
                         }
-                        if (act) {
-                            const float4 cm = lds4(trS + 80u * k + 32u);
-                            if (t == 0) {
-                                U[k][0].x = cm.y + __uint_as_float(ev[0]);   // U_1 = ln A01 + E[0,1] + ln A11
-                            } else {
-                                const float4 c03 = lds4(trS + 80u * k), c47 = lds4(trS + 80u * k + 16u);
-                                const uint32_t bits = vit_step<true>(U[k], Ux[k], c03, c47, cm.x, cm.y, ev, t);
-                                bpt[(size_t)k * bp_model] = (uint16_t)bits;
-                                if ((t & 3) == 0) vit_renorm(U[k], Ux[k], baseS + (uint32_t)k * (TC_WORKERS * 8u));
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(barA_full + 8 * c3);
+                        if (fi == F - 1 || t == Tt - 1) mbar_arrive(barRaw_empty + 8 * slot);
+                    }
+                    if (++c3 == 3) c3 = 0;
+                    if (TRACE && trole >= 0) trace(trole, fr, 2);
+                };
+                // accumulators of frame fr ready?  (their release needs no barrier: a warp signals A_full(fr + 2) only after
+                // its last tcgen05.ld of frame fr, and the MMAs of frame fr + 2 wait for every warp's A_full(fr + 2))
+                auto acc_ready = [&](uint32_t fr) -> uint32_t {
+                    const uint32_t s = fr & 1u;
+                    if (TRACE && trole >= 0) trace(trole, fr, 3);
+                    mbar_wait(barAcc_full + 8 * s, (fr >> 1) & 1u);
+                    if (TRACE && trole >= 0) trace(trole, fr, 4);
+                    tc_fence_after();
+                    return acc0 + s * (uint32_t)ncols;
+                };
+                auto dbg_dump = [&](int k, int t, const uint32_t (&ev)[8]) {
+                    const float4 st0 = lds4(trS + 80u * k + 48u), st1 = lds4(trS + 80u * k + 64u);
+                    const float st[8] = {st0.x, st0.y, st0.z, st0.w, st1.x, st1.y, st1.z, st1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        p.dbgE[(size_t)(off + t) * ncols + (mbeg + k) * 8 + j] = __uint_as_float(ev[j]) - st[j];
+                };
+
+                if (Tt > 0) convert(0, f);
+                if (rec_first && Tt > 1) convert(1, f + 1);
+                const int Tearly = min(Tt, 9);
+                int t = 0;
+                // ---- frames 0 .. 8: entry state, closed exit (generic step) ----
+                for (; t < Tearly; t++, f++) {
+                    if (!rec_first && t + 1 < Tt) convert(t + 1, f + 1);
+                    const uint32_t tacc = acc_ready(f);
+                    const bool act = t < Te;
+#pragma unroll
+                    for (int k = 0; k < MCMAX; k++) {
+                        if (k < mc) {
+                            uint32_t ev[8];
+                            tmem_ld8(tacc + 8u * k, ev);
+                            tmem_ld_wait();
+                            if (DBG && p.dbgE && act) dbg_dump(k, t, ev);
+                            if (act) {
+                                const float4 cm = lds4(trS + 80u * k + 32u);
+                                if (t == 0) {
+                                    U[k][0].x = cm.y + __uint_as_float(ev[0]);   // U_1 = ln A01 + E[0,1] + ln A11
+                                } else {
+                                    const float4 c03 = lds4(trS + 80u * k), c47 = lds4(trS + 80u * k + 16u);
+                                    const uint32_t bits = vit_step<true>(U[k], Ux[k], c03, c47, cm.x, cm.y, ev, t);
+                                    bpt[(size_t)k * bp_model] = (uint16_t)bits;
+                                    if ((t & 3) == 0) vit_renorm(U[k], Ux[k], base[k]);
+                                }
                             }
                         }
                     }
+                    tc_fence_before();
+                    if (TRACE && trole >= 0) trace(trole, f, 5);
+                    bpt += bp_frame;
+                    if (rec_first && t + 2 < Tt) convert(t + 2, f + 2);
                 }
-                tc_fence_before();
-                bpt += bp_frame;
-            }
-            // ---- steady state: no entry arc, exit open ----
-            for (; t < Tt; t++, f++) {
-                if (t + 1 < Tt) convert(t + 1, f + 1);
-                const uint32_t tacc = acc_ready(f);
-                const bool act = t < Te;
-                const bool rn = (t & 3) == 0;
+                // ---- steady state: no entry arc, exit open ----
+                for (; t < Tt; t++, f++) {
+                    if (!rec_first && t + 1 < Tt) convert(t + 1, f + 1);
+                    const uint32_t tacc = acc_ready(f);
+                    const bool act = t < Te;
+                    const bool rn = (t & 3) == 0;
 #pragma unroll
-                for (int k = 0; k < MG; k++) {
-                    if (k < mcnt) {
-                        uint32_t ev[8];
-                        tmem_ld8(tacc + 8u * k, ev);
-                        tmem_ld_wait();
-                        if (DBG && p.dbgE && act) {
-                            const float4 st0 = lds4(trS + 80u * k + 48u), st1 = lds4(trS + 80u * k + 64u);
-                            const float st[8] = {st0.x, st0.y, st0.z, st0.w, st1.x, st1.y, st1.z, st1.w};
-#pragma unroll
-                            for (int j = 0; j < 8; j++)
-                                p.dbgE[(size_t)(off + t) * ncols + (mbeg + k) * 8 + j] = __uint_as_float(ev[j]) - st[j];
-                        }
-                        if (act) {
-                            const float4 c03 = lds4(trS + 80u * k), c47 = lds4(trS + 80u * k + 16u), cm = lds4(trS + 80u * k + 32u);
-                            const uint32_t bits = vit_step<false>(U[k], Ux[k], c03, c47, cm.x, cm.y, ev, t);
-                            bpt[(size_t)k * bp_model] = (uint16_t)bits;
-                            if (rn) vit_renorm(U[k], Ux[k], baseS + (uint32_t)k * (TC_WORKERS * 8u));
+                    for (int k = 0; k < MCMAX; k++) {
+                        if (k < mc) {
+                            uint32_t ev[8];
+                            tmem_ld8(tacc + 8u * k, ev);
+                            tmem_ld_wait();
+                            if (DBG && p.dbgE && act) dbg_dump(k, t, ev);
+                            if (act) {
+                                const float4 c03 = lds4(trS + 80u * k), c47 = lds4(trS + 80u * k + 16u), cm = lds4(trS + 80u * k + 32u);
+                                const uint32_t bits = vit_step<false>(U[k], Ux[k], c03, c47, cm.x, cm.y, ev, t);
+                                bpt[(size_t)k * bp_model] = (uint16_t)bits;
+                                if (rn) vit_renorm(U[k], Ux[k], base[k]);
+                            }
                         }
                     }
+                    tc_fence_before();
+                    if (TRACE && trole >= 0) trace(trole, f, 5);
+                    bpt += bp_frame;
+                    if (rec_first && t + 2 < Tt) convert(t + 2, f + 2);
                 }
-                tc_fence_before();
-                if (TRACE && trole >= 0) trace(trole, f, 5);
-                bpt += bp_frame;
-            }
-            sg = sg0 + (uint32_t)((Tt + F - 1) >> p.Fshift);
-            if (live) {
+                sg = sg0 + (uint32_t)((Tt + F - 1) >> p.Fshift);
+                if (live) {
 #pragma unroll
-                for (int k = 0; k < MG; k++)
-                    if (k < mcnt) {
-                        double b;
-                        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b) : "r"(baseS + (uint32_t)k * (TC_WORKERS * 8u)));
-                        const double sc = (Te > 0 && Ux[k] > -INFINITY) ? (double)Ux[k] + b : -INFINITY;
-                        p.scores[(size_t)ul * M + mbeg + k] = sc;
-                    }
+                    for (int k = 0; k < MCMAX; k++)
+                        if (k < mc) {
+                            const double sc = (Te > 0 && Ux[k] > -INFINITY) ? (double)Ux[k] + (double)base[k] : -INFINITY;
+                            p.scores[(size_t)ul * M + mbeg + k] = sc;
+                        }
+                }
             }
-        }
+        };
+        // the cfg-2 split (M = 11, D = 39): group 0 = 2 chunk pairs + 2 models, groups 1-3 = 1 pair + 3 models
+        if (MG == 3 && npr == 2 && mcnt == 2) run(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{});
+        else if (MG == 3 && npr == 1 && mcnt == 3) run(std::integral_constant<int, 1>{}, std::integral_constant<int, 3>{});
+        else run(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
     }
     tc_fence_before();
     __syncthreads();
@@ -786,6 +801,23 @@ int sapr_viterbi_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
         prm.sb = (const float *)((const char *)m->tc_image + w); prm.trp = (const float4 *)((const char *)m->tc_image + w + g);
         prm.bp = bp; prm.Bpad = Bpad; prm.maxT = Tm; prm.scores = sc_ws; prm.dbgE = dbgE;
         prm.Fshift = Fshift; prm.nst_shift = nst_shift; prm.rstride = rstride; prm.trace = nullptr;
+        {   // split chunk pairs and models over the 4 worker groups so that 30 * chunks + 60 * models is balanced:
+            // pairs go to the low groups first, models to the high groups first
+            const int npairs = nck / 2;
+            int pc[TC_GROUPS], mcn[TC_GROUPS];
+            for (int gI = 0; gI < TC_GROUPS; gI++) { pc[gI] = npairs / TC_GROUPS + (gI < npairs % TC_GROUPS ? 1 : 0); mcn[gI] = 0; }
+            for (int mI = 0; mI < M; mI++) {      // next model to the group with the least work so far (ties: highest group)
+                int best = TC_GROUPS - 1;
+                for (int gI = TC_GROUPS - 1; gI >= 0; gI--)
+                    if (mcn[gI] < MG && (mcn[best] >= MG || 60 * pc[gI] + 60 * mcn[gI] < 60 * pc[best] + 60 * mcn[best])) best = gI;
+                mcn[best]++;
+            }
+            int pa = 0, ma = 0;
+            for (int gI = 0; gI < TC_GROUPS; gI++) {
+                prm.pair0[gI] = pa; prm.npair[gI] = pc[gI]; pa += pc[gI];
+                prm.mod0[gI] = ma; prm.nmod[gI] = mcn[gI]; ma += mcn[gI];
+            }
+        }
         const char *trace_path = getenv("SAPR_TC_TRACE");
         if (trace_path && MG == 3 && !dbgE && u0 == 0) {      // tuning aid: one traced launch, timestamps to a text file
             const size_t nrec = (size_t)TC_TRACE_ROLES * TC_TRACE_FRAMES * TC_TRACE_EVENTS;
