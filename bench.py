@@ -221,13 +221,24 @@ def main():
     utt_per_launch = B * args.steps / max(k_n, 1)
     k_avg_ms = k_ms / max(k_n, 1)
     achieved = ALG_BYTES_PER_UTT * utt_per_launch / (k_avg_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_viterbi_fused<float,u16,8>", "achieved": achieved, "peak": peak,
+    tc = prec == engine.FP32 and os.environ.get("SAPR_TC", "1") != "0"
+    kname = "k_viterbi_tc<3,5> (tcgen05 emission, TMEM-resident operands, fused max-product recursion)" if tc \
+        else "k_viterbi_fused<R,u16,8> (SIMT emission)"
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp)).get("k_viterbi_tc" if tc else "k_viterbi_fused")
+        if tj:
+            traffic = tj["dram_bytes_per_launch"] / tj["utterances_per_launch"] * utt_per_launch
+            traffic_src = tj["source"]
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                 "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback",
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "launches": k_n,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "launches": k_n,
                 "avg_launch_ms": k_avg_ms, "alg_bytes_per_launch": ALG_BYTES_PER_UTT * utt_per_launch,
                 "kernel_share_of_step": k_ms / (ms_per_step * args.steps),
                 "finish_kernel_ms_per_step": f_ms / args.steps,
-                "note": "SIMT fp32 emission: FMA-issue bound (SURVEY 8d), not yet HBM bound"}
+                "note": ("instruction-issue bound (conversion + recursion share the SM sub-partitions' issue slots); "
+                         "features are read once from HBM") if tc else "SIMT fp32 emission: FMA-issue bound (SURVEY 8d)"}
 
     # ---- end to end through the host-buffer C-ABI call (pinned host features) ----
     e2e = None
