@@ -123,6 +123,8 @@ int sapr_tc_prepare(sapr_models *m);
 int sapr_viterbi_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int B,
                            int64_t total_frames, int max_T, int first_frames, int32_t *best_word, double *best_score,
                            double *scores, uint8_t *best_path, uint8_t *all_paths, float *dbgE);
+int sapr_estep_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int B, int max_T,
+                         const int32_t *order, const int32_t *model_start, float *gamma, float *ustats, double *loglik);
 int sapr_emission_into(sapr_ctx *ctx, sapr_models *m, int mi, const float *X, int ldx, const int64_t *offsets, int B,
                        int64_t total_frames, double *E);
 

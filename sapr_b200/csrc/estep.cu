@@ -14,6 +14,8 @@
 //                 one utterance, float64 across utterances, fixed-order reduction across CTAs.
 // k_stats_reduce  deterministic reduction of the per-tile partials into the packed stats block.
 // k_mstep_diag    A_ii = Xi/G, means, variances with the reference's floor.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 template <typename R> struct alignas(16) Vec4e { R x, y, z, w; };
@@ -415,6 +417,26 @@ static int launch_estep(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, 
         if ((rc = sapr_ws_reserve(ctx, 3, sizeof(R) * (size_t)total_frames * N))) return rc;
         gamma = (R *)ctx->ws[3];
     }
+    const int upc = std::max(8, std::min(256, B / (4 * ctx->sm_count)));
+    const int ntile_max = (B + upc - 1) / upc + M;
+    if ((rc = sapr_ws_reserve(ctx, 4, sizeof(double) * (size_t)ntile_max * 2 * N * Dp))) return rc;
+    double *partial = (double *)ctx->ws[4];
+    bool tc_done = false;
+    if (std::is_same<R, float>::value && m->tc_image && sapr_tc_eligible(m)) {
+        // production fp32 path: emission on the tensor cores, forward and backward sweep of a tile in one persistent CTA
+        const char *env = getenv("SAPR_TC");
+        if (!env || env[0] != '0') {
+            if ((rc = sapr_ws_reserve(ctx, 1, sizeof(float) * (size_t)B * 3 * N))) return rc;
+            if ((rc = sapr_estep_tc_launch(ctx, m, X, ldx, offsets, B, max_T, order, model_start, (float *)gamma,
+                                           (float *)ctx->ws[1], loglik)))
+                return rc;
+            k_reduce_triples<float><<<dim3(3 * N, M), 256, 0, ctx->stream>>>(model_start, N, S, (const float *)ctx->ws[1], 0, B,
+                                                                             stats, stride);
+            SAPR_LAUNCH_CHECK(ctx);
+            tc_done = true;
+        }
+    }
+    if (!tc_done) {
     // forward/backward lattice scratch, chunked over pairs so it stays bounded (<= ~1 GB)
     const size_t per_pair = (size_t)max_T * N * sizeof(R) * 2;
     int chunk = (int)std::min<int64_t>(B, std::max<int64_t>(128, ((int64_t)1 << 30) / (int64_t)per_pair));
@@ -424,10 +446,6 @@ static int launch_estep(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, 
     R *scr_alpha = (R *)ctx->ws[0];
     R *scr_e = scr_alpha + (size_t)chunk * max_T * N;
     R *ustats = (R *)ctx->ws[1];
-    const int upc = std::max(8, std::min(256, B / (4 * ctx->sm_count)));
-    const int ntile_max = (B + upc - 1) / upc + M;
-    if ((rc = sapr_ws_reserve(ctx, 4, sizeof(double) * (size_t)ntile_max * 2 * N * Dp))) return rc;
-    double *partial = (double *)ctx->ws[4];
 
     const R *pk = std::is_same<R, float>::value ? (const R *)m->pk32 : (const R *)m->pk64;
     const R *cst = std::is_same<R, float>::value ? (const R *)m->cst32 : (const R *)m->cst64;
@@ -449,6 +467,7 @@ static int launch_estep(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, 
         // the small per-utterance triples are folded into stats chunk by chunk (fixed order)
         k_reduce_triples<R><<<dim3(3 * N, M), 256, 0, ctx->stream>>>(model_start, N, S, ustats, p0, np, stats, stride);
         SAPR_LAUNCH_CHECK(ctx);
+    }
     }
     // feature statistics over the whole batch
     const int ntiles = ntile_max;

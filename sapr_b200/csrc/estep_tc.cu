@@ -1,0 +1,512 @@
+// estep_tc.cu -- Baum-Welch E-step (forward, backward, gamma, xi sums) with the emission on the tensor cores.
+//
+// Replaces custom_hmm.py:417-439 (compute_emission_matrix, forward, backward, compute_gamma, compute_xi and the
+// accumulators of baum_welch) for every utterance against its own word model, fp32 production mode.  Same machine
+// mapping as viterbi_tc.cu: a tile is 128 utterances at the same frame index, the diagonal-Gaussian log-density of
+// one frame is the contraction [x', x'^2, 1] . W on tcgen05 (A operand written into TMEM by the threads that own
+// the rows, W in shared memory, fp32 accumulators in TMEM), raw features arrive through a cp.async.bulk ring.
+//
+// Differences from the Viterbi kernel:
+//   * utterances are visited in model order (order[] grouped by word, every model's group padded to a multiple of
+//     32 rows), so the 32 rows of a TMEM lane quadrant share ONE model and a tile spans one or two adjacent
+//     models: the MMA is N = 16 (two models' states) instead of N = 96;
+//   * a persistent CTA sweeps its tile FORWARD (alpha-hat rows go to an L2-resident per-CTA scratch,
+//     [frame][state][row], 4 KB per frame) and then BACKWARD over the same tile (features are fetched a second time,
+//     emissions recomputed on the tensor core, beta / gamma / xi on the fly); only sum_t gamma, sum_t xi(j,j),
+//     gamma_t (for the feature statistics) and the log-likelihood leave the CTA;
+//   * warp roles: warps 0-3 run the recursions (one thread per utterance: the left-to-right chain of 8 states is
+//     register resident, log-sum-exp in the forward sweep, max-normalised linear sums in the backward sweep),
+//     warps 4-15 standardise / square / split the features into the A operand, warp 16 issues the MMAs,
+//     warps 17-19 issue the bulk copies.
+#include "tc_common.cuh"
+
+#define ET_REC_WARPS 4
+#define ET_CONV_WARPS (TC_WORKER_WARPS - ET_REC_WARPS)
+
+struct EtParams {
+    const float *X; int ldx; const int64_t *offsets; int B;
+    const int32_t *order; const int32_t *model_start;       // utterance ids grouped by model; [M+1] group starts
+    int M, D, nck, ncols;
+    const __half *wimg; const float *sb; const float4 *trp;
+    float *scratch; int maxT;                                // alpha-hat: [grid][maxT][8][128]
+    float *gamma;                                            // [sum_T][8]
+    float *ustats;                                           // [B][24] by position in order[]: G | Xi | occ
+    double *loglik;                                          // [B] by utterance id
+    int Fshift, nst_shift; uint32_t rstride;
+    int pair0[TC_GROUPS], npair[TC_GROUPS];                  // chunk pairs of the converting groups (group 0: none)
+};
+
+struct EtSmem { uint32_t w, raw, tr, sb, pad, bar, total; };
+__host__ __device__ inline EtSmem et_smem_layout(int M, int nck, int ncols, int nst, uint32_t rstride) {
+    EtSmem L;
+    L.w = 0;
+    L.raw = (uint32_t)2 * (ncols / 8) * nck * 128;
+    L.tr = L.raw + (uint32_t)nst * TC_ROWS * rstride;
+    L.sb = L.tr + (uint32_t)M * 5 * 16;
+    L.pad = (L.sb + (uint32_t)8 * nck * 4 + 15u) & ~15u;        // int pad_start[16], cnt[16]
+    L.bar = L.pad + 32 * 4;
+    L.total = L.bar + (2 * TC_MAX_STAGES + 10) * 8 + 16;
+    return L;
+}
+
+// log(exp(x) + exp(y)), fp32 production form
+__device__ __forceinline__ float lae32(float x, float y) {
+    const float m = fmaxf(x, y);
+    if (m == -INFINITY) return m;
+    return m + __logf(1.0f + __expf(-fabsf(x - y)));
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int nck = p.nck, ncols = p.ncols, M = p.M;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int F = 1 << p.Fshift, nst = 1 << p.nst_shift;
+    const uint32_t rowbytes = (uint32_t)p.ldx * 4u, rstride = p.rstride, stage_bytes = TC_ROWS * rstride;
+    const EtSmem L = et_smem_layout(M, nck, ncols, nst, rstride);
+    const uint32_t w_plane = (uint32_t)(ncols / 8) * nck * 128;
+    unsigned char *sW = smem + L.w;
+    unsigned char *sRaw = smem + L.raw;
+    const float4 *sTr = reinterpret_cast<const float4 *>(smem + L.tr);
+    const float4 *sS = reinterpret_cast<const float4 *>(smem + L.sb);
+    int *sPad = reinterpret_cast<int *>(smem + L.pad);          // pad_start[0..M], then cnt[0..M-1] at +16
+    uint64_t *sBar = reinterpret_cast<uint64_t *>(smem + L.bar);
+    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 2 * TC_MAX_STAGES + 10);
+    const uint32_t barRaw_full = smem_u32(sBar), barRaw_empty = barRaw_full + 8 * TC_MAX_STAGES;
+    const uint32_t barA_full = barRaw_empty + 8 * TC_MAX_STAGES, barA_free = barA_full + 24;   // [3], [3]
+    const uint32_t barAcc_full = barA_free + 24, barAcc_empty = barAcc_full + 16;               // [2], [2]
+
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.wimg);
+        uint4 *dst = reinterpret_cast<uint4 *>(sW);
+        for (uint32_t i = tid; i < 2 * w_plane / 16; i += TC_THREADS) dst[i] = src[i];
+        float4 *dtr = reinterpret_cast<float4 *>(smem + L.tr);
+        for (int i = tid; i < M * 5; i += TC_THREADS) dtr[i] = p.trp[i];
+        float *dsb = reinterpret_cast<float *>(smem + L.sb);
+        for (int i = tid; i < 8 * nck; i += TC_THREADS) dsb[i] = p.sb[i];
+    }
+    if (tid == 0) {
+        int acc = 0;
+        for (int m = 0; m < M; m++) {
+            const int cnt = p.model_start[m + 1] - p.model_start[m];
+            sPad[m] = acc; sPad[16 + m] = cnt;
+            acc += (cnt + 31) / 32 * 32;
+        }
+        sPad[M] = acc;
+        for (int s = 0; s < nst; s++) {
+            mbar_init(barRaw_full + 8 * s, 32 * TC_LOADERS);
+            mbar_init(barRaw_empty + 8 * s, ET_CONV_WARPS);
+        }
+        for (int s = 0; s < 3; s++) { mbar_init(barA_full + 8 * s, ET_CONV_WARPS); mbar_init(barA_free + 8 * s, 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(barAcc_full + 8 * s, 1); mbar_init(barAcc_empty + 8 * s, ET_REC_WARPS); }
+        fence_barrier_init();
+    }
+    const uint32_t a_cols = 8u * nck;
+    uint32_t tcols = 32;
+    while (tcols < 2u * ncols + 3u * a_cols) tcols <<= 1;
+    if (warp == TC_WORKER_WARPS) tmem_alloc(smem_u32(sTmem), tcols);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sTmem;
+    const uint32_t tmem_acc = tmem_base, tmem_a = tmem_base + 2u * ncols;   // 2 accumulator stages (N <= ncols), then 3 A stages
+
+    const int total_pad = sPad[M];
+    const int ntiles = (total_pad + TC_ROWS - 1) / TC_ROWS;
+
+    // padded row -> (model, utterance id or -1, frames)
+    auto row_info = [&](int prow, int &m, int &pos, int64_t &off) -> int {
+        m = 0; pos = -1; off = 0;
+        if (prow >= total_pad) { m = M - 1; return 0; }
+        while (m + 1 < M && prow >= sPad[m + 1]) m++;
+        const int idx = prow - sPad[m];
+        if (idx >= sPad[16 + m]) return 0;
+        pos = p.model_start[m] + idx;
+        const int u = p.order[pos];
+        off = p.offsets[u];
+        return (int)(p.offsets[u + 1] - off);
+    };
+    auto tile_frames = [&](int tile) -> int {
+        int Tt = 0;
+        for (int r = lane; r < TC_ROWS; r += 32) {
+            int m, pos; int64_t o;
+            Tt = max(Tt, row_info(tile * TC_ROWS + r, m, pos, o));
+        }
+        for (int o = 16; o > 0; o >>= 1) Tt = max(Tt, __shfl_xor_sync(0xffffffffu, Tt, o));
+        return Tt;
+    };
+    // models a tile spans -> first model whose states the MMA covers, and N (16 .. ncols)
+    auto tile_models = [&](int tile, int &mbase) -> int {
+        int mf = 0, ml = 0;
+        const int r0 = tile * TC_ROWS, r1 = min(r0 + TC_ROWS, total_pad) - 1;
+        while (mf + 1 < M && r0 >= sPad[mf + 1]) mf++;
+        ml = mf;
+        while (ml + 1 < M && r1 >= sPad[ml + 1]) ml++;
+        const int n = ((ml - mf + 1) * 8 + 15) / 16 * 16;
+        mbase = min(mf, (ncols - n) / 8);
+        return n;
+    };
+
+    uint32_t f = 0, sg = 0;
+
+    if (warp > TC_WORKER_WARPS) {
+        // ===================== bulk-copy producers: forward sweep, then backward sweep of every tile =====================
+        constexpr int RPL = (TC_ROWS + TC_LOADERS - 1) / TC_LOADERS;
+        const int lw = warp - TC_WORKER_WARPS - 1;
+        const int rlo = lw * RPL, rhi = min(rlo + RPL, TC_ROWS);
+        const int rr[2] = {rlo + lane, rlo + lane + 32};
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int Tt = tile_frames(tile);
+            const int nsg = (Tt + F - 1) >> p.Fshift;
+            int Te[2]; int64_t off[2];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                int m, pos;
+                Te[i] = (rr[i] < rhi) ? row_info(tile * TC_ROWS + rr[i], m, pos, off[i]) : 0;
+                if (rr[i] >= rhi) off[i] = 0;
+            }
+            for (int phase = 0; phase < 2; phase++)
+                for (int k = 0; k < nsg; k++, sg++) {
+                    const uint32_t slot = sg & (uint32_t)(nst - 1), ph = (sg >> p.nst_shift) & 1u;
+                    const uint32_t bar = barRaw_full + 8 * slot;
+                    int lo[2], nf[2];
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        if (phase == 0) { lo[i] = k * F; nf[i] = min(max(Te[i] - k * F, 0), F); }
+                        else { const int hi = Te[i] - k * F; lo[i] = max(hi - F, 0); nf[i] = max(hi, 0) - lo[i]; }
+                    }
+                    mbar_wait(barRaw_empty + 8 * slot, ph ^ 1u);
+                    mbar_arrive_tx(bar, (uint32_t)(nf[0] + nf[1]) * rowbytes);
+#pragma unroll
+                    for (int i = 0; i < 2; i++)
+                        if (nf[i] > 0)
+                            bulk_g2s(smem_u32(sRaw) + slot * stage_bytes + (uint32_t)rr[i] * rstride,
+                                     p.X + (size_t)(off[i] + lo[i]) * p.ldx, (uint32_t)nf[i] * rowbytes, bar);
+                }
+        }
+    } else if (warp == TC_WORKER_WARPS) {
+        // ===================== MMA issuer =====================
+        const uint32_t sW_hi = smem_u32(sW), sW_lo = sW_hi + w_plane;
+        const uint32_t sboW = (uint32_t)nck * 128u;
+        const int nks = nck / 2;
+        uint32_t a3 = 0, aph = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int Tt = tile_frames(tile);
+            int mbase;
+            const int n = tile_models(tile, mbase);
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+            const uint64_t dW_hi = make_desc(sW_hi + (uint32_t)mbase * sboW, 128, sboW);
+            const uint64_t dW_lo = make_desc(sW_lo + (uint32_t)mbase * sboW, 128, sboW);
+            for (int t = 0; t < 2 * Tt; t++, f++) {
+                const uint32_t s = f & 1, ph = (f >> 1) & 1;
+                mbar_wait(barA_full + 8 * a3, aph);
+                mbar_wait(barAcc_empty + 8 * s, ph ^ 1u);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t d_tmem = tmem_acc + s * (uint32_t)ncols;
+                    const uint32_t a_hi = tmem_a + a3 * a_cols, a_lo = a_hi + 8u;
+                    uint64_t dh = dW_hi, dl = dW_lo;
+                    uint32_t a = a_lo;
+                    for (int ks = 0; ks < nks; ks++, a += 16, dh += 16) umma_f16_ts(d_tmem, a, dh, idesc, ks > 0);   // lo * W_hi
+                    a = a_hi;
+                    for (int ks = 0; ks < nks; ks++, a += 16, dl += 16) umma_f16_ts(d_tmem, a, dl, idesc, 1);        // hi * W_lo
+                    a = a_hi; dh = dW_hi;
+                    for (int ks = 0; ks < nks; ks++, a += 16, dh += 16) umma_f16_ts(d_tmem, a, dh, idesc, 1);        // hi * W_hi
+                    umma_commit(barAcc_full + 8 * s);
+                    umma_commit(barA_free + 8 * a3);
+                }
+                __syncwarp();
+                if (++a3 == 3) { a3 = 0; aph ^= 1u; }
+            }
+        }
+    } else {
+        const int q = warp & 3, g = warp >> 2, r = q * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        auto lds4 = [](uint32_t a) -> float4 {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+            return v;
+        };
+        if (g > 0) {
+            // ===================== converters: features -> A operand in TMEM =====================
+            const int pr0 = p.pair0[g], npr = p.npair[g];
+            const uint32_t ta0 = tmem_a + lane_sel + 16u * pr0;
+            const uint32_t raw0 = smem_u32(sRaw) + (uint32_t)r * rstride + 32u * pr0;
+            const uint32_t sbS = smem_u32(sS) + 32u * pr0, sbB = sbS + 16u * nck;
+            const int nrd4 = p.ldx / 4 - 2 * pr0;
+            uint32_t c3 = 0, cph = 0;
+            auto split4 = [&](const float4 x, const float4 sc, const float4 of, uint32_t *hi, uint32_t *lo) {
+                const float2 a01 = fma2(make_float2(x.x, x.y), make_float2(sc.x, sc.y), make_float2(of.x, of.y));
+                const float2 a23 = fma2(make_float2(x.z, x.w), make_float2(sc.z, sc.w), make_float2(of.z, of.w));
+                const float2 q01 = mul2(a01, a01), q23 = mul2(a23, a23);
+                hi[0] = pack_h2(a01); hi[1] = pack_h2(a23); hi[2] = pack_h2(q01); hi[3] = pack_h2(q23);
+                lo[0] = pack_h2(sub2(a01, unpack_h2(hi[0]))); lo[1] = pack_h2(sub2(a23, unpack_h2(hi[1])));
+                lo[2] = pack_h2(sub2(q01, unpack_h2(hi[2]))); lo[3] = pack_h2(sub2(q23, unpack_h2(hi[3])));
+            };
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int Tt = tile_frames(tile);
+                const int nsg = (Tt + F - 1) >> p.Fshift;
+                int m, pos; int64_t off;
+                const int Te = row_info(tile * TC_ROWS + r, m, pos, off);
+                for (int phase = 0; phase < 2; phase++) {
+                    for (int tau = 0; tau < Tt; tau++, f++) {
+                        const int kk = tau >> p.Fshift, fi = tau & (F - 1);
+                        const uint32_t slot = sg & (uint32_t)(nst - 1);
+                        if (fi == 0) mbar_wait(barRaw_full + 8 * slot, (sg >> p.nst_shift) & 1u);
+                        // frame of this row at tile time tau, and its position inside the staged block
+                        int t, rel;
+                        if (phase == 0) { t = tau; rel = fi; }
+                        else { t = Te - 1 - tau; rel = t - max(Te - (kk + 1) * F, 0); }
+                        const bool ok = tau < Te;
+                        const uint32_t rowp = raw0 + slot * stage_bytes + (uint32_t)(ok ? rel : 0) * rowbytes;
+                        // A stage free?  (the MMAs that read it three frames ago have completed)
+                        mbar_wait(barA_free + 8 * c3, cph ^ 1u);
+                        tc_fence_after();
+                        const uint32_t ta = ta0 + c3 * a_cols;
+#pragma unroll
+                        for (int c = 0; c < 2; c++) {
+                            if (c < npr) {
+                                float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+                                if (ok && 2 * c < nrd4) x0 = lds4(rowp + 32u * c);
+                                if (ok && 2 * c + 1 < nrd4) x1 = lds4(rowp + 32u * c + 16u);
+                                uint32_t v[16];
+                                split4(x0, lds4(sbS + 32u * c), lds4(sbB + 32u * c), v, v + 8);
+                                split4(x1, lds4(sbS + 32u * c + 16u), lds4(sbB + 32u * c + 16u), v + 4, v + 12);
+                                tmem_st16(ta + 16u * c, v);
+                            }
+                        }
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            mbar_arrive(barA_full + 8 * c3);
+                            if (fi == F - 1 || tau == Tt - 1) mbar_arrive(barRaw_empty + 8 * slot);
+                        }
+                        if (fi == F - 1 || tau == Tt - 1) sg++;
+                        if (++c3 == 3) { c3 = 0; cph ^= 1u; }
+                    }
+                }
+                (void)nsg;
+            }
+        } else {
+            // ===================== recursions: one thread per utterance =====================
+            float *scr = p.scratch + (size_t)blockIdx.x * p.maxT * 8 * TC_ROWS + r;      // [t][j][row]
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int Tt = tile_frames(tile);
+                int mbase;
+                tile_models(tile, mbase);
+                int m, pos; int64_t off;
+                const int T = row_info(tile * TC_ROWS + r, m, pos, off);
+                const int u = pos >= 0 ? p.order[pos] : 0;
+                const uint32_t acc_col = tmem_acc + lane_sel + (uint32_t)(m - mbase) * 8u;   // warp-uniform: one model per quadrant
+                const float4 c03 = sTr[m * 5 + 0], c47 = sTr[m * 5 + 1], cm = sTr[m * 5 + 2];
+                const float4 st03 = sTr[m * 5 + 3], st47 = sTr[m * 5 + 4];
+                const float cadv[8] = {0.f, c03.x, c03.y, c03.z, c03.w, c47.x, c47.y, c47.z};   // into state j from j-1 (U form)
+                const float cx = c47.w, lb0 = cm.y;
+                const float stay[8] = {st03.x, st03.y, st03.z, st03.w, st47.x, st47.y, st47.z, st47.w};
+                float badv[7];          // ln A[j, j+1] - ln A[j+1, j+1]: the advance arc of state j on top of self[j+1]
+#pragma unroll
+                for (int j = 0; j < 7; j++) badv[j] = cadv[j + 1] + stay[j] - stay[j + 1];
+
+                auto fetch = [&](float (&e)[8]) {        // e'_t(j) = E[t, j] + ln A[j, j] of this thread's model
+                    const uint32_t s = f & 1u;
+                    mbar_wait(barAcc_full + 8 * s, (f >> 1) & 1u);
+                    tc_fence_after();
+                    uint32_t ev[8];
+                    tmem_ld8(acc_col + s * (uint32_t)ncols, ev);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(barAcc_empty + 8 * s);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) e[j] = __uint_as_float(ev[j]);
+                };
+
+                // ---------------- forward (custom_hmm.py:176-211), U_j = alpha-hat_j + ln A[j,j] ----------------
+                float U[8], ax = -INFINITY, base = 0.f;
+                float best_mx = 0.f, best_base = 0.f;        // max over all alpha cells = best_mx + best_base; alpha[0,0] = 0
+                double ll = 0.0;
+                bool exit_ok = false;
+#pragma unroll
+                for (int j = 0; j < 8; j++) U[j] = -INFINITY;
+                for (int t = 0; t < Tt; t++, f++) {
+                    float e[8];
+                    fetch(e);
+                    if (t < T) {
+                        if (t == 0) {
+                            U[0] = lb0 + e[0];
+                        } else {
+                            const float nx = U[7] + cx;                       // alpha[t, exit] = alpha[t-1, N] + ln A[N, exit]
+#pragma unroll
+                            for (int j = 7; j >= 1; j--) U[j] = lae32(U[j - 1] + cadv[j], U[j]) + e[j];
+                            const float ent = (t == 1) ? lb0 - base : -INFINITY;     // alpha[t-1, entry] is 0 at t == 1 only
+                            U[0] = lae32(ent, U[0]) + e[0];
+                            ax = nx;
+                        }
+                        float a[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) a[j] = U[j] - stay[j];
+                        float mx = fmaxf(fmaxf(a[0], a[1]), ax);
+                        mx = fmaxf(fmaxf(a[2], a[3]), mx);
+                        mx = fmaxf(fmaxf(a[4], a[5]), mx);
+                        mx = fmaxf(fmaxf(a[6], a[7]), mx);
+                        if (mx + base > best_mx + best_base) { best_mx = mx; best_base = base; }
+                        if (t == T - 1) {      // reported log-likelihood: logaddexp.reduce(alpha[T-1, :]) - max(alpha)
+                            float rr = (T == 1) ? 0.f - base : -INFINITY;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) rr = lae32(rr, a[j]);
+                            rr = lae32(rr, ax);
+                            ll = ((double)rr + (double)base) - ((double)best_mx + (double)best_base);
+                            exit_ok = (T > 1) && (ax > -INFINITY);
+                        }
+                        // renormalise with an integer shift (exactly representable running offset)
+                        const float sh = (t == 0) ? 0.f : rintf(fminf(fmaxf(mx, -4194304.f), 4194304.f));   // frame 0 stays unshifted (alpha[0, entry] = 0)
+#pragma unroll
+                        for (int j = 0; j < 8; j++) { U[j] -= sh; a[j] -= sh; }
+                        ax -= sh; base += sh;
+                        float *sp = scr + (size_t)t * 8 * TC_ROWS;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) sp[j * TC_ROWS] = a[j];
+                    }
+                }
+                if (pos >= 0 && T > 0) p.loglik[u] = ll;
+
+                // ---------------- backward + gamma + xi sums (custom_hmm.py:213-322) ----------------
+                float gG[8], gO[8], gX[8], b[8], en[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) { gG[j] = 0.f; gO[j] = 0.f; gX[j] = 0.f; b[j] = -INFINITY; en[j] = 0.f; }
+                float bx = 0.f;                                    // beta[T-1, exit] = 0
+                for (int tau = 0; tau < Tt; tau++, f++) {
+                    float e[8];
+                    fetch(e);
+                    if (tau < T) {
+                        const int t = T - 1 - tau;
+                        float *go = p.gamma + (size_t)(off + t) * 8;
+                        if (tau == 0) {
+                            // gamma[T-1] is one-hot on the exit state unless alpha[T-1, exit] = -inf (then the row is NaN)
+                            const float gl = exit_ok ? 0.f : NAN;
+                            *reinterpret_cast<float4 *>(go) = make_float4(gl, gl, gl, gl);
+                            *reinterpret_cast<float4 *>(go + 4) = make_float4(gl, gl, gl, gl);
+#pragma unroll
+                            for (int j = 0; j < 8; j++) gO[j] += gl;
+                        } else {
+                            const float *sp = scr + (size_t)t * 8 * TC_ROWS;
+                            float at[8], self[8], nb[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) { at[j] = sp[j * TC_ROWS]; self[j] = en[j] + b[j]; }   // ln A_jj + e_{t+1}(j) + beta_{t+1}(j)
+#pragma unroll
+                            for (int j = 0; j < 7; j++) nb[j] = lae32(self[j], badv[j] + self[j + 1]);
+                            nb[7] = lae32(self[7], (cx + stay[7]) + bx);                 // ln A[N, exit] + beta[t+1, exit]
+                            const float b0 = (lb0 - stay[0]) + self[0];                  // beta[t, entry]
+                            float lg[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) lg[j] = at[j] + nb[j];
+                            const float xs7 = at[7] + self[7];
+                            float mxl = fmaxf(fmaxf(lg[0], lg[1]), lg[2]);
+                            mxl = fmaxf(fmaxf(lg[3], lg[4]), mxl);
+                            mxl = fmaxf(fmaxf(lg[5], lg[6]), mxl);
+                            mxl = fmaxf(lg[7], mxl);
+                            const float ent = (t == 0) ? b0 : -INFINITY;                 // alpha[0, entry] = 0
+                            mxl = fmaxf(mxl, ent);
+                            float pj[8], sum = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) { pj[j] = __expf(lg[j] - mxl); sum += pj[j]; }
+                            const float pe = __expf(ent - mxl);
+                            // xi normaliser (:319-320): arcs (0,1), (i,i), (i,i+1) for i < N; the (N, exit) arc contributes 0
+                            const float q7 = __expf(xs7 - mxl);
+                            const float xsum = (sum - pj[7]) + q7 + pe;
+                            sum += pe;
+                            const float inv = 1.0f / sum;                                // all -inf row -> NaN like the reference
+                            const float xinv = (mxl > -INFINITY && xsum > 0.f) ? 1.0f / xsum : 0.f;
+                            float gm[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                gm[j] = pj[j] * inv;
+                                gG[j] += gm[j]; gO[j] += gm[j];
+                                const float xq = (mxl > -INFINITY) ? __expf((at[j] + self[j]) - mxl) : 0.f;
+                                gX[j] += xq * xinv;
+                            }
+                            *reinterpret_cast<float4 *>(go) = make_float4(gm[0], gm[1], gm[2], gm[3]);
+                            *reinterpret_cast<float4 *>(go + 4) = make_float4(gm[4], gm[5], gm[6], gm[7]);
+                            float mb = fmaxf(fmaxf(nb[0], nb[1]), nb[2]);
+                            mb = fmaxf(fmaxf(nb[3], nb[4]), mb);
+                            mb = fmaxf(fmaxf(nb[5], nb[6]), mb);
+                            mb = fmaxf(nb[7], mb);
+                            const bool fin = mb > -INFINITY && mb < INFINITY;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) b[j] = fin ? nb[j] - mb : nb[j];
+                            bx = -INFINITY;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; j++) en[j] = e[j];
+                    }
+                }
+                if (pos >= 0) {
+                    float *us = p.ustats + (size_t)pos * 24;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { us[j] = gG[j]; us[8 + j] = gX[j]; us[16 + j] = gO[j]; }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_WORKER_WARPS) tmem_dealloc(tmem_base, tcols);
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t sapr_tc_image_bytes(const sapr_models *m, int *nck_out, int *ncols_out);
+
+// launcher: fills gamma [sum_T][8] (fp32), ustats [B][24] by position in order[], loglik[B]
+int sapr_estep_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int B, int max_T,
+                         const int32_t *order, const int32_t *model_start, float *gamma, float *ustats, double *loglik) {
+    int nck, ncols;
+    sapr_tc_image_bytes(m, &nck, &ncols);
+    auto al256 = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t w = al256((size_t)2 * (ncols / 8) * nck * 64 * sizeof(__half));
+    const size_t g = al256((size_t)8 * nck * sizeof(float));
+    const int M = m->M;
+    const uint32_t rowbytes = (uint32_t)ldx * 4u;
+    const size_t budget = 225 * 1024;
+    int Fshift = 3, nst = 2, nst_shift = 1;
+    uint32_t rstride = 0;
+    EtSmem L;
+    for (;; Fshift--) {
+        const uint32_t F = 1u << Fshift;
+        rstride = F * rowbytes + 16u;
+        if (((rstride >> 4) & 1u) == 0) rstride += 16u;
+        L = et_smem_layout(M, nck, ncols, nst, rstride);
+        if (L.total <= budget) break;
+        if (Fshift == 0) SAPR_FAIL(ctx, SAPR_E_RANGE, "estep (tensor core): feature rows too wide for the shared-memory ring");
+    }
+    if (Fshift <= 1 && et_smem_layout(M, nck, ncols, 4, rstride).total <= budget) { nst = 4; nst_shift = 2; }
+    L = et_smem_layout(M, nck, ncols, nst, rstride);
+    const int grid = std::min((B + 31 * M + TC_ROWS - 1) / TC_ROWS, ctx->sm_count);
+    int rc = sapr_ws_reserve(ctx, 7, (size_t)grid * max_T * 8 * TC_ROWS * sizeof(float));
+    if (rc) return rc;
+    EtParams prm;
+    prm.X = X; prm.ldx = ldx; prm.offsets = offsets; prm.B = B; prm.order = order; prm.model_start = model_start;
+    prm.M = M; prm.D = m->D; prm.nck = nck; prm.ncols = ncols;
+    prm.wimg = (const __half *)m->tc_image;
+    prm.sb = (const float *)((const char *)m->tc_image + w);
+    prm.trp = (const float4 *)((const char *)m->tc_image + w + g);
+    prm.scratch = (float *)ctx->ws[7]; prm.maxT = max_T;
+    prm.gamma = gamma; prm.ustats = ustats; prm.loglik = loglik;
+    prm.Fshift = Fshift; prm.nst_shift = nst_shift; prm.rstride = rstride;
+    {   // chunk pairs over the three converting groups (group 0 runs the recursions)
+        const int npairs = nck / 2;
+        int pa = 0;
+        prm.pair0[0] = 0; prm.npair[0] = 0;
+        for (int gI = 1; gI < TC_GROUPS; gI++) {
+            const int cnt = npairs / 3 + ((gI - 1) < npairs % 3 ? 1 : 0);
+            prm.pair0[gI] = pa; prm.npair[gI] = cnt; pa += cnt;
+        }
+    }
+    SAPR_CUDA(ctx, cudaFuncSetAttribute(k_estep_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    {
+        ProfScope ps(ctx, 2);
+        k_estep_tc<<<grid, TC_THREADS, L.total, ctx->stream>>>(prm);
+    }
+    SAPR_LAUNCH_CHECK(ctx);
+    return SAPR_OK;
+}
