@@ -340,6 +340,208 @@ __global__ void k_stats_diag(const float *__restrict__ X, int ldx, const int64_t
     }
 }
 
+// Production form of k_stats_diag for N == 8, fp32 gamma: blockDim = (Dp/2 dim pairs, 16 frame slots).
+// A thread owns two feature dims and every 16th frame of the tile's utterances: per frame one 8-byte feature load
+// (a warp reads whole 160-byte rows), gamma_t broadcast from two 16-byte loads, then per state
+//   S1_j += gamma_j x';  S2_j += gamma_j x'^2;  G_j += gamma_j     (x' = x - g, g = mean of the model's state means;
+//                                                                    two FFMA2 per state, packed over the two dims)
+// fp32 inside a tile (a thread sees at most a few thousand frames; the raw moments are centred on g, so the relative
+// error of the variance stays below 1e-4 even for states 8 sigma away from g), float64 across tiles; at the end of
+// the tile the raw moments are re-pivoted in float64 to the model's current state means c_j (what the packed
+// statistics block holds):
+//   sum gamma (x-c) = S1 - (c-g) G,   sum gamma (x-c)^2 = S2 - 2 (c-g) S1 + (c-g)^2 G
+// and reduced over the frame slots in a fixed order.
+#define STATS2_SLOTS 32
+#define STATS2_MAXUPC 256
+__device__ __forceinline__ float2 st_fma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long *>(&a)),
+        "l"(*reinterpret_cast<unsigned long long *>(&b)), "l"(*reinterpret_cast<unsigned long long *>(&c)));
+    return *reinterpret_cast<float2 *>(&d);
+}
+__device__ __forceinline__ float2 st_mul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long *>(&a)),
+        "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&d);
+}
+__device__ __forceinline__ float2 st_sub2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long *>(&a)),
+        "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&d);
+}
+
+// Shared-memory staged: a producer warp bulk-copies chunks of up to STATS2_CF consecutive frames of one utterance
+// (feature rows and gamma rows are both contiguous in HBM) into a 3-stage ring; the ndp x 32 consumer threads read
+// their two dims and gamma from shared memory.  blockDim.x = ndp * STATS2_SLOTS; thread 0 doubles as the producer
+// (it requests chunk k + 2 before it consumes chunk k).
+#define STATS2_CF 128
+#define STATS2_STAGES 6
+__device__ __forceinline__ uint32_t st_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\tmov.u32 n, 0;\n\t"
+        "LW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 2000;\n\t@p bra LD;\n\t"
+        "add.u32 n, n, 1;\n\tsetp.gt.u32 p, n, 8000000;\n\t@p trap;\n\tbra LW;\n\tLD:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(640, 1)
+k_stats_diag8(const float *__restrict__ X, int ldx, const int64_t *__restrict__ offsets, const int32_t *__restrict__ order,
+              const int32_t *__restrict__ model_start, int M, int D, int Dp, int S, int upc, const double *__restrict__ mean,
+              const float *__restrict__ gamma, double *__restrict__ partial) {
+    constexpr int N = 8;
+    __shared__ int s_m, s_tim;
+    __shared__ int64_t s_off[STATS2_MAXUPC];
+    __shared__ int s_T[STATS2_MAXUPC];
+    __shared__ __align__(8) uint64_t s_bar[2 * STATS2_STAGES];
+    const int ndp = Dp / 2, ncons = ndp * STATS2_SLOTS, tid = threadIdx.x;
+    const bool consumer = tid < ncons;
+    const int dp = tid % ndp, slot = tid / ndp, d0 = 2 * dp;
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    // the ring; at the end of the tile it is reused for the per-slot partials S1, S2 [STATS2_SLOTS][2][N][Dp], G [STATS2_SLOTS][N]
+    float *s_acc = reinterpret_cast<float *>(s_dyn);
+    float *s_g = s_acc + (size_t)STATS2_SLOTS * 2 * N * Dp;
+    const uint32_t rowbytes = (uint32_t)ldx * 4u;
+    const uint32_t stage_bytes = STATS2_CF * (rowbytes + 32u);
+    unsigned char *s_stage = s_dyn;                                          // per stage: X rows, then gamma rows
+    const uint32_t bar_full = st_smem(s_bar), bar_empty = bar_full + 8 * STATS2_STAGES;
+    if (tid == 0) {
+        s_m = find_tile(model_start, M, upc, blockIdx.x, &s_tim);
+        for (int i = 0; i < STATS2_STAGES; i++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * i), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_empty + 8 * i), "r"(ncons / 32));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int m = s_m;
+    float *mine = s_acc + (size_t)slot * 2 * N * Dp + d0;       // element (k, j, q) at mine[(k * N + j) * Dp + q]
+    float2 s1[N], s2[N], gs[N / 2];
+#pragma unroll
+    for (int j = 0; j < N; j++) { s1[j] = make_float2(0.f, 0.f); s2[j] = make_float2(0.f, 0.f); }
+#pragma unroll
+    for (int j = 0; j < N / 2; j++) gs[j] = make_float2(0.f, 0.f);
+    (void)consumer;
+    int nutt = 0;
+    if (m >= 0) {
+        const int pbeg = model_start[m] + s_tim * upc;
+        nutt = min(pbeg + upc, model_start[m + 1]) - pbeg;
+        for (int i = tid; i < nutt; i += blockDim.x) {      // the tile's utterance table: frame offset and length
+            const int u = order[pbeg + i];
+            const int64_t o = offsets[u];
+            s_off[i] = o; s_T[i] = (int)(offsets[u + 1] - o);
+        }
+    }
+    __syncthreads();
+    // pivot g: mean of the model's state means, rounded to fp32 (the same value is used in the float64 re-pivot)
+    float2 g = make_float2(0.f, 0.f);
+    if (m >= 0) {
+        double gx = 0.0, gy = 0.0;
+        for (int j = 0; j < N; j++) {
+            if (d0 < D) gx += mean[((size_t)m * S + j + 1) * D + d0];
+            if (d0 + 1 < D) gy += mean[((size_t)m * S + j + 1) * D + d0 + 1];
+        }
+        g = make_float2((float)(gx / N), (float)(gy / N));
+    }
+    if (m >= 0 && nutt > 0) {
+        // producer state (thread 0): next chunk to request
+        int ppi = 0, pc0 = 0;
+        uint32_t pk = 0;
+        auto issue_next = [&]() {
+            if (ppi >= nutt) return;
+            const int T = s_T[ppi];
+            const uint32_t st = pk % STATS2_STAGES, ph = (pk / STATS2_STAGES) & 1u;
+            const int n = min(STATS2_CF, T - pc0);
+            st_wait(bar_empty + 8 * st, ph ^ 1u);
+            const uint32_t dst = st_smem(s_stage) + st * stage_bytes;
+            const uint32_t bx = (uint32_t)n * rowbytes, bg = (uint32_t)n * 32u;
+            asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n\t}"
+                         ::"r"(bar_full + 8 * st), "r"(bx + bg) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(X + (size_t)(s_off[ppi] + pc0) * ldx), "r"(bx), "r"(bar_full + 8 * st) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + STATS2_CF * rowbytes), "l"(gamma + (size_t)(s_off[ppi] + pc0) * N), "r"(bg),
+                         "r"(bar_full + 8 * st) : "memory");
+            pk++; pc0 += STATS2_CF;
+            while (ppi < nutt && pc0 >= s_T[ppi]) { pc0 = 0; ppi++; }
+        };
+        if (tid == 0) {
+            while (ppi < nutt && s_T[ppi] <= 0) ppi++;
+            for (int i = 0; i < STATS2_STAGES - 1; i++) issue_next();
+        }
+        const float2 kk = make_float2((d0 < D) ? 1.f : 0.f, (d0 + 1 < D) ? 1.f : 0.f);
+        const float2 ng = make_float2(-g.x * kk.x, -g.y * kk.y);
+        uint32_t k = 0;
+        for (int pi = 0; pi < nutt; pi++) {
+            const int T = s_T[pi];
+            for (int c0 = 0; c0 < T; c0 += STATS2_CF, k++) {
+                const uint32_t st = k % STATS2_STAGES, ph = (k / STATS2_STAGES) & 1u;
+                const int n = min(STATS2_CF, T - c0);
+                if (tid == 0) issue_next();
+                st_wait(bar_full + 8 * st, ph);
+                const unsigned char *sx = s_stage + st * stage_bytes;
+                const unsigned char *sg = sx + STATS2_CF * rowbytes;
+                auto frame = [&](int fi) {
+                    const float2 xr = *reinterpret_cast<const float2 *>(sx + (size_t)fi * rowbytes + 8 * dp);
+                    const float4 g0 = *reinterpret_cast<const float4 *>(sg + fi * 32);
+                    const float4 g1 = *reinterpret_cast<const float4 *>(sg + fi * 32 + 16);
+                    const float2 x = st_fma2(xr, kk, ng);            // x' = x - g (0 for padded dims)
+                    const float2 q = st_mul2(x, x);
+                    const float gj[N] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                    for (int j = 0; j < N; j++) {
+                        const float2 gg = make_float2(gj[j], gj[j]);
+                        s1[j] = st_fma2(gg, x, s1[j]);
+                        s2[j] = st_fma2(gg, q, s2[j]);
+                    }
+                    gs[0].x += g0.x; gs[0].y += g0.y; gs[1].x += g0.z; gs[1].y += g0.w;
+                    gs[2].x += g1.x; gs[2].y += g1.y; gs[3].x += g1.z; gs[3].y += g1.w;
+                };
+                if (n == STATS2_CF) {
+#pragma unroll
+                    for (int i = 0; i < STATS2_CF / STATS2_SLOTS; i++) frame(slot + i * STATS2_SLOTS);
+                } else {
+                    for (int fi = slot; fi < n; fi += STATS2_SLOTS) frame(fi);
+                }
+                __syncwarp();
+                if ((tid & 31) == 0)
+                    asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.shared::cta.b64 t, [%0];\n\t}" ::"r"(bar_empty + 8 * st) : "memory");
+            }
+        }
+    }
+    __syncthreads();            // every chunk consumed: the ring is free, reuse it for the per-slot partials
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        mine[(0 * N + j) * Dp] = s1[j].x; mine[(0 * N + j) * Dp + 1] = s1[j].y;
+        mine[(1 * N + j) * Dp] = s2[j].x; mine[(1 * N + j) * Dp + 1] = s2[j].y;
+        if (dp == 0) s_g[slot * N + j] = (j & 1) ? gs[j >> 1].y : gs[j >> 1].x;
+    }
+    __syncthreads();
+    // fixed-order reduction over the frame slots and float64 re-pivot to the state means: one thread per output element
+    double *out = partial + (size_t)blockIdx.x * 2 * N * Dp;
+    const int nsd = N * Dp;
+    for (int i = tid; i < nsd; i += blockDim.x) {
+        const int j = i / Dp, d = i % Dp;
+        double S1 = 0.0, S2 = 0.0, G = 0.0;
+        for (int sl = 0; sl < STATS2_SLOTS; sl++) {
+            const float *b = s_acc + (size_t)sl * 2 * nsd;
+            S1 += (double)b[i]; S2 += (double)b[nsd + i]; G += (double)s_g[sl * N + j];
+        }
+        double r1 = 0.0, r2 = 0.0;
+        if (m >= 0 && d < D) {
+            double gm = 0.0;
+            for (int jj = 0; jj < N; jj++) gm += mean[((size_t)m * S + jj + 1) * D + d];
+            const double gd = (double)(float)(gm / N);
+            const double dc = mean[((size_t)m * S + j + 1) * D + d] - gd;
+            r1 = S1 - dc * G;
+            r2 = S2 - 2.0 * dc * S1 + dc * dc * G;
+        }
+        out[i] = r1; out[nsd + i] = r2;
+    }
+}
+
 // fixed-order sum of the tile partials: one thread per (model, k, state, dim)
 __global__ void k_reduce_partials(const int32_t *__restrict__ model_start, int M, int N, int D, int Dp, int S, int upc,
                                   const double *__restrict__ partial, double *__restrict__ stats, int64_t stride) {
@@ -471,6 +673,24 @@ static int launch_estep(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, 
     }
     // feature statistics over the whole batch
     const int ntiles = ntile_max;
+    if (std::is_same<R, float>::value && N == 8) {
+        const int ncons = (Dp / 2) * STATS2_SLOTS;
+        dim3 sb2(ncons);
+        const size_t ssm2 = std::max(sizeof(float) * STATS2_SLOTS * (2 * N * Dp + N), (size_t)STATS2_STAGES * STATS2_CF * (ldx * 4 + 32));
+        if (ssm2 <= 227 * 1024 && ncons <= 640 && ncons % 32 == 0 && upc <= STATS2_MAXUPC) {
+            SAPR_CUDA(ctx, cudaFuncSetAttribute(k_stats_diag8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm2));
+            {
+                ProfScope ps(ctx, 3);
+                k_stats_diag8<<<ntiles, sb2, ssm2, ctx->stream>>>(X, ldx, offsets, order, model_start, M, D, Dp, S, upc, m->mean,
+                                                                  (const float *)gamma, partial);
+            }
+            SAPR_LAUNCH_CHECK(ctx);
+            k_reduce_partials<<<(M * 2 * N * D + 127) / 128, 128, 0, ctx->stream>>>(model_start, M, N, D, Dp, S, upc, partial,
+                                                                                    stats, stride);
+            SAPR_LAUNCH_CHECK(ctx);
+            return SAPR_OK;
+        }
+    }
     dim3 sb(Dp, STATS_SLOTS);
     size_t ssm = sizeof(double) * STATS_SLOTS * 2 * N * Dp;
     auto skern = k_stats_diag<R, NMAX>;
