@@ -264,6 +264,31 @@ def test_moderate_batch_against_oracle(eng):
     assert_close(tot.cpu().numpy(), full.cpu().numpy(), 1e-12, atol=1e-9, what="sharded stats")
 
 
+def test_estep_short_and_ragged_utterances_tc_vs_float64(eng):
+    """The tensor-core E-step (fp32) against the float64 verification kernel on the shapes the reference's own
+    recursions treat specially: T = 1, 2 (gamma rows NaN / one-hot, custom_hmm.py:252-255), T <= N (exit state
+    unreachable), T = N + 1, ragged lengths inside one 128-utterance tile, several models per tile."""
+    import torch
+    from sapr_b200 import synth
+    rng = np.random.default_rng(5)
+    lens = [1, 2, 5, 8, 9, 10, 17, 33, 64, 3, 9, 12] + list(rng.integers(9, 70, size=200))
+    feats, labels, mu, sd = synth.make_corpus(len(lens), 11, 8, 39, 70, 70, seed=3)
+    feats = [f[:, :T] for f, T in zip(feats, lens)]
+    A, means, var = synth.truth_models(mu, sd, 0.9)
+    m = eng.WordModels(11, 8, 39)
+    m.set(means, var, A)
+    batch = eng.PackedBatch.from_features(feats)
+    lab = torch.as_tensor(labels, device="cuda")
+    s64, l64, g64 = m.estep(batch, lab, None, eng.FP64, want_gamma=True)
+    s32, l32, g32 = m.estep(batch, lab, None, eng.FP32, want_gamma=True)
+    assert_close(l32.cpu().numpy(), l64.cpu().numpy(), 1e-6, what="loglik")
+    assert_close(g32.cpu().numpy(), g64.cpu().numpy(), 0, 2e-5, what="gamma")
+    a, b = s32.cpu().numpy(), s64.cpu().numpy()
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = ~np.isnan(b)
+    assert np.max(np.abs(a[ok] - b[ok]) / (1.0 + np.abs(b[ok]))) < 2e-4
+
+
 def test_launch_counter_and_errors(eng):
     from sapr_b200 import _lib
     ctx = _lib.default_context()
