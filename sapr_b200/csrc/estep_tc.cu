@@ -16,15 +16,17 @@
 //     gamma_t (for the feature statistics) and the log-likelihood leave the CTA;
 //   * warp roles: warps 0-3 run the recursions (one thread per utterance: the left-to-right chain of 8 states is
 //     register resident, log-sum-exp in the forward sweep, max-normalised linear sums in the backward sweep),
-//     warps 4-15 standardise / square / split the features into the A operand, warp 16 issues the MMAs,
-//     warps 17-19 issue the bulk copies.  (Giving the recursion warps the highest warp ids instead was measured: 7 % slower.)
+//     warps 4-11 standardise / square / split the features into the A operand, warp 12 issues the MMAs,
+//     warps 13-19 issue the bulk copies (a per-lane cp.async.bulk costs ~90 issue cycles, so the copy issue is
+//     spread over seven warps).  (Giving the recursion warps the highest warp ids instead was measured: 7 % slower.)
 #include "tc_common.cuh"
 
-#define ET_REC_WARPS 4
-#define ET_CONV_WARPS (TC_WORKER_WARPS - ET_REC_WARPS)
-#define ET_REC_WARP0 0                            /* 0 .. 3 */
-#define ET_MMA_WARP TC_WORKER_WARPS               /* 16 */
-#define ET_LOAD_WARP0 (TC_WORKER_WARPS + 1)       /* 17, 18, 19 */
+#define ET_REC_WARPS 4                            /* warps 0 .. 3 */
+#define ET_CONV_GROUPS 2
+#define ET_CONV_WARPS (4 * ET_CONV_GROUPS)         /* warps 4 .. 11 */
+#define ET_MMA_WARP (ET_REC_WARPS + ET_CONV_WARPS) /* 12 */
+#define ET_LOAD_WARP0 (ET_MMA_WARP + 1)           /* 13 .. 19 */
+#define ET_LOADERS (TC_THREADS / 32 - ET_LOAD_WARP0)
 
 struct EtParams {
     const float *X; int ldx; const int64_t *offsets; int B;
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
         }
         sPad[M] = acc;
         for (int s = 0; s < nst; s++) {
-            mbar_init(barRaw_full + 8 * s, 32 * TC_LOADERS);
+            mbar_init(barRaw_full + 8 * s, 32 * ET_LOADERS);
             mbar_init(barRaw_empty + 8 * s, ET_CONV_WARPS);
         }
         for (int s = 0; s < 3; s++) { mbar_init(barA_full + 8 * s, ET_CONV_WARPS); mbar_init(barA_free + 8 * s, 1); }
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
 
     if (warp >= ET_LOAD_WARP0) {
         // ===================== bulk-copy producers: forward sweep, then backward sweep of every tile =====================
-        constexpr int RPL = (TC_ROWS + TC_LOADERS - 1) / TC_LOADERS;
+        constexpr int RPL = (TC_ROWS + ET_LOADERS - 1) / ET_LOADERS;
         const int lw = warp - ET_LOAD_WARP0;
         const int rlo = lw * RPL, rhi = min(rlo + RPL, TC_ROWS);
         const int rr[2] = {rlo + lane, rlo + lane + 32};
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
                         tc_fence_after();
                         const uint32_t ta = ta0 + c3 * a_cols;
 #pragma unroll
-                        for (int c = 0; c < 2; c++) {
+                        for (int c = 0; c < 3; c++) {
                             if (c < npr) {
                                 float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
                                 if (ok && 2 * c < nrd4) x0 = lds4(rowp + 32u * c);
@@ -518,12 +520,12 @@ int sapr_estep_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx,
     prm.scratch = (float *)ctx->ws[7]; prm.maxT = max_T;
     prm.gamma = gamma; prm.ustats = ustats; prm.loglik = loglik;
     prm.Fshift = Fshift; prm.nst_shift = nst_shift; prm.rstride = rstride;
-    {   // chunk pairs over the three converting groups (group 0 runs the recursions)
+    {   // chunk pairs over the converting groups (group 0 runs the recursions)
         const int npairs = nck / 2;
         int pa = 0;
         prm.pair0[0] = 0; prm.npair[0] = 0;
         for (int gI = 1; gI < TC_GROUPS; gI++) {
-            const int cnt = npairs / 3 + ((gI - 1) < npairs % 3 ? 1 : 0);
+            const int cnt = (gI <= ET_CONV_GROUPS) ? npairs / ET_CONV_GROUPS + ((gI - 1) < npairs % ET_CONV_GROUPS ? 1 : 0) : 0;
             prm.pair0[gI] = pa; prm.npair[gI] = cnt; pa += cnt;
         }
     }
