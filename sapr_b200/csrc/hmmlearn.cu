@@ -3,7 +3,10 @@
 // (hmmlearn_hmm.py:27-43, :103-104 fit/score; decoder.py:43 decode).  hmmlearn is not vendored in the
 // reference; semantics follow SURVEY.md Appendix B (forward_log / backward_log / compute_log_xi_sum /
 // viterbi with max-shifted logsumexp).  float64; one thread per utterance, state vectors in local
-// arrays (S <= 32) -- small-N ergodic models are latency bound by nature.
+// arrays (S <= 32) -- small-N ergodic models are latency bound by nature.  For 32 < S <= 1024 (BASELINE cfg 4: the
+// N = 256 ergodic model) score and decode run one CTA per utterance, one thread per state (k_hl_*_cta): same
+// arithmetic and summation order, so the two mappings agree bit for bit; the tensor-core forward-backward for
+// training such models is not built.
 #include "common.cuh"
 
 #define HL_MAX_S 32
@@ -158,13 +161,85 @@ __global__ void k_hl_viterbi(const double *__restrict__ lf, const int64_t *__res
     logprob[u] = best;
 }
 
+// ---- one CTA per utterance, one thread per destination state (32 < S <= 1024) ----
+#define HL_MAX_S_CTA 1024
+__global__ void k_hl_forward_cta(const double *__restrict__ lf, const int64_t *__restrict__ offsets, int S,
+                                 const double *__restrict__ logpi, const double *__restrict__ logA,
+                                 double *__restrict__ logprob) {
+    extern __shared__ double sh_prev[];   // [S]
+    const int u = blockIdx.x, j = threadIdx.x;
+    const int64_t off = offsets[u];
+    const int T = (int)(offsets[u + 1] - off);
+    if (T <= 0) { if (j == 0) logprob[u] = 0.0; return; }
+    if (j < S) sh_prev[j] = logpi[j] + lf[(size_t)off * S + j];
+    __syncthreads();
+    for (int t = 1; t < T; t++) {
+        double cur = 0.0;
+        if (j < S) {
+            double m = -INFINITY;
+            for (int i = 0; i < S; i++) { const double v = sh_prev[i] + logA[(size_t)i * S + j]; if (v > m) m = v; }
+            double r = -INFINITY;
+            if (m > -INFINITY) {
+                double s = 0.0;
+                for (int i = 0; i < S; i++) s += exp(sh_prev[i] + logA[(size_t)i * S + j] - m);
+                r = log(s) + m;
+            }
+            cur = r + lf[(size_t)(off + t) * S + j];
+        }
+        __syncthreads();
+        if (j < S) sh_prev[j] = cur;
+        __syncthreads();
+    }
+    if (j == 0) logprob[u] = hl_lse(sh_prev, S);
+}
+
+__global__ void k_hl_viterbi_cta(const double *__restrict__ lf, const int64_t *__restrict__ offsets, int S,
+                                 const double *__restrict__ logpi, const double *__restrict__ logA,
+                                 double *__restrict__ delta_ws, double *__restrict__ logprob, int32_t *__restrict__ path) {
+    const int u = blockIdx.x, j = threadIdx.x;
+    const int64_t off = offsets[u];
+    const int T = (int)(offsets[u + 1] - off);
+    if (T <= 0) { if (j == 0) logprob[u] = 0.0; return; }
+    double *dl = delta_ws + (size_t)off * S;
+    if (j < S) dl[j] = logpi[j] + lf[(size_t)off * S + j];
+    __syncthreads();
+    for (int t = 1; t < T; t++) {
+        if (j < S) {
+            double m = -INFINITY;
+            for (int i = 0; i < S; i++) {
+                const double v = dl[(size_t)(t - 1) * S + i] + logA[(size_t)i * S + j];
+                if (v > m) m = v;
+            }
+            dl[(size_t)t * S + j] = m + lf[(size_t)(off + t) * S + j];
+        }
+        __syncthreads();      // global writes of this CTA are visible to it after the barrier
+    }
+    if (j == 0) {            // terminal arg-max and back-trace: first maximum wins (lowest index)
+        int cur = 0;
+        double best = dl[(size_t)(T - 1) * S];
+        for (int i = 1; i < S; i++) if (dl[(size_t)(T - 1) * S + i] > best) { best = dl[(size_t)(T - 1) * S + i]; cur = i; }
+        path[off + T - 1] = cur;
+        for (int t = T - 2; t >= 0; t--) {
+            int arg = 0;
+            double m = dl[(size_t)t * S] + logA[cur];
+            for (int i = 1; i < S; i++) {
+                const double v = dl[(size_t)t * S + i] + logA[(size_t)i * S + cur];
+                if (v > m) { m = v; arg = i; }
+            }
+            cur = arg;
+            path[off + t] = cur;
+        }
+        logprob[u] = best;
+    }
+}
+
 #define HL_CHECK(fn)                                                                             \
     if (!ctx || !m || !X || !offsets) return SAPR_E_INVALID;                                     \
     if (!m->valid) SAPR_FAIL(ctx, SAPR_E_INVALID, fn ": model parameters not set");              \
     if (mi < 0 || mi >= m->M) SAPR_FAIL(ctx, SAPR_E_INVALID, fn ": model index out of range");   \
     if (m->topology != SAPR_TOPO_DENSE || m->emission != SAPR_EMIT_DIAG)                         \
         SAPR_FAIL(ctx, SAPR_E_INVALID, fn ": needs DENSE topology + DIAG emission");             \
-    if (m->S > HL_MAX_S) SAPR_FAIL(ctx, SAPR_E_RANGE, fn ": more than 32 states (the N=256 ergodic kernel is not built yet)")
+    if (m->S > HL_MAX_S_CTA) SAPR_FAIL(ctx, SAPR_E_RANGE, fn ": more than 1024 states")
 
 extern "C" int64_t sapr_hl_stats_len(int S, int D) { return (int64_t)S + (int64_t)S * S + S + 2 * (int64_t)S * D; }
 
@@ -176,8 +251,12 @@ extern "C" int sapr_hl_score(sapr_ctx *ctx, sapr_models *m, int mi, const float 
     if (rc) return rc;
     double *lf = (double *)ctx->ws[4];
     if ((rc = sapr_emission_into(ctx, m, mi, X, ldx, offsets, B, total_frames, lf))) return rc;
-    k_hl_forward<<<(B + 31) / 32, 32, 0, ctx->stream>>>(lf, offsets, B, S, m->logpi + (size_t)mi * S,
-                                                        m->logA + (size_t)mi * S * S, nullptr, logprob);
+    if (S <= HL_MAX_S)
+        k_hl_forward<<<(B + 31) / 32, 32, 0, ctx->stream>>>(lf, offsets, B, S, m->logpi + (size_t)mi * S,
+                                                            m->logA + (size_t)mi * S * S, nullptr, logprob);
+    else
+        k_hl_forward_cta<<<B, (S + 31) / 32 * 32, sizeof(double) * S, ctx->stream>>>(lf, offsets, S, m->logpi + (size_t)mi * S,
+                                                                                     m->logA + (size_t)mi * S * S, logprob);
     SAPR_LAUNCH_CHECK(ctx);
     return SAPR_OK;
 }
@@ -190,8 +269,12 @@ extern "C" int sapr_hl_decode(sapr_ctx *ctx, sapr_models *m, int mi, const float
     if (rc) return rc;
     double *lf = (double *)ctx->ws[4], *dl = lf + (size_t)total_frames * S;
     if ((rc = sapr_emission_into(ctx, m, mi, X, ldx, offsets, B, total_frames, lf))) return rc;
-    k_hl_viterbi<<<(B + 31) / 32, 32, 0, ctx->stream>>>(lf, offsets, B, S, m->logpi + (size_t)mi * S,
-                                                        m->logA + (size_t)mi * S * S, dl, logprob, path);
+    if (S <= HL_MAX_S)
+        k_hl_viterbi<<<(B + 31) / 32, 32, 0, ctx->stream>>>(lf, offsets, B, S, m->logpi + (size_t)mi * S,
+                                                            m->logA + (size_t)mi * S * S, dl, logprob, path);
+    else
+        k_hl_viterbi_cta<<<B, (S + 31) / 32 * 32, 0, ctx->stream>>>(lf, offsets, S, m->logpi + (size_t)mi * S,
+                                                                    m->logA + (size_t)mi * S * S, dl, logprob, path);
     SAPR_LAUNCH_CHECK(ctx);
     return SAPR_OK;
 }
@@ -200,6 +283,8 @@ extern "C" int sapr_hl_estep(sapr_ctx *ctx, sapr_models *m, int mi, const float 
                              int B, int64_t total_frames, double *stats, double *logprob) {
     HL_CHECK("hl_estep");
     if (!stats || !logprob) return SAPR_E_INVALID;
+    if (m->S > HL_MAX_S)
+        SAPR_FAIL(ctx, SAPR_E_RANGE, "hl_estep: training with more than 32 states is not built (score / decode are)");
     const int S = m->S, D = m->D;
     const size_t lat = (size_t)total_frames * S;
     const int len = S + S * S + S;

@@ -55,6 +55,34 @@ def test_score_decode_vs_oracle(cuda, rung1_d13):
     assert model.covars_.shape == (10, 13, 13)      # hmmlearn getter expands 'diag' to full matrices
 
 
+def test_large_ergodic_score_decode_vs_oracle(cuda):
+    """BASELINE cfg 4 shape at test size: N = 256 fully connected states (rows ~ Dirichlet(1)), D = 39 -- score and
+    Viterbi decode through the one-CTA-per-utterance kernels against the oracle restatement; fit must refuse loudly."""
+    from sapr_b200.hmmlearn_hmm import GaussianHMM
+    rng = np.random.default_rng(4)
+    S, D = 256, 39
+    means = 2.0 * rng.standard_normal((S, D)); var = rng.uniform(0.5, 1.5, (S, D)) ** 2
+    tm = rng.dirichlet(np.ones(S), size=S); sp = rng.dirichlet(np.ones(S))
+    lengths = [37, 5, 1, 64]
+    states = rng.integers(0, S, size=sum(lengths))
+    X = (means[states] + np.sqrt(var[states]) * rng.standard_normal((sum(lengths), D))).astype(np.float32)
+    model = GaussianHMM(n_components=S, covariance_type="diag", n_iter=1, init_params="")
+    model.means_, model.covars_, model.transmat_, model.startprob_ = means, var, tm, sp
+    offs = np.concatenate([[0], np.cumsum(lengths)])
+    tot, tot_v, paths = 0.0, 0.0, []
+    for a, b in zip(offs[:-1], offs[1:]):
+        lf = orc.emission_diag(X[a:b].T, means, var, all_emit=True)
+        tot += orc.hl_forward(lf, sp, tm)[0]
+        lp, p = orc.hl_viterbi(lf, sp, tm)
+        tot_v += lp; paths.append(p)
+    assert abs(model.score(X, lengths) - tot) <= 1e-10 * abs(tot)
+    lp, path = model.decode(X, lengths)
+    assert abs(lp - tot_v) <= 1e-10 * abs(tot_v)
+    assert np.array_equal(path, np.concatenate(paths))
+    with pytest.raises(Exception):
+        model.fit(X, lengths)
+
+
 def test_fit_vs_oracle(cuda, rung1_d13):
     model, X, lengths, (means, var, tm, sp) = _setup(rung1_d13, w=2)
     offs = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
