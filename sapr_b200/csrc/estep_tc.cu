@@ -16,13 +16,12 @@
 //     gamma_t (for the feature statistics) and the log-likelihood leave the CTA;
 //   * warp roles: warps 0-3 run the recursions (one thread per utterance: the left-to-right chain of 8 states is
 //     register resident, log-sum-exp in the forward sweep, max-normalised linear sums in the backward sweep),
-//     warps 4-11 standardise / square / split the features into the A operand, warp 12 issues the MMAs,
-//     warps 13-19 issue the bulk copies (a per-lane cp.async.bulk costs ~90 issue cycles, so the copy issue is
-//     spread over seven warps).  (Giving the recursion warps the highest warp ids instead was measured: 7 % slower.)
+//     warps 4-15 standardise / square / split the features into the A operand (three groups, each converting every
+//     third frame into its own A stage), warp 16 issues the MMAs, warps 17-19 issue the bulk copies.  (Giving the recursion warps the highest warp ids instead was measured: 7 % slower.)
 #include "tc_common.cuh"
 
 #define ET_REC_WARPS 4                            /* warps 0 .. 3 */
-#define ET_CONV_GROUPS 2
+#define ET_CONV_GROUPS 3
 #define ET_CONV_WARPS (4 * ET_CONV_GROUPS)         /* warps 4 .. 11 */
 #define ET_MMA_WARP (ET_REC_WARPS + ET_CONV_WARPS) /* 12 */
 #define ET_LOAD_WARP0 (ET_MMA_WARP + 1)           /* 13 .. 19 */
@@ -39,6 +38,7 @@ struct EtParams {
     double *loglik;                                          // [B] by utterance id
     int Fshift, nst_shift; uint32_t rstride;
     int pair0[TC_GROUPS], npair[TC_GROUPS];                  // chunk pairs of the converting groups (group 0: none)
+    long long *trace;                                        // [ET_TRACE_ROLES][ET_TRACE_FRAMES][ET_TRACE_EVENTS] or null
 };
 
 struct EtSmem { uint32_t w, raw, tr, sb, pad, bar, total; };
@@ -71,6 +71,11 @@ __device__ __forceinline__ float fexp32(float x) {      // exp(x), x <= 0 or -in
     return t;
 }
 
+// TRACE: CTA 0 records clock64() at its pipeline events (tuning aid, SAPR_ET_TRACE=file)
+#define ET_TRACE_FRAMES 64
+#define ET_TRACE_EVENTS 4
+#define ET_TRACE_ROLES 4
+template <bool TRACE, int NKS>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int nck = p.nck, ncols = p.ncols, M = p.M;
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
             mbar_init(barRaw_full + 8 * s, 32 * ET_LOADERS);
             mbar_init(barRaw_empty + 8 * s, ET_CONV_WARPS);
         }
-        for (int s = 0; s < 3; s++) { mbar_init(barA_full + 8 * s, ET_CONV_WARPS); mbar_init(barA_free + 8 * s, 1); }
+        for (int s = 0; s < 3; s++) { mbar_init(barA_full + 8 * s, 4); mbar_init(barA_free + 8 * s, 1); }   // one converter group per A stage
         for (int s = 0; s < 2; s++) { mbar_init(barAcc_full + 8 * s, 1); mbar_init(barAcc_empty + 8 * s, ET_REC_WARPS); }
         fence_barrier_init();
     }
@@ -163,6 +168,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
     };
 
     uint32_t f = 0, sg = 0;
+    auto trace = [&](int role, uint32_t frame, int ev) {
+        if (TRACE && blockIdx.x == 0 && lane == 0 && frame >= 40 && frame < 40 + ET_TRACE_FRAMES)
+            p.trace[((size_t)role * ET_TRACE_FRAMES + (frame - 40)) * ET_TRACE_EVENTS + ev] = clock64();
+    };
 
     if (warp >= ET_LOAD_WARP0) {
         // ===================== bulk-copy producers: forward sweep, then backward sweep of every tile =====================
@@ -190,13 +199,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
                         if (phase == 0) { lo[i] = k * F; nf[i] = min(max(Te[i] - k * F, 0), F); }
                         else { const int hi = Te[i] - k * F; lo[i] = max(hi - F, 0); nf[i] = max(hi, 0) - lo[i]; }
                     }
+                    if (lw == 0) trace(3, sg * 4 + 40, 0);
                     mbar_wait(barRaw_empty + 8 * slot, ph ^ 1u);
+                    if (lw == 0) trace(3, sg * 4 + 40, 1);
                     mbar_arrive_tx(bar, (uint32_t)(nf[0] + nf[1]) * rowbytes);
 #pragma unroll
                     for (int i = 0; i < 2; i++)
                         if (nf[i] > 0)
                             bulk_g2s(smem_u32(sRaw) + slot * stage_bytes + (uint32_t)rr[i] * rstride,
                                      p.X + (size_t)(off[i] + lo[i]) * p.ldx, (uint32_t)nf[i] * rowbytes, bar);
+                    if (lw == 0) trace(3, sg * 4 + 40, 2);
                 }
         }
     } else if (warp == ET_MMA_WARP) {
@@ -214,23 +226,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
             const uint64_t dW_lo = make_desc(sW_lo + (uint32_t)mbase * sboW, 128, sboW);
             for (int t = 0; t < 2 * Tt; t++, f++) {
                 const uint32_t s = f & 1, ph = (f >> 1) & 1;
+                trace(0, f, 0);
                 mbar_wait(barA_full + 8 * a3, aph);
+                trace(0, f, 1);
                 mbar_wait(barAcc_empty + 8 * s, ph ^ 1u);
+                trace(0, f, 2);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t d_tmem = tmem_acc + s * (uint32_t)ncols;
                     const uint32_t a_hi = tmem_a + a3 * a_cols, a_lo = a_hi + 8u;
-                    uint64_t dh = dW_hi, dl = dW_lo;
-                    uint32_t a = a_lo;
-                    for (int ks = 0; ks < nks; ks++, a += 16, dh += 16) umma_f16_ts(d_tmem, a, dh, idesc, ks > 0);   // lo * W_hi
-                    a = a_hi;
-                    for (int ks = 0; ks < nks; ks++, a += 16, dl += 16) umma_f16_ts(d_tmem, a, dl, idesc, 1);        // hi * W_lo
-                    a = a_hi; dh = dW_hi;
-                    for (int ks = 0; ks < nks; ks++, a += 16, dh += 16) umma_f16_ts(d_tmem, a, dh, idesc, 1);        // hi * W_hi
+                    if (NKS > 0) {
+#pragma unroll
+                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_lo + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, ks > 0);   // lo * W_hi
+#pragma unroll
+                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_lo + (uint64_t)(16 * ks), idesc, 1);        // hi * W_lo
+#pragma unroll
+                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, 1);        // hi * W_hi
+                    } else {
+                        uint64_t dh = dW_hi, dl = dW_lo;
+                        uint32_t a = a_lo;
+                        for (int ks = 0; ks < nks; ks++, a += 16, dh += 16) umma_f16_ts(d_tmem, a, dh, idesc, ks > 0);   // lo * W_hi
+                        a = a_hi;
+                        for (int ks = 0; ks < nks; ks++, a += 16, dl += 16) umma_f16_ts(d_tmem, a, dl, idesc, 1);        // hi * W_lo
+                        a = a_hi; dh = dW_hi;
+                        for (int ks = 0; ks < nks; ks++, a += 16, dh += 16) umma_f16_ts(d_tmem, a, dh, idesc, 1);        // hi * W_hi
+                    }
                     umma_commit(barAcc_full + 8 * s);
                     umma_commit(barA_free + 8 * a3);
                 }
                 __syncwarp();
+                trace(0, f, 3);
                 if (++a3 == 3) { a3 = 0; aph ^= 1u; }
             }
         }
@@ -244,12 +269,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
         };
         if (g > 0) {
             // ===================== converters: features -> A operand in TMEM =====================
-            const int pr0 = p.pair0[g], npr = p.npair[g];
-            const uint32_t ta0 = tmem_a + lane_sel + 16u * pr0;
-            const uint32_t raw0 = smem_u32(sRaw) + (uint32_t)r * rstride + 32u * pr0;
-            const uint32_t sbS = smem_u32(sS) + 32u * pr0, sbB = sbS + 16u * nck;
-            const int nrd4 = p.ldx / 4 - 2 * pr0;
-            uint32_t c3 = 0, cph = 0;
+            // Frame-parallel: converter group gi owns A stage gi and converts every third frame (all feature chunks of
+            // its row).  One conversion is a ~1000-cycle dependent chain (LDS -> FFMA2 -> F2FP -> ... -> tcgen05.st ->
+            // wait), so three frames in flight -- not more threads per frame -- is what raises the frame rate.
+            const uint32_t gi = (uint32_t)(g - 1);
+            const int npairs = nck / 2;
+            const uint32_t ta = tmem_a + lane_sel + gi * a_cols;
+            const uint32_t raw0 = smem_u32(sRaw) + (uint32_t)r * rstride;
+            const uint32_t sbS = smem_u32(sS), sbB = sbS + 16u * nck;
+            const int nrd4 = p.ldx / 4;
+            uint32_t cph = 0;
             auto split4 = [&](const float4 x, const float4 sc, const float4 of, uint32_t *hi, uint32_t *lo) {
                 const float2 a01 = fma2(make_float2(x.x, x.y), make_float2(sc.x, sc.y), make_float2(of.x, of.y));
                 const float2 a23 = fma2(make_float2(x.z, x.w), make_float2(sc.z, sc.w), make_float2(of.z, of.w));
@@ -258,29 +287,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
                 lo[0] = pack_h2(sub2(a01, unpack_h2(hi[0]))); lo[1] = pack_h2(sub2(a23, unpack_h2(hi[1])));
                 lo[2] = pack_h2(sub2(q01, unpack_h2(hi[2]))); lo[3] = pack_h2(sub2(q23, unpack_h2(hi[3])));
             };
+            uint32_t fm3 = 0;                              // f % 3, kept incrementally
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int Tt = tile_frames(tile);
-                const int nsg = (Tt + F - 1) >> p.Fshift;
                 int m, pos; int64_t off;
                 const int Te = row_info(tile * TC_ROWS + r, m, pos, off);
                 for (int phase = 0; phase < 2; phase++) {
+                    bool waited = false;                   // raw_full of the current stage already observed by this warp
                     for (int tau = 0; tau < Tt; tau++, f++) {
                         const int kk = tau >> p.Fshift, fi = tau & (F - 1);
                         const uint32_t slot = sg & (uint32_t)(nst - 1);
-                        if (fi == 0) mbar_wait(barRaw_full + 8 * slot, (sg >> p.nst_shift) & 1u);
-                        // frame of this row at tile time tau, and its position inside the staged block
-                        int t, rel;
-                        if (phase == 0) { t = tau; rel = fi; }
-                        else { t = Te - 1 - tau; rel = t - max(Te - (kk + 1) * F, 0); }
-                        const bool ok = tau < Te;
-                        const uint32_t rowp = raw0 + slot * stage_bytes + (uint32_t)(ok ? rel : 0) * rowbytes;
-                        // A stage free?  (the MMAs that read it three frames ago have completed)
-                        mbar_wait(barA_free + 8 * c3, cph ^ 1u);
-                        tc_fence_after();
-                        const uint32_t ta = ta0 + c3 * a_cols;
-#pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            if (c < npr) {
+                        if (fm3 == gi) {
+                            if (warp == 4) trace(1, f, 0);
+                            if (!waited) { mbar_wait(barRaw_full + 8 * slot, (sg >> p.nst_shift) & 1u); waited = true; }
+                            if (warp == 4) trace(1, f, 1);
+                            // frame of this row at tile time tau, and its position inside the staged block
+                            int t, rel;
+                            if (phase == 0) { t = tau; rel = fi; }
+                            else { t = Te - 1 - tau; rel = t - max(Te - (kk + 1) * F, 0); }
+                            const bool ok = tau < Te;
+                            const uint32_t rowp = raw0 + slot * stage_bytes + (uint32_t)(ok ? rel : 0) * rowbytes;
+                            // A stage free?  (the MMAs that read it three frames ago have completed)
+                            mbar_wait(barA_free + 8 * gi, cph ^ 1u);
+                            if (warp == 4) trace(1, f, 2);
+                            tc_fence_after();
+#pragma unroll 2
+                            for (int c = 0; c < npairs; c++) {
                                 float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
                                 if (ok && 2 * c < nrd4) x0 = lds4(rowp + 32u * c);
                                 if (ok && 2 * c + 1 < nrd4) x1 = lds4(rowp + 32u * c + 16u);
@@ -289,19 +321,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
                                 split4(x1, lds4(sbS + 32u * c + 16u), lds4(sbB + 32u * c + 16u), v + 4, v + 12);
                                 tmem_st16(ta + 16u * c, v);
                             }
+                            tmem_st_wait();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(barA_full + 8 * gi);
+                            cph ^= 1u;
+                            if (warp == 4) trace(1, f, 3);
                         }
-                        tmem_st_wait();
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) {
-                            mbar_arrive(barA_full + 8 * c3);
-                            if (fi == F - 1 || tau == Tt - 1) mbar_arrive(barRaw_empty + 8 * slot);
+                        if (fi == F - 1 || tau == Tt - 1) {      // leaving this stage: every converter warp releases it once
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(barRaw_empty + 8 * slot);
+                            sg++; waited = false;
                         }
-                        if (fi == F - 1 || tau == Tt - 1) sg++;
-                        if (++c3 == 3) { c3 = 0; cph ^= 1u; }
+                        if (++fm3 == 3) fm3 = 0;
                     }
                 }
-                (void)nsg;
             }
         } else {
             // ===================== recursions: one thread per utterance =====================
@@ -323,9 +357,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
 #pragma unroll
                 for (int j = 0; j < 7; j++) badv[j] = cadv[j + 1] + stay[j] - stay[j + 1];
 
-                auto fetch = [&](float (&e)[8]) {        // e'_t(j) = E[t, j] + ln A[j, j] of this thread's model
-                    const uint32_t s = f & 1u;
-                    mbar_wait(barAcc_full + 8 * s, (f >> 1) & 1u);
+                // e'_t(j) = E[t, j] + ln A[j, j] of this thread's model, frame counter fr.  (Fetching one frame ahead was
+                // measured: the extra live registers spill inside the serial recursion and the kernel gets 45 % slower.)
+                auto fetch = [&](uint32_t fr, float (&e)[8]) {
+                    const uint32_t s = fr & 1u;
+                    if (warp == 0) trace(2, fr, 0);
+                    mbar_wait(barAcc_full + 8 * s, (fr >> 1) & 1u);
+                    if (warp == 0) trace(2, fr, 1);
                     tc_fence_after();
                     uint32_t ev[8];
                     tmem_ld8(acc_col + s * (uint32_t)ncols, ev);
@@ -333,6 +371,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(barAcc_empty + 8 * s);
+                    if (warp == 0) trace(2, fr, 2);
 #pragma unroll
                     for (int j = 0; j < 8; j++) e[j] = __uint_as_float(ev[j]);
                 };
@@ -346,7 +385,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
                 for (int j = 0; j < 8; j++) U[j] = -INFINITY;
                 for (int t = 0; t < Tt; t++, f++) {
                     float e[8];
-                    fetch(e);
+                    fetch(f, e);
                     if (t < T) {
                         if (t == 0) {
                             U[0] = lb0 + e[0];
@@ -401,7 +440,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
                 }
                 for (int tau = 0; tau < Tt; tau++, f++) {
                     float e[8];
-                    fetch(e);
+                    fetch(f, e);
                     if (tau < T) {
                         const int t = T - 1 - tau;
                         float *go = p.gamma + (size_t)(off + t) * 8;
@@ -529,10 +568,37 @@ int sapr_estep_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx,
             prm.pair0[gI] = pa; prm.npair[gI] = cnt; pa += cnt;
         }
     }
-    SAPR_CUDA(ctx, cudaFuncSetAttribute(k_estep_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    prm.trace = nullptr;
+    const char *trace_path = getenv("SAPR_ET_TRACE");
+    if (trace_path) {       // tuning aid: one traced launch, timestamps to a text file
+        const size_t nrec = (size_t)ET_TRACE_ROLES * ET_TRACE_FRAMES * ET_TRACE_EVENTS;
+        long long *dtr = nullptr;
+        SAPR_CUDA(ctx, cudaMalloc(&dtr, nrec * sizeof(long long)));
+        SAPR_CUDA(ctx, cudaMemsetAsync(dtr, 0, nrec * sizeof(long long), ctx->stream));
+        prm.trace = dtr;
+        SAPR_CUDA(ctx, cudaFuncSetAttribute(k_estep_tc<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        k_estep_tc<true, 0><<<grid, TC_THREADS, L.total, ctx->stream>>>(prm);
+        SAPR_LAUNCH_CHECK(ctx);
+        std::vector<long long> h(nrec);
+        cudaMemcpyAsync(h.data(), dtr, nrec * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(dtr);
+        if (FILE *fp = fopen(trace_path, "w")) {
+            for (int ro = 0; ro < ET_TRACE_ROLES; ro++)
+                for (int fr = 0; fr < ET_TRACE_FRAMES; fr++) {
+                    fprintf(fp, "%d %d", ro, fr + 40);
+                    for (int e = 0; e < ET_TRACE_EVENTS; e++) fprintf(fp, " %lld", h[((size_t)ro * ET_TRACE_FRAMES + fr) * ET_TRACE_EVENTS + e]);
+                    fprintf(fp, "\n");
+                }
+            fclose(fp);
+        }
+        prm.trace = nullptr;
+    }
+    auto kern = (nck == 10) ? k_estep_tc<false, 5> : (nck == 4) ? k_estep_tc<false, 2> : k_estep_tc<false, 0>;
+    SAPR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     {
         ProfScope ps(ctx, 2);
-        k_estep_tc<<<grid, TC_THREADS, L.total, ctx->stream>>>(prm);
+        kern<<<grid, TC_THREADS, L.total, ctx->stream>>>(prm);
     }
     SAPR_LAUNCH_CHECK(ctx);
     return SAPR_OK;
