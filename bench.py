@@ -306,11 +306,20 @@ def main():
         dist.max_(em)
         e_val = world * Be * T_FRAMES * N_STATES / (float(em.item()) / 1e3)
         e_gbs = ESTEP_BYTES_PER_UTT * Be / (float(em.item()) / 1e3) / 1e9
+        e_traffic = None
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tc and "k_estep_tc" in tj and "k_stats_diag8" in tj:
+                e_traffic = sum(tj[k]["dram_bytes_per_launch"] / tj[k]["utterances_per_launch"] for k in ("k_estep_tc", "k_stats_diag8")) * Be
         estep = {"metric": "Baum-Welch E-step frame*state updates/s (fwd-bwd + statistics + all-reduce)",
                  "value": e_val, "unit": "updates/s", "ms_per_iteration": float(em.item()), "utterances_per_gpu": Be,
                  "roofline": {"bound": "hbm", "achieved": e_gbs, "peak": peak, "unit": "GB/s", "frac": e_gbs / peak,
+                              "kernels": ("k_estep_tc (tcgen05 emission, forward + backward sweep per tile) + k_stats_diag8"
+                                          if tc else "k_estep_fused + k_stats_diag"),
                               "fwdbwd_kernel_ms": fb_ms / n_it, "stats_kernel_ms": st_ms / n_it,
-                              "alg_bytes_per_iteration": ESTEP_BYTES_PER_UTT * Be}}
+                              "alg_bytes_per_iteration": ESTEP_BYTES_PER_UTT * Be, "traffic": e_traffic,
+                              "note": "the implementation reads the features three times (forward, backward, statistics); "
+                                      "algorithmic bytes count one read"}}
         models.mstep(stats, floor_v)
         torch.cuda.synchronize()
 
