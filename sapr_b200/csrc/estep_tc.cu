@@ -47,7 +47,7 @@ __host__ __device__ inline EtSmem et_smem_layout(int M, int nck, int ncols, int 
     L.w = 0;
     L.raw = (uint32_t)2 * (ncols / 8) * nck * 128;
     L.tr = L.raw + (uint32_t)nst * TC_ROWS * rstride;
-    L.sb = L.tr + (uint32_t)M * 5 * 16;
+    L.sb = L.tr + (uint32_t)M * TC_TRQ * 16;
     L.pad = (L.sb + (uint32_t)8 * nck * 4 + 15u) & ~15u;        // int pad_start[16], cnt[16]
     L.bar = L.pad + 32 * 4;
     L.total = L.bar + (2 * TC_MAX_STAGES + 10) * 8 + 16;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
         uint4 *dst = reinterpret_cast<uint4 *>(sW);
         for (uint32_t i = tid; i < 2 * w_plane / 16; i += TC_THREADS) dst[i] = src[i];
         float4 *dtr = reinterpret_cast<float4 *>(smem + L.tr);
-        for (int i = tid; i < M * 5; i += TC_THREADS) dtr[i] = p.trp[i];
+        for (int i = tid; i < M * TC_TRQ; i += TC_THREADS) dtr[i] = p.trp[i];
         float *dsb = reinterpret_cast<float *>(smem + L.sb);
         for (int i = tid; i < 8 * nck; i += TC_THREADS) dsb[i] = p.sb[i];
     }
@@ -348,14 +348,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
                 const int T = row_info(tile * TC_ROWS + r, m, pos, off);
                 const int u = pos >= 0 ? p.order[pos] : 0;
                 const uint32_t acc_col = tmem_acc + lane_sel + (uint32_t)(m - mbase) * 8u;   // warp-uniform: one model per quadrant
-                const float4 c03 = sTr[m * 5 + 0], c47 = sTr[m * 5 + 1], cm = sTr[m * 5 + 2];
-                const float4 st03 = sTr[m * 5 + 3], st47 = sTr[m * 5 + 4];
-                const float cadv[8] = {0.f, c03.x, c03.y, c03.z, c03.w, c47.x, c47.y, c47.z};   // into state j from j-1 (U form)
-                const float cx = c47.w, lb0 = cm.y;
-                const float stay[8] = {st03.x, st03.y, st03.z, st03.w, st47.x, st47.y, st47.z, st47.w};
-                float badv[7];          // ln A[j, j+1] - ln A[j+1, j+1]: the advance arc of state j on top of self[j+1]
-#pragma unroll
-                for (int j = 0; j < 7; j++) badv[j] = cadv[j + 1] + stay[j] - stay[j + 1];
+                // transition constants of this thread's model stay in shared memory and are re-read every frame: holding the
+                // 25 of them in registers made the recursion spill (local-memory round trips inside a serial chain)
+                const uint32_t trM = smem_u32(sTr) + (uint32_t)m * (TC_TRQ * 16u);
+                const float lb0 = sTr[m * TC_TRQ + 2].y;
 
                 // e'_t(j) = E[t, j] + ln A[j, j] of this thread's model, frame counter fr.  (Fetching one frame ahead was
                 // measured: the extra live registers spill inside the serial recursion and the kernel gets 45 % slower.)
@@ -387,10 +383,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
                     float e[8];
                     fetch(f, e);
                     if (t < T) {
+                        const float4 c03 = lds4(trM), c47 = lds4(trM + 16u), st03 = lds4(trM + 48u), st47 = lds4(trM + 64u);
+                        const float cadv[8] = {0.f, c03.x, c03.y, c03.z, c03.w, c47.x, c47.y, c47.z};   // into state j from j-1 (U form)
+                        const float stay[8] = {st03.x, st03.y, st03.z, st03.w, st47.x, st47.y, st47.z, st47.w};
                         if (t == 0) {
                             U[0] = lb0 + e[0];
                         } else {
-                            const float nx = U[7] + cx;                       // alpha[t, exit] = alpha[t-1, N] + ln A[N, exit]
+                            const float nx = U[7] + c47.w;                    // alpha[t, exit] = alpha[t-1, N] + ln A[N, exit]
 #pragma unroll
                             for (int j = 7; j >= 1; j--) U[j] = lae32(U[j - 1] + cadv[j], U[j]) + e[j];
                             const float ent = (t == 1) ? lb0 - base : -INFINITY;     // alpha[t-1, entry] is 0 at t == 1 only
@@ -426,9 +425,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
                 if (pos >= 0 && T > 0) p.loglik[u] = ll;
 
                 // ---------------- backward + gamma + xi sums (custom_hmm.py:213-322) ----------------
-                float gG[8], gO[8], gX[8], b[8], en[8];
+                float gG[8], gX[8], b[8], en[8];
+                float glast = 0.f;                                 // gamma[T-1, j] of the emitting states (0 or NaN): occ = G + it
 #pragma unroll
-                for (int j = 0; j < 8; j++) { gG[j] = 0.f; gO[j] = 0.f; gX[j] = 0.f; b[j] = -INFINITY; en[j] = 0.f; }
+                for (int j = 0; j < 8; j++) { gG[j] = 0.f; gX[j] = 0.f; b[j] = -INFINITY; en[j] = 0.f; }
                 float bx = 0.f;                                    // beta[T-1, exit] = 0
                 float atn[8];                                      // alpha-hat of the next backward frame, loaded one frame ahead
 #pragma unroll
@@ -449,9 +449,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
                             const float gl = exit_ok ? 0.f : NAN;
                             *reinterpret_cast<float4 *>(go) = make_float4(gl, gl, gl, gl);
                             *reinterpret_cast<float4 *>(go + 4) = make_float4(gl, gl, gl, gl);
-#pragma unroll
-                            for (int j = 0; j < 8; j++) gO[j] += gl;
+                            glast = gl;
                         } else {
+                            const float4 bd03 = lds4(trM + 80u), bd47 = lds4(trM + 96u);
+                            const float badv[7] = {bd03.x, bd03.y, bd03.z, bd03.w, bd47.x, bd47.y, bd47.z};
                             float at[8], self[8], nb[8];
 #pragma unroll
                             for (int j = 0; j < 8; j++) { at[j] = atn[j]; self[j] = en[j] + b[j]; }   // ln A_jj + e_{t+1}(j) + beta_{t+1}(j)
@@ -462,8 +463,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
                             }
 #pragma unroll
                             for (int j = 0; j < 7; j++) nb[j] = lae32(self[j], badv[j] + self[j + 1]);
-                            nb[7] = lae32(self[7], (cx + stay[7]) + bx);                 // ln A[N, exit] + beta[t+1, exit]
-                            const float b0 = (lb0 - stay[0]) + self[0];                  // beta[t, entry]
+                            nb[7] = lae32(self[7], bd47.w + bx);                         // ln A[N, exit] + beta[t+1, exit]
+                            const float b0 = sTr[m * TC_TRQ + 7].x + self[0];            // beta[t, entry] = ln A01 - ln A11 + self_1
                             float lg[8];
 #pragma unroll
                             for (int j = 0; j < 8; j++) lg[j] = at[j] + nb[j];
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
 #pragma unroll
                             for (int j = 0; j < 8; j++) {
                                 gm[j] = pj[j] * inv;
-                                gG[j] += gm[j]; gO[j] += gm[j];
+                                gG[j] += gm[j];
                                 const float xq = (mxl > -INFINITY) ? fexp32((at[j] + self[j]) - mxl) : 0.f;
                                 gX[j] += xq * xinv;
                             }
@@ -510,7 +511,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
                 if (pos >= 0) {
                     float *us = p.ustats + (size_t)pos * 24;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) { us[j] = gG[j]; us[8 + j] = gX[j]; us[16 + j] = gO[j]; }
+                    for (int j = 0; j < 8; j++) { us[j] = gG[j]; us[8 + j] = gX[j]; us[16 + j] = gG[j] + glast; }
                 }
             }
         }

@@ -16,6 +16,7 @@
 #define TC_LOADERS 3
 #define TC_THREADS (TC_WORKERS + 32 + 32 * TC_LOADERS)    /* + MMA warp + bulk-copy warps */
 #define TC_MAX_STAGES 4
+#define TC_TRQ 8          /* float4 per model in the transition block (k_prepare_tc) */
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers

@@ -32,10 +32,11 @@
 //   8 K elements ordered [x'_0 .. x'_3, x'^2_0 .. x'^2_3] (so a packed pair of one kind is one TMEM column).
 //   Dim index D is the constant slot: x' = 1 there; its x' weight carries the constant and its (otherwise
 //   unused) x'^2 weight the part of the constant the fp16 hi/lo pair of the first cannot represent.
-//   sb[2][4*nck] float (scale s, offset b: x' = x*s + b);  trp[M][5] float4 transition block:
+//   sb[2][4*nck] float (scale s, offset b: x' = x*s + b);  trp[M][TC_TRQ = 8] float4 transition block:
 //     [0] = (c1, c2, c3, c4)  [1] = (c5, c6, c7, cx)   c_j = ln A[j-1,j] - ln A[j-1,j-1] (advance minus stay),
 //                                                      cx = ln A[N,exit] - ln A[N,N]
 //     [2] = (ln A[exit,exit], ln A[0,1], 0, 0)   [3], [4] = stay_1 .. stay_8 = ln A[j,j] (folded into W's constant)
+//     [5], [6] = (badv_1 .. badv_7, ln A[N,exit])   [7] = (ln A[0,1] - ln A[1,1], 0, 0, 0)   (E-step backward sweep)
 __global__ void k_prepare_tc(int M, int S, int D, int nck, int ncols, const double *__restrict__ mean,
                              const double *__restrict__ var, const double *__restrict__ la, const double *__restrict__ lb,
                              __half *__restrict__ wimg, float *__restrict__ sb, float4 *__restrict__ trp) {
@@ -104,7 +105,13 @@ __global__ void k_prepare_tc(int M, int S, int D, int nck, int ncols, const doub
         v[7] = (float)(b[N] - a[N]);                                                              // cx (N == 8)
         v[8] = (float)a[S - 1]; v[9] = (float)b[0]; v[10] = 0.f; v[11] = 0.f;
         for (int j = 1; j <= 8; j++) v[11 + j] = (j <= N) ? (float)a[j] : 0.f;
-        for (int q = 0; q < 5; q++) trp[(size_t)m * 5 + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        // E-step extras: badv_j = ln A[j,j+1] - ln A[j+1,j+1] (advance arc of state j on top of self[j+1]), ln A[N,exit],
+        // ln A[0,1] - ln A[1,1]
+        float w[12];
+        for (int j = 1; j <= 7; j++) w[j - 1] = (j + 1 <= N) ? (float)(b[j] - a[j + 1]) : -INFINITY;
+        w[7] = (float)b[N]; w[8] = (float)(b[0] - a[1]); w[9] = 0.f; w[10] = 0.f; w[11] = 0.f;
+        for (int q = 0; q < 5; q++) trp[(size_t)m * TC_TRQ + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        for (int q = 0; q < 3; q++) trp[(size_t)m * TC_TRQ + 5 + q] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
     }
 }
 
@@ -127,7 +134,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(int M, int nck, int ncols, int 
     L.w = 0;
     L.raw = (uint32_t)2 * (ncols / 8) * nck * 128;
     L.tr = L.raw + (uint32_t)nst * TC_ROWS * rstride;
-    L.sb = L.tr + (uint32_t)M * 5 * 16;
+    L.sb = L.tr + (uint32_t)M * TC_TRQ * 16;
     L.base = 0;
     L.bar = (L.sb + (uint32_t)8 * nck * 4 + 15u) & ~15u;
     L.total = L.bar + (2 * TC_MAX_STAGES + 6) * 8 + 16;
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
         uint4 *dst = reinterpret_cast<uint4 *>(sW);
         for (uint32_t i = tid; i < 2 * w_plane / 16; i += TC_THREADS) dst[i] = src[i];
         float4 *dtr = reinterpret_cast<float4 *>(smem + L.tr);
-        for (int i = tid; i < M * 5; i += TC_THREADS) dtr[i] = p.trp[i];
+        for (int i = tid; i < M * TC_TRQ; i += TC_THREADS) dtr[i] = p.trp[i];
         float *dsb = reinterpret_cast<float *>(smem + L.sb);
         for (int i = tid; i < 8 * nck; i += TC_THREADS) dsb[i] = p.sb[i];
     }
@@ -375,7 +382,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
         const uint32_t ta0 = pin_reg(tmem_a + lane_sel + 16u * pr0);               // A operand, stage 0 (stage 1: + a_cols)
         const uint32_t acc0 = pin_reg(tmem_acc + lane_sel + (uint32_t)mbeg * 8u);  // accumulators, stage 0 (stage 1: + ncols)
         const uint32_t raw0 = pin_reg(smem_u32(sRaw) + (uint32_t)r * rstride + 32u * pr0);
-        const uint32_t trS = pin_reg(smem_u32(sTr) + (uint32_t)mbeg * 80u);
+        const uint32_t trS = pin_reg(smem_u32(sTr) + (uint32_t)mbeg * (TC_TRQ * 16u));
         const uint32_t sbS = pin_reg(smem_u32(sS) + 32u * pr0);
         const uint32_t sbB = sbS + 16u * nck;
         const size_t bp_model = (size_t)p.maxT * p.Bpad;                 // elements between consecutive models
@@ -464,7 +471,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
                     return acc0 + s * (uint32_t)ncols;
                 };
                 auto dbg_dump = [&](int k, int t, const uint32_t (&ev)[8]) {
-                    const float4 st0 = lds4(trS + 80u * k + 48u), st1 = lds4(trS + 80u * k + 64u);
+                    const float4 st0 = lds4(trS + (TC_TRQ * 16u) * k + 48u), st1 = lds4(trS + (TC_TRQ * 16u) * k + 64u);
                     const float st[8] = {st0.x, st0.y, st0.z, st0.w, st1.x, st1.y, st1.z, st1.w};
 #pragma unroll
                     for (int j = 0; j < 8; j++)
@@ -488,11 +495,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
                             tmem_ld_wait();
                             if (DBG && p.dbgE && act) dbg_dump(k, t, ev);
                             if (act) {
-                                const float4 cm = lds4(trS + 80u * k + 32u);
+                                const float4 cm = lds4(trS + (TC_TRQ * 16u) * k + 32u);
                                 if (t == 0) {
                                     U[k][0].x = cm.y + __uint_as_float(ev[0]);   // U_1 = ln A01 + E[0,1] + ln A11
                                 } else {
-                                    const float4 c03 = lds4(trS + 80u * k), c47 = lds4(trS + 80u * k + 16u);
+                                    const float4 c03 = lds4(trS + (TC_TRQ * 16u) * k), c47 = lds4(trS + (TC_TRQ * 16u) * k + 16u);
                                     const uint32_t bits = vit_step<true>(U[k], Ux[k], c03, c47, cm.x, cm.y, ev, t);
                                     bpt[(size_t)k * bp_model] = (uint16_t)bits;
                                     if ((t & 3) == 0) vit_renorm(U[k], Ux[k], base[k]);
@@ -519,7 +526,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
                             tmem_ld_wait();
                             if (DBG && p.dbgE && act) dbg_dump(k, t, ev);
                             if (act) {
-                                const float4 c03 = lds4(trS + 80u * k), c47 = lds4(trS + 80u * k + 16u), cm = lds4(trS + 80u * k + 32u);
+                                const float4 c03 = lds4(trS + (TC_TRQ * 16u) * k), c47 = lds4(trS + (TC_TRQ * 16u) * k + 16u), cm = lds4(trS + (TC_TRQ * 16u) * k + 32u);
                                 const uint32_t bits = vit_step<false>(U[k], Ux[k], c03, c47, cm.x, cm.y, ev, t);
                                 bpt[(size_t)k * bp_model] = (uint16_t)bits;
                                 if (rn) vit_renorm(U[k], Ux[k], base[k]);
@@ -574,7 +581,7 @@ size_t sapr_tc_image_bytes(const sapr_models *m, int *nck_out, int *ncols_out) {
     if (nck_out) *nck_out = nck;
     if (ncols_out) *ncols_out = ncols;
     return al256((size_t)2 * (ncols / 8) * nck * 64 * sizeof(__half)) + al256((size_t)8 * nck * sizeof(float)) +
-           al256((size_t)m->M * 5 * sizeof(float4));
+           al256((size_t)m->M * TC_TRQ * sizeof(float4));
 }
 
 int sapr_tc_prepare(sapr_models *m) {
