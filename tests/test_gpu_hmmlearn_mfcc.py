@@ -138,3 +138,38 @@ def test_mfcc_vs_oracle(cuda, which):
         assert np.max(np.abs(got - ref)) < (5e-2 if which == "librosa" else 5e-3), np.max(np.abs(got - ref))
     one = mx.mfcc_from_samples(sigs[0], sr, p)
     assert one.shape[0] == 13 and one.dtype == np.float32
+
+
+def test_cfg5_audio_to_words_on_device(cuda):
+    """BASELINE cfg 5 at test size: synthetic 16 kHz audio -> fused MFCC kernel (25 ms / 10 ms Hamming, 512-pt FFT, 26 mel,
+    DCT-13, pre-emphasis) -> batched Viterbi against 11 word models, features never leaving the GPU.  The recognised
+    words / paths must equal the oracle's decoding of the very same feature tensor (float64 mode: bit-exact)."""
+    from sapr_b200 import engine, mfcc_extract as mx, synth
+    rng = np.random.default_rng(9)
+    sr, B = 16000, 24
+    sigs = []
+    for u in range(B):
+        n = int(rng.integers(sr // 2, sr))
+        t = np.arange(n) / sr
+        y = sum(a * np.sin(2 * np.pi * f * t + ph) for a, f, ph in zip((0.5, 0.3, 0.2), rng.uniform(200, 3000, 3), rng.uniform(0, 6, 3)))
+        sigs.append((y + 0.05 * rng.standard_normal(n)).astype(np.float32))
+    audio = cuda.as_tensor(np.concatenate(sigs), device="cuda")
+    so = np.concatenate([[0], np.cumsum([len(s) for s in sigs])]).astype(np.int64)
+    feats, fo = mx.mfcc_batch(audio, so, mx.cfg5_params())
+    assert feats.shape[1] == 16 and fo[-1] == feats.shape[0]
+    # word models around the corpus statistics (any fixed model set exercises the path)
+    F = feats[:, :13].cpu().numpy().astype(np.float64)
+    mu, sd = F.mean(0), F.std(0) + 1e-3
+    means = np.zeros((11, 10, 13)); var = np.ones((11, 10, 13))
+    means[:, 1:-1] = mu + sd * rng.standard_normal((11, 8, 13)); var[:, 1:-1] = (sd * rng.uniform(0.7, 1.3, (11, 8, 13))) ** 2
+    A = synth.truth_models(np.zeros((11, 8, 13)), np.ones((11, 8, 13)), 0.9)[0]
+    m = engine.WordModels(11, 8, 13)
+    m.set(means, var, A)
+    batch = engine.PackedBatch(feats, cuda.as_tensor(fo, device="cuda"), 13, fo)
+    bw, bs, sc, bp = orc.viterbi_batch(F, fo, A, means, var)
+    o64 = m.viterbi(batch, None, engine.FP64, 0, want_scores=True)
+    assert np.array_equal(o64["best_word"].cpu().numpy(), bw)
+    assert np.array_equal(o64["path"].cpu().numpy().astype(np.int32), bp)
+    o32 = m.viterbi(batch, None, engine.FP32, 0, want_scores=True)      # tensor-core path, D = 13
+    assert_close(o32["scores"].cpu().numpy(), sc, 1e-6, what="scores32")
+    assert np.mean(o32["best_word"].cpu().numpy() == bw) >= 0.95
