@@ -410,13 +410,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
             constexpr int NPT = decltype(NPc)::value, MCT = decltype(MCc)::value;
             constexpr int NPMAX = NPT > 0 ? NPT : 2, MCMAX = MCT > 0 ? MCT : MG;
             const int np = NPT > 0 ? NPT : npr, mc = MCT > 0 ? MCT : mcnt;
+            const uint32_t recf = pin_reg(rec_first ? 1u : 0u);
+            // accumulator stage / phase of the frame being recursed (frame counter f): toggled, not recomputed
+            uint32_t as = f & 1u, aph = (f >> 1) & 1u;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int Tt = tile_frames(tile);
+                // tile length, and whether every row is live with exactly that length (equal-length batches: the
+                // per-row activity tests then drop out of the frame loops)
+                int Tt = 0, Tmin = 0x7fffffff;
+                for (int rr = lane; rr < TC_ROWS; rr += 32) {
+                    int64_t o;
+                    const int Tr = row_frames(tile * TC_ROWS + rr, o);
+                    Tt = max(Tt, Tr); Tmin = min(Tmin, Tr);
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    Tt = max(Tt, __shfl_xor_sync(0xffffffffu, Tt, o));
+                    Tmin = min(Tmin, __shfl_xor_sync(0xffffffffu, Tmin, o));
+                }
+                const bool uniform = Tmin == Tt;
                 const int ul = tile * TC_ROWS + r;
                 int64_t off;
                 const int Te = row_frames(ul, off);
                 const bool live = ul < p.nu;
-                const uint32_t sg0 = sg;
 
                 float2 U[MCMAX][4];
                 float Ux[MCMAX], base[MCMAX];
@@ -428,22 +442,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
                     for (int j = 0; j < 4; j++) U[k][j] = make_float2(-INFINITY, -INFINITY);
                 }
 
-                // frame t of this tile -> standardise, square, split, store into A-operand stage fr & 1
-                auto convert = [&](int t, uint32_t fr) {      // frames are converted in order: c3 tracks fr % 3
-                    const int kk = t >> p.Fshift, fi = t & (F - 1);
-                    const uint32_t sgk = sg0 + (uint32_t)kk, slot = sgk & (uint32_t)(nst - 1);
+                // conversion cursor: frames are converted strictly in order, so the ring position is kept incrementally
+                int cfi = 0, ct = 0;                                        // frame inside the stage, frame of the tile
+                uint32_t cslot = sg & (uint32_t)(nst - 1), crph = (sg >> p.nst_shift) & 1u;
+                uint32_t crow = raw0 + cslot * stage_bytes;
+                // frame ct of this tile -> standardise, square, split, store into A-operand stage c3 (= frame counter mod 3)
+                auto convert = [&](auto UNIc, uint32_t fr) {
+                    constexpr bool UNI = decltype(UNIc)::value;
                     if (TRACE && trole >= 0) trace(trole, fr, 0);
-                    if (fi == 0) mbar_wait(barRaw_full + 8 * slot, (sgk >> p.nst_shift) & 1u);
+                    if (cfi == 0) mbar_wait(barRaw_full + 8 * cslot, crph);
                     if (TRACE && trole >= 0) trace(trole, fr, 1);
-                    const uint32_t rowp = raw0 + slot * stage_bytes + (uint32_t)fi * rowbytes;
-                    const bool ok = t < Te;                      // Te == 0 for rows beyond the batch
+                    const bool ok = UNI || ct < Te;              // Te == 0 for rows beyond the batch
                     const uint32_t ta = ta0 + c3 * a_cols;
 #pragma unroll
                     for (int c = 0; c < NPMAX; c++) {
                         if (c < np) {
                             float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-                            if (ok && 2 * c < nrd4) x0 = lds4(rowp + 32u * c);
-                            if (ok && 2 * c + 1 < nrd4) x1 = lds4(rowp + 32u * c + 16u);
+                            if (ok && 2 * c < nrd4) x0 = lds4(crow + 32u * c);
+                            if (ok && 2 * c + 1 < nrd4) x1 = lds4(crow + 32u * c + 16u);
                             uint32_t v[16];      // [hi chunk 0 | hi chunk 1 | lo chunk 0 | lo chunk 1] = 16 consecutive TMEM columns
                             split4(x0, lds4(sbS + 32u * c), lds4(sbB + 32u * c), v, v + 8);
                             split4(x1, lds4(sbS + 32u * c + 16u), lds4(sbB + 32u * c + 16u), v + 4, v + 12);
@@ -453,23 +469,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
                     tmem_st_wait();
                     tc_fence_before();
                     __syncwarp();
+                    const bool last = (cfi == F - 1) || (ct == Tt - 1);
                     if (lane == 0) {
                         mbar_arrive(barA_full + 8 * c3);
-                        if (fi == F - 1 || t == Tt - 1) mbar_arrive(barRaw_empty + 8 * slot);
+                        if (last) mbar_arrive(barRaw_empty + 8 * cslot);
                     }
                     if (++c3 == 3) c3 = 0;
+                    ct++;
+                    if (last) {                                   // next stage of the ring
+                        cfi = 0; sg++;
+                        if (++cslot == (uint32_t)nst) { cslot = 0; crph ^= 1u; }
+                        crow = raw0 + cslot * stage_bytes;
+                    } else {
+                        cfi++; crow += rowbytes;
+                    }
                     if (TRACE && trole >= 0) trace(trole, fr, 2);
                 };
-                // accumulators of frame fr ready?  (their release needs no barrier: a warp signals A_full(fr + 2) only after
-                // its last tcgen05.ld of frame fr, and the MMAs of frame fr + 2 wait for every warp's A_full(fr + 2))
-                auto acc_ready = [&](uint32_t fr) -> uint32_t {
-                    const uint32_t s = fr & 1u;
-                    if (TRACE && trole >= 0) trace(trole, fr, 3);
-                    mbar_wait(barAcc_full + 8 * s, (fr >> 1) & 1u);
-                    if (TRACE && trole >= 0) trace(trole, fr, 4);
+                // accumulators of the current frame ready?  (their release needs no barrier: a warp signals A_full(f + 2) only
+                // after its last tcgen05.ld of frame f, and the MMAs of frame f + 2 wait for every warp's A_full(f + 2))
+                auto acc_ready = [&]() -> uint32_t {
+                    if (TRACE && trole >= 0) trace(trole, f, 3);
+                    mbar_wait(barAcc_full + 8 * as, aph);
+                    if (TRACE && trole >= 0) trace(trole, f, 4);
                     tc_fence_after();
-                    return acc0 + s * (uint32_t)ncols;
+                    return acc0 + as * (uint32_t)ncols;
                 };
+                auto acc_next = [&]() { aph ^= as; as ^= 1u; };       // phase flips when the stage wraps from 1 to 0
                 auto dbg_dump = [&](int k, int t, const uint32_t (&ev)[8]) {
                     const float4 st0 = lds4(trS + (TC_TRQ * 16u) * k + 48u), st1 = lds4(trS + (TC_TRQ * 16u) * k + 64u);
                     const float st[8] = {st0.x, st0.y, st0.z, st0.w, st1.x, st1.y, st1.z, st1.w};
@@ -477,15 +502,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
                     for (int j = 0; j < 8; j++)
                         p.dbgE[(size_t)(off + t) * ncols + (mbeg + k) * 8 + j] = __uint_as_float(ev[j]) - st[j];
                 };
+                constexpr std::integral_constant<bool, false> RAGGED{};
+                constexpr std::integral_constant<bool, true> UNIFORM{};
 
-                if (Tt > 0) convert(0, f);
-                if (rec_first && Tt > 1) convert(1, f + 1);
+                if (Tt > 0) convert(RAGGED, f);
+                if (recf && Tt > 1) convert(RAGGED, f + 1);
                 const int Tearly = min(Tt, 9);
                 int t = 0;
                 // ---- frames 0 .. 8: entry state, closed exit (generic step) ----
                 for (; t < Tearly; t++, f++) {
-                    if (!rec_first && t + 1 < Tt) convert(t + 1, f + 1);
-                    const uint32_t tacc = acc_ready(f);
+                    if (!recf && t + 1 < Tt) convert(RAGGED, f + 1);
+                    const uint32_t tacc = acc_ready();
+                    acc_next();
                     const bool act = t < Te;
 #pragma unroll
                     for (int k = 0; k < MCMAX; k++) {
@@ -510,35 +538,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
                     tc_fence_before();
                     if (TRACE && trole >= 0) trace(trole, f, 5);
                     bpt += bp_frame;
-                    if (rec_first && t + 2 < Tt) convert(t + 2, f + 2);
+                    if (recf && t + 2 < Tt) convert(RAGGED, f + 2);
                 }
                 // ---- steady state: no entry arc, exit open ----
-                for (; t < Tt; t++, f++) {
-                    if (!rec_first && t + 1 < Tt) convert(t + 1, f + 1);
-                    const uint32_t tacc = acc_ready(f);
-                    const bool act = t < Te;
-                    const bool rn = (t & 3) == 0;
+                auto steady = [&](auto UNIc) {
+                    constexpr bool UNI = decltype(UNIc)::value;
+                    for (; t < Tt; t++, f++) {
+                        if (!recf && t + 1 < Tt) convert(UNIc, f + 1);
+                        const uint32_t tacc = acc_ready();
+                        acc_next();
+                        const bool act = UNI || t < Te;
+                        const bool rn = (t & 3) == 0;
 #pragma unroll
-                    for (int k = 0; k < MCMAX; k++) {
-                        if (k < mc) {
-                            uint32_t ev[8];
-                            tmem_ld8(tacc + 8u * k, ev);
-                            tmem_ld_wait();
-                            if (DBG && p.dbgE && act) dbg_dump(k, t, ev);
-                            if (act) {
-                                const float4 c03 = lds4(trS + (TC_TRQ * 16u) * k), c47 = lds4(trS + (TC_TRQ * 16u) * k + 16u), cm = lds4(trS + (TC_TRQ * 16u) * k + 32u);
-                                const uint32_t bits = vit_step<false>(U[k], Ux[k], c03, c47, cm.x, cm.y, ev, t);
-                                bpt[(size_t)k * bp_model] = (uint16_t)bits;
-                                if (rn) vit_renorm(U[k], Ux[k], base[k]);
+                        for (int k = 0; k < MCMAX; k++) {
+                            if (k < mc) {
+                                uint32_t ev[8];
+                                tmem_ld8(tacc + 8u * k, ev);
+                                tmem_ld_wait();
+                                if (DBG && p.dbgE && act) dbg_dump(k, t, ev);
+                                if (act) {
+                                    const float4 c03 = lds4(trS + (TC_TRQ * 16u) * k), c47 = lds4(trS + (TC_TRQ * 16u) * k + 16u), cm = lds4(trS + (TC_TRQ * 16u) * k + 32u);
+                                    const uint32_t bits = vit_step<false>(U[k], Ux[k], c03, c47, cm.x, cm.y, ev, t);
+                                    bpt[(size_t)k * bp_model] = (uint16_t)bits;
+                                    if (rn) vit_renorm(U[k], Ux[k], base[k]);
+                                }
                             }
                         }
+                        tc_fence_before();
+                        if (TRACE && trole >= 0) trace(trole, f, 5);
+                        bpt += bp_frame;
+                        if (recf && t + 2 < Tt) convert(UNIc, f + 2);
                     }
-                    tc_fence_before();
-                    if (TRACE && trole >= 0) trace(trole, f, 5);
-                    bpt += bp_frame;
-                    if (rec_first && t + 2 < Tt) convert(t + 2, f + 2);
-                }
-                sg = sg0 + (uint32_t)((Tt + F - 1) >> p.Fshift);
+                };
+                if (uniform) steady(UNIFORM); else steady(RAGGED);
                 if (live) {
 #pragma unroll
                     for (int k = 0; k < MCMAX; k++)
