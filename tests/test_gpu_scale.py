@@ -1,0 +1,107 @@
+"""Parity at BASELINE.json's full sizes through size-independent properties (no oracle run is affordable at
+100 000 x 11 x 200): structural invariants of the reference's decode / E-step, agreement of the fp32 tensor-core
+path with the float64 verification kernels, an oracle check on a fixed sub-sample, and shard invariance."""
+import numpy as np
+import pytest
+
+from conftest import assert_close
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+M, N, D, T = 11, 8, 39, 200
+
+
+@pytest.fixture(scope="module")
+def big():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from sapr_b200 import engine, synth
+    dev = torch.device("cuda", 0)
+    B = 100_000
+    X, offsets, labels, mu, sd = synth.device_corpus(B, M, N, D, T, 20241118 + 2, dev)
+    A, means, var = synth.truth_models(mu, sd, 0.9)
+    m = engine.WordModels(M, N, D)
+    m.set(means, var, A)
+    batch = engine.PackedBatch(X, offsets, D, offsets.cpu().numpy(), labels)
+    return dict(eng=engine, torch=torch, m=m, batch=batch, labels=labels, A=A, means=means, var=var, B=B)
+
+
+def test_cfg2_viterbi_full_size_properties(big):
+    eng, torch, m, batch, B = big["eng"], big["torch"], big["m"], big["batch"], big["B"]
+    o32 = m.viterbi(batch, None, eng.FP32, 0, want_scores=True, want_path=True)
+    o64 = m.viterbi(batch, None, eng.FP64, 0, want_scores=True, want_path=True)
+    sc32, sc64 = o32["scores"], o64["scores"]
+    # the winner is the strict-'>' arg-max of the scores (decoder.py:44) and its score is reported
+    for o, sc in ((o32, sc32), (o64, sc64)):
+        bw = o["best_word"].long()
+        assert torch.equal(bw, sc.argmax(dim=1))
+        assert torch.equal(o["best_score"], sc.gather(1, bw.view(-1, 1)).view(-1))
+    # fp32 tensor-core scores against float64: stated tolerance rel 1e-6
+    rel = ((sc32 - sc64).abs() / sc64.abs()).max().item()
+    assert rel < 1e-6, rel
+    # recognised words: identical except float64 near-ties.  (Accuracy against the labels is NOT a property of the
+    # reference's decode: once open, its exit state is free, so paths park there early -- SURVEY D9 -- and the winner is
+    # decided by the first few frames; the oracle sub-sample below is the check that this is reproduced.)
+    same = (o32["best_word"] == o64["best_word"]).float().mean().item()
+    assert same > 0.9999, same
+    # state paths: left-to-right, start in state 1, end in the exit state S-1, one step at a time (custom_hmm.py:505-512)
+    for o in (o32, o64):
+        p = o["path"].view(B, T).to(torch.int16)
+        assert int(p[:, 0].min()) >= 0 and int(p[:, -1].min()) == N + 1 and int(p[:, -1].max()) == N + 1
+        d = p[:, 1:] - p[:, :-1]
+        assert int(d.min()) >= 0 and int(d.max()) <= 1
+    agree = (o32["path"] == o64["path"]).float().mean().item()
+    assert agree > 0.9995, agree
+    # fixed sub-sample against the CPU oracle (float64: bit-exact words, paths; scores 1e-12)
+    ids = np.arange(0, B, B // 256)[:256]
+    Xs = batch.X.view(B, T, -1)[torch.as_tensor(ids, device=batch.X.device)].reshape(-1, batch.ldx)[:, :D].cpu().numpy()
+    offs = (np.arange(len(ids) + 1) * T).astype(np.int64)
+    bw, bs, sc, bp = orc.viterbi_batch(Xs.astype(np.float64), offs, big["A"], big["means"], big["var"])
+    assert np.array_equal(o64["best_word"].cpu().numpy()[ids], bw)
+    assert_close(sc64.cpu().numpy()[ids], sc, 1e-12, what="scores vs oracle")
+    assert np.array_equal(o64["path"].view(B, T).cpu().numpy()[ids].reshape(-1).astype(np.int32), bp)
+    # shard invariance: decoding a contiguous shard gives the same answers (no cross-utterance arithmetic)
+    half = B // 2
+    sub = eng.PackedBatch(batch.X[half * T:], (batch.offsets[half:] - half * T).contiguous(), D,
+                          batch.offsets_host[half:] - half * T, None)
+    os_ = m.viterbi(sub, None, eng.FP32, 0, want_scores=True, want_path=True)
+    assert torch.equal(os_["best_word"], o32["best_word"][half:])
+    assert torch.equal(os_["scores"], sc32[half:])
+    assert torch.equal(os_["path"], o32["path"][half * T:])
+
+
+def test_cfg3_estep_full_size_properties(big):
+    eng, torch, m, batch, B, labels = big["eng"], big["torch"], big["m"], big["batch"], big["B"], big["labels"]
+    order = eng.group_by_model(labels)
+    s32, l32, _ = m.estep(batch, labels, order, eng.FP32)
+    s64, l64, _ = m.estep(batch, labels, order, eng.FP64)
+    assert_close(l32.cpu().numpy(), l64.cpu().numpy(), 1e-6, what="loglik fp32 vs fp64")
+    S = N + 2
+    st32, st64 = m.unpack_stats(s32), m.unpack_stats(s64)
+    # gamma rows sum to one; the last row is one-hot on the exit state and row 0 shares its mass with the entry state
+    # (SURVEY D4): the emitting occupancies of a word add up to between T - 2 and T - 1 per utterance
+    # (custom_hmm.py:248-257, :372-379); the rows t <= T-2 that G sums hold the same mass
+    counts = np.bincount(labels.cpu().numpy(), minlength=M)
+    for st in (st32, st64):
+        per_utt = st["occ"][:, 1:-1].sum(1) / counts
+        assert np.all(per_utt > T - 2 - 1e-3) and np.all(per_utt <= T - 1 + 1e-3), per_utt
+        assert np.max(np.abs(st["G"][:, 1:-1].sum(1) - st["occ"][:, 1:-1].sum(1))) < 1e-3 * counts.max()
+        assert np.all(st["Xi"][:, 1:-1] <= st["G"][:, 1:-1] * (1 + 1e-6))          # self-loop mass <= occupancy
+    # fp32 statistics against float64
+    assert np.max(np.abs(st32["occ"] - st64["occ"]) / (1.0 + st64["occ"])) < 2e-5
+    assert np.max(np.abs(st32["Xi"] - st64["Xi"]) / (1.0 + st64["Xi"])) < 2e-5
+    sig = np.sqrt(big["var"])
+    occ = np.maximum(st64["occ"], 1.0)[:, :, None]
+    assert np.max(np.abs(st32["s1"] - st64["s1"]) / occ / sig) < 1e-4              # mean shift in units of sigma
+    assert np.max(np.abs(st32["s2"] - st64["s2"]) / occ / sig ** 2) < 1e-3         # variance, relative
+    # the reduced statistics of two shards equal the statistics of the whole batch (what the NCCL all-reduce sums)
+    half = B // 2
+    tot = None
+    for a, b in ((0, half), (half, B)):
+        sub = eng.PackedBatch(batch.X[a * T:b * T], (batch.offsets[a:b + 1] - a * T).contiguous(), D,
+                              batch.offsets_host[a:b + 1] - a * T, None)
+        s, _, _ = m.estep(sub, labels[a:b].contiguous(), None, eng.FP64)
+        tot = s if tot is None else tot + s
+    assert_close(tot.cpu().numpy(), s64.cpu().numpy(), 1e-10, atol=1e-7, what="sharded stats")
