@@ -65,7 +65,8 @@ int sapr_sync(sapr_ctx *ctx);
 /* Per-kernel device timing for bench.py's roofline: when enabled, CUDA events bracket every launch of the
  * dominant kernels on the ctx stream.  sapr_profile_read synchronises, then returns the summed duration (ms)
  * and launch count of kernel class `which` (0 = fused Viterbi, 1 = Viterbi finish/back-trace,
- * 2 = fused E-step forward/backward, 3 = E-step feature statistics) since the last sapr_profile(ctx, 1). */
+ * 2 = fused E-step forward/backward, 3 = E-step feature statistics, 4 = ergodic tensor-core emission,
+ * 5 = ergodic tensor-core forward) since the last sapr_profile(ctx, 1). */
 int sapr_profile(sapr_ctx *ctx, int enable);
 int sapr_profile_read(sapr_ctx *ctx, int which, double *ms, int64_t *launches);
 
@@ -168,6 +169,15 @@ int sapr_hl_score(sapr_ctx *ctx, sapr_models *m, int mi, const float *X, int ldx
                   int64_t total_frames, double *logprob);
 int sapr_hl_decode(sapr_ctx *ctx, sapr_models *m, int mi, const float *X, int ldx, const int64_t *offsets, int B,
                    int64_t total_frames, double *logprob, int32_t *path);
+/* Tensor-core forward (score) for large dense models: S in {64, 128, 192, 256}, D <= 39, fp32 scaled linear-domain
+ * recursion; both contractions run on tcgen05 (ergodic_tc.cu): the emission [x', x'^2, 1] . W_e per frame and the
+ * [128 utterances x S] . [S x S] transition product per frame.  Arguments as sapr_hl_score (which stays the float64
+ * verification mode) except max_T, an upper bound on the utterance length that sizes the emission staging
+ * (an utterance longer than max_T scores NaN).  Transition weights are fp16 (2^-12 relative), the state vector fp16 hi/lo:
+ * |d logP| <= 5e-6 |logP| + 2e-4 T against the float64 kernel.  Replaces hmmlearn GaussianHMM.score as called at
+ * hmmlearn_hmm.py:46-75. */
+int sapr_ergodic_score(sapr_ctx *ctx, sapr_models *m, int mi, const float *X, int ldx, const int64_t *offsets, int B,
+                       int max_T, double *logprob);
 /* stats = [start S | trans S*S | post S | obs S*D | obs2 S*D] float64, zeroed by the call */
 int64_t sapr_hl_stats_len(int S, int D);
 int sapr_hl_estep(sapr_ctx *ctx, sapr_models *m, int mi, const float *X, int ldx, const int64_t *offsets, int B,

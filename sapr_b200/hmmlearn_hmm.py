@@ -112,13 +112,24 @@ class GaussianHMM:
     def _batch(X, lengths):
         return PackedBatch.from_frames(np.asarray(X), lengths)
 
-    def score(self, X, lengths=None):
+    def score_each(self, X, lengths=None, precision="float64"):
+        """Per-sequence log-probabilities (device float64 tensor).  ``precision="float64"`` is the log-domain
+        verification mode; ``"tc"`` runs the fp32 tensor-core scaled forward of csrc/ergodic_tc.cu (dense models
+        with 64/128/192/256 states, BASELINE cfg 4)."""
         torch = _torch()
         m = self._models()
         b = self._batch(X, lengths)
         lp = torch.zeros(b.B, dtype=torch.float64, device=b.X.device)
-        m.ctx.check(m.lib.sapr_hl_score(m.ctx.h, m.h, 0, ptr(b.X), b.ldx, ptr(b.offsets), b.B, b.total_frames, ptr(lp)))
-        return float(lp.cpu().numpy().sum())
+        if precision not in ("float64", "tc"):
+            raise ValueError("precision must be 'float64' or 'tc'")
+        if precision == "float64":
+            m.ctx.check(m.lib.sapr_hl_score(m.ctx.h, m.h, 0, ptr(b.X), b.ldx, ptr(b.offsets), b.B, b.total_frames, ptr(lp)))
+        else:
+            m.ctx.check(m.lib.sapr_ergodic_score(m.ctx.h, m.h, 0, ptr(b.X), b.ldx, ptr(b.offsets), b.B, b.max_T, ptr(lp)))
+        return lp
+
+    def score(self, X, lengths=None, precision="float64"):
+        return float(self.score_each(X, lengths, precision).cpu().numpy().sum())
 
     def decode(self, X, lengths=None, algorithm=None):
         torch = _torch()

@@ -83,6 +83,40 @@ def test_large_ergodic_score_decode_vs_oracle(cuda):
         model.fit(X, lengths)
 
 
+@pytest.mark.parametrize("S,D", [(256, 39), (128, 13), (64, 39)])
+def test_ergodic_tensor_core_score_vs_float64(cuda, S, D):
+    """BASELINE cfg 4: the fp32 tensor-core scaled forward (csrc/ergodic_tc.cu) against the float64 log-domain kernel on
+    the same device batch -- more than one 128-utterance tile, ragged lengths down to one frame, a sparse row in the
+    transition matrix.  Tolerance (include/sapr_b200.h): fp16 transition weights (2^-12 relative, one entry dominates a
+    peaked sum) + fp16 hi/lo emission operands give |d logP| <= 5e-6 |logP| + 2e-4 T."""
+    from sapr_b200.hmmlearn_hmm import GaussianHMM
+    rng = np.random.default_rng(S + D)
+    means = 2.0 * rng.standard_normal((S, D)); var = rng.uniform(0.5, 1.5, (S, D)) ** 2
+    tm = rng.dirichlet(np.ones(S), size=S); sp = rng.dirichlet(np.ones(S))
+    tm[3] = 0.0; tm[3, 3] = 0.7; tm[3, 4] = 0.3                    # a left-to-right style row inside the dense matrix
+    lengths = [int(x) for x in rng.integers(1, 90, size=150)]
+    lengths[0], lengths[1], lengths[140] = 1, 2, 120
+    states = np.empty(sum(lengths), dtype=np.int64)
+    o = 0
+    for T in lengths:                                             # hidden paths drawn from the chain itself
+        st = rng.choice(S, p=sp)
+        for t in range(T):
+            states[o + t] = st
+            st = rng.choice(S, p=tm[st])
+        o += T
+    X = (means[states] + np.sqrt(var[states]) * rng.standard_normal((sum(lengths), D))).astype(np.float32)
+    model = GaussianHMM(n_components=S, covariance_type="diag", n_iter=1, init_params="")
+    model.means_, model.covars_, model.transmat_, model.startprob_ = means, var, tm, sp
+    ref = model.score_each(X, lengths).cpu().numpy()
+    got = model.score_each(X, lengths, precision="tc").cpu().numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - ref)
+    tol = 5e-6 * np.abs(ref) + 2e-4 * np.asarray(lengths)
+    print("ergodic tc: max err", err.max(), "max err/tol", (err / tol).max())
+    assert (err <= tol).all(), (err.max(), (err / tol).max())
+    assert abs(model.score(X, lengths, precision="tc") - ref.sum()) <= 5e-6 * abs(ref.sum())
+
+
 def test_fit_vs_oracle(cuda, rung1_d13):
     model, X, lengths, (means, var, tm, sp) = _setup(rung1_d13, w=2)
     offs = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
