@@ -174,7 +174,9 @@ int sapr_hl_decode(sapr_ctx *ctx, sapr_models *m, int mi, const float *X, int ld
  * [128 utterances x S] . [S x S] transition product per frame.  Arguments as sapr_hl_score (which stays the float64
  * verification mode) except max_T, an upper bound on the utterance length that sizes the emission staging
  * (an utterance longer than max_T scores NaN).  Transition weights are fp16 (2^-12 relative), the state vector fp16 hi/lo:
- * |d logP| <= 5e-6 |logP| + 2e-4 T against the float64 kernel.  Replaces hmmlearn GaussianHMM.score as called at
+ * |d logP| <= 5e-6 |logP| + 2e-4 T against the float64 kernel.  Operand range: transition probabilities below 2^-39 and
+ * posterior mass below 2^-39 of a frame's total count as zero (normal precision above 2^-29); a sequence whose likelihood
+ * is carried only through such tails needs the float64 mode.  Replaces hmmlearn GaussianHMM.score as called at
  * hmmlearn_hmm.py:46-75. */
 int sapr_ergodic_score(sapr_ctx *ctx, sapr_models *m, int mi, const float *X, int ldx, const int64_t *offsets, int B,
                        int max_T, double *logprob);

@@ -6,13 +6,15 @@
 // against this repo's float64 restatement).  fp32 production mode; the float64 path of hmmlearn.cu is the verification mode.
 //
 // Scaled linear-domain forward recursion, 128 utterances per CTA at the same frame index:
-//     v_t(j) = b_t(j) * sum_i alpha^_{t-1}(i) A(i, j),   b_t(j) = exp(lf_t(j) - m_t),  m_t = max_j lf_t(j)
-//     alpha^_t = v_t / V_t,  V_t = sum_j v_t(j),          log P = sum_t (m_t + ln V_t)
+//     v_t(j) = kappa_t b_t(j) * sum_i alpha^_{t-1}(i) A(i, j),   b_t(j) = exp(lf_t(j) - m_t),  m_t = max_j lf_t(j)
+//     alpha^_t = v_t,  kappa_{t+1} = C / sum_j v_t(j)  (the normaliser lags one frame, so the products go straight from the
+//     accumulator into the next A operand; a frame whose mass collapses is rewritten with its exact normaliser),
+//     log P = sum_t (m_t - ln kappa_t) + ln sum_j alpha^_{T-1}(j)
 // The contraction over i is one [128 x S] . [S x S] product per frame on tcgen05: the A operand (alpha^, fp16 hi/lo
 // split, 22 bits) is written by the threads that own the rows straight into TMEM, the transition matrix (fp16, S*S*2
 // bytes = 128 KB at S = 256) stays resident in shared memory, the fp32 accumulator [128 x S] lives in TMEM and
-// tcgen05.ld hands thread (row r, quarter g) its S/4 states.  TMEM is full at S = 256 (accumulator 256 columns + A operand
-// 256 columns), so v_t is parked in the accumulator columns between the two worker passes (sum, then normalise).
+// tcgen05.ld hands thread (row r, quarter g) its S/4 states.  While the tensor pipe runs frame t's product, the worker
+// threads load frame t's emissions and turn them into kappa_t b_t(j) in registers.
 // Emissions are a second tensor-core contraction, [x', x'^2, 1] . W_e (k_erg_emission_tc, the operand construction of
 // viterbi_tc.cu with S columns), written to HBM as fp32 in the layout the forward kernel reads coalesced:
 //     lf[tile][t][j/4][row][4],  rmax[tile][t][quarter][row]     (row = utterance within the 128-utterance tile)
@@ -23,9 +25,9 @@
 
 #define ERG_MAX_S 256
 #define ERG_WS_BYTES ((size_t)24 << 30)   /* emission staging per chunk of tiles */
-#define ERG_W_SCALE 256.0          /* weight image = 256 A: keeps small transition probabilities out of the fp16 subnormals */
+#define ERG_W_SCALE 32768.0        /* weight image = 2^15 A: fp16 then spans transition probabilities from 1 down to 2^-39 (normal above 2^-29) */
 #define ERG_ALPHA_SCALE 32768.0f   /* stored vector = 32768 alpha^ (sum over states): fp16 hi/lo parts stay normal */
-#define ERG_LN_SCALE 15.942385152878742   /* ln(256 * 32768) */
+#define ERG_RESCUE (1.0f / 4194304.0f)  /* redo a frame exactly when its lagged-normalised mass falls below this: the dominant entry keeps >= 15 bits */
 
 // ------------------------------------------------------------------------------------------------
 // transition image: W[n = j][k = i] = 256 A[i][j] as fp16, K-major no-swizzle core matrices (8 rows x 8 halves)
@@ -265,14 +267,15 @@ __global__ void __launch_bounds__(ERG_THREADS, 1) k_erg_emission_tc(const ErgPar
 
 // ------------------------------------------------------------------------------------------------
 // forward recursion over the emissions of k_erg_emission_tc
+template <int NCH>   // 16-state chunks per thread = S / 64
 __global__ void __launch_bounds__(ERG_THREADS, 1) k_erg_forward_tc(const ErgParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int S = p.S;
+    constexpr int S = 64 * NCH;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t w_bytes = (uint32_t)S * S * 2u;
     unsigned char *sW = smem;
-    float *sSum = reinterpret_cast<float *>(smem + w_bytes);                    // [2][128][4] partial row sums (frame parity)
-    float *sPi = sSum + 2 * TC_ROWS * TC_GROUPS;                               // [S]
+    float *sSum = reinterpret_cast<float *>(smem + w_bytes);                    // [2][128][4] partial row sums (frame parity) + [128][4] rare path
+    float *sPi = sSum + 3 * TC_ROWS * TC_GROUPS;                               // [S]
     uint64_t *sBar = reinterpret_cast<uint64_t *>(sPi + S);
     uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 2);
     const uint32_t barA_full = smem_u32(sBar), barAcc_full = barA_full + 8;
@@ -322,8 +325,8 @@ __global__ void __launch_bounds__(ERG_THREADS, 1) k_erg_forward_tc(const ErgPara
         // ===================== workers: thread (row r, quarter g) owns S/4 states =====================
         const int q = warp & 3, g = warp >> 2, r = q * 32 + lane;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        const int spt = S / TC_GROUPS, j0 = g * spt;              // states per thread, first state
-        const int nch = spt / 16;
+        constexpr int spt = S / TC_GROUPS;                        // states per thread
+        const int j0 = g * spt;
         for (int tl = blockIdx.x; tl < p.ntiles; tl += gridDim.x) {
             const int Tt = erg_tile_frames(p, p.tile0 + tl, lane);
             const int u = (p.tile0 + tl) * TC_ROWS + r;
@@ -332,80 +335,156 @@ __global__ void __launch_bounds__(ERG_THREADS, 1) k_erg_forward_tc(const ErgPara
             const int T = min(Tfull, p.maxT);
             const float4 *lft = reinterpret_cast<const float4 *>(p.lf + (size_t)tl * p.maxT * S * TC_ROWS) + (size_t)(j0 / 4) * TC_ROWS + r;
             const float *rmt = p.rmax + (size_t)tl * p.maxT * TC_GROUPS * TC_ROWS + r;
-            double logp = 0.0;
+            // a_t = Z_t * (stored vector): logz = ln Z_t;  kappa = scale applied to this frame's products
+            double logz = 0.0;
+            float kappa = ERG_ALPHA_SCALE, Vlast = 0.f;
+            bool alive = true;
             for (int t = 0; t < Tt; t++, fa++) {
                 const bool act = t < T;
+                // ---- in the shadow of this frame's transition product: emissions -> bk_j = exp(lf_j - m) * kappa ----
+                float bk[spt];
                 float m = 0.f;
                 if (act) {
                     const float *rm = rmt + (size_t)t * TC_GROUPS * TC_ROWS;
-                    m = fmaxf(fmaxf(rm[0], rm[TC_ROWS]), fmaxf(rm[2 * TC_ROWS], rm[3 * TC_ROWS]));
+                    m = fmaxf(fmaxf(__ldg(rm), __ldg(rm + TC_ROWS)), fmaxf(__ldg(rm + 2 * TC_ROWS), __ldg(rm + 3 * TC_ROWS)));
+                    const float4 *lfr = lft + (size_t)t * (S / 4) * TC_ROWS;
+#pragma unroll
+                    for (int i4 = 0; i4 < spt / 4; i4++) {
+                        const float4 l = __ldg(lfr + (size_t)i4 * TC_ROWS);
+                        bk[4 * i4] = l.x; bk[4 * i4 + 1] = l.y; bk[4 * i4 + 2] = l.z; bk[4 * i4 + 3] = l.w;
+                    }
+                    const float ml2 = m * 1.4426950408889634f;
+#pragma unroll
+                    for (int i = 0; i < spt; i++) {
+                        float b;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(fmaf(bk[i], 1.4426950408889634f, -ml2)));
+                        bk[i] = b * kappa;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < spt; i++) bk[i] = 0.f;
                 }
                 if (t >= 1) {
                     mbar_wait(barAcc_full, fc & 1u);
                     fc++;
                     tc_fence_after();
                 }
-                const float4 *lfr = lft + (size_t)t * (S / 4) * TC_ROWS;
-                const float ml2 = m * 1.4426950408889634f;
-                // pass 1: v_j = b_t(j) * s_j, written back over the accumulator columns; partial row sum
-                float lsum = 0.f;
-                for (int c = 0; c < nch; c++) {
-                    uint32_t ev[16];
-                    float4 l[4];
+                // ---- v_j = s_j * bk_j straight into the A operand (fp16 hi/lo), partial row sum ----
+                auto emit = [&]() -> float {
+                    float lsum = 0.f;
 #pragma unroll
-                    for (int i4 = 0; i4 < 4; i4++) l[i4] = act ? __ldg(lfr + (size_t)(4 * c + i4) * TC_ROWS) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (t >= 1) {
-                        tmem_ld16(tmem_acc + lane_sel + (uint32_t)(j0 + 16 * c), ev);
-                        tmem_ld_wait();
-                    } else {
+                    for (int c = 0; c < NCH; c++) {
+                        uint32_t ev[16];
+                        if (t >= 1) {
+                            tmem_ld16(tmem_acc + lane_sel + (uint32_t)(j0 + 16 * c), ev);
+                            tmem_ld_wait();
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < 16; i++) ev[i] = __float_as_uint(sPi[j0 + 16 * c + i]);
-                    }
-#pragma unroll
-                    for (int i4 = 0; i4 < 4; i4++) {
-                        const float lv[4] = {l[i4].x, l[i4].y, l[i4].z, l[i4].w};
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            float b;
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(fmaf(lv[i], 1.4426950408889634f, -ml2)));
-                            const float v = act ? __uint_as_float(ev[4 * i4 + i]) * b : 0.f;
-                            ev[4 * i4 + i] = __float_as_uint(v);
-                            lsum += v;
+                            for (int i = 0; i < 16; i++) ev[i] = __float_as_uint(sPi[j0 + 16 * c + i]);
                         }
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const float2 v2 = make_float2(__uint_as_float(ev[2 * i]) * bk[16 * c + 2 * i],
+                                                    __uint_as_float(ev[2 * i + 1]) * bk[16 * c + 2 * i + 1]);
+                            lsum += v2.x + v2.y;
+                            hi[i] = pack_h2(v2);
+                            lo[i] = pack_h2(sub2(v2, unpack_h2(hi[i])));
+                        }
+                        tmem_st8(tmem_ahi + lane_sel + (uint32_t)(j0 + 16 * c) / 2u, hi);
+                        tmem_st8(tmem_alo + lane_sel + (uint32_t)(j0 + 16 * c) / 2u, lo);
                     }
-                    tmem_st16(tmem_acc + lane_sel + (uint32_t)(j0 + 16 * c), ev);
-                }
+                    return lsum;
+                };
                 float *srow = sSum + ((fa & 1u) * TC_ROWS + r) * TC_GROUPS;
-                srow[g] = lsum;
-                tmem_st_wait();
+                srow[g] = emit();
                 asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");     // the four warps that share these 32 rows
                 const float4 ps = *reinterpret_cast<const float4 *>(srow);
-                const float V = (ps.x + ps.y) + (ps.z + ps.w);
-                // log P(o_t | o_<t) = m_t + ln V - ln(scale of the stored vector x scale of the weight image)
-                if (act) logp += (double)m + (double)logf(V) - (t >= 1 ? (double)ERG_LN_SCALE : 0.0);
-                const float inv = (act && V > 0.f) ? ERG_ALPHA_SCALE / V : 0.f;
-                // pass 2: alpha^_t = C v / V, fp16 hi/lo, into the A operand columns of these states
-                for (int c = 0; c < nch; c++) {
-                    uint32_t ev[16];
-                    tmem_ld16(tmem_acc + lane_sel + (uint32_t)(j0 + 16 * c), ev);
-                    tmem_ld_wait();
-                    uint32_t hi[8], lo[8];
+                float V = (ps.x + ps.y) + (ps.z + ps.w);
+                float lscale = (t >= 1 ? (float)ERG_W_SCALE : 1.f) * kappa;    // a_t = Z_{t-1} e^{m} / lscale * (stored vector)
+                // The products carry the normaliser of the PREVIOUS frame and the global row maximum.  When a frame's mass
+                // collapses below what the fp16 pair resolves (or underflows: the reachable states sit > 87 nats under the best
+                // one), the quadrant redoes the frame in the log domain with its exact maximum and normaliser; the accumulator
+                // is still intact.  Same rows and same V in the four warps of the quadrant, hence the same decision.
+                const bool low = act && alive && V < ERG_ALPHA_SCALE * ERG_RESCUE;
+                if (__any_sync(0xffffffffu, low)) {
+                    const float4 *lfr = lft + (size_t)t * (S / 4) * TC_ROWS;
+                    float wmax = -INFINITY;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const float2 v2 = make_float2(__uint_as_float(ev[2 * i]) * inv, __uint_as_float(ev[2 * i + 1]) * inv);
-                        hi[i] = pack_h2(v2);
-                        lo[i] = pack_h2(sub2(v2, unpack_h2(hi[i])));
+                    for (int c = 0; c < NCH; c++) {
+                        uint32_t ev[16];
+                        if (t >= 1) {
+                            tmem_ld16(tmem_acc + lane_sel + (uint32_t)(j0 + 16 * c), ev);
+                            tmem_ld_wait();
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) ev[i] = __float_as_uint(sPi[j0 + 16 * c + i]);
+                        }
+#pragma unroll
+                        for (int i4 = 0; i4 < 4; i4++) {
+                            const float4 l = act ? __ldg(lfr + (size_t)(4 * c + i4) * TC_ROWS) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float lv[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                const float w = (act && alive) ? lv[i] + logf(fmaxf(__uint_as_float(ev[4 * i4 + i]), 0.f)) : -INFINITY;
+                                bk[16 * c + 4 * i4 + i] = w;
+                                wmax = fmaxf(wmax, w);
+                            }
+                        }
                     }
-                    tmem_st8(tmem_ahi + lane_sel + (uint32_t)(j0 + 16 * c) / 2u, hi);
-                    tmem_st8(tmem_alo + lane_sel + (uint32_t)(j0 + 16 * c) / 2u, lo);
+                    float *xrow = sSum + (2 * TC_ROWS + r) * TC_GROUPS;      // exchange area of the rare path
+                    xrow[g] = wmax;
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+                    const float4 pm = *reinterpret_cast<const float4 *>(xrow);
+                    const float m2 = fmaxf(fmaxf(pm.x, pm.y), fmaxf(pm.z, pm.w));
+                    float lsum = 0.f;
+#pragma unroll
+                    for (int i = 0; i < spt; i++) {
+                        const float v = (m2 > -INFINITY) ? expf(bk[i] - m2) : 0.f;
+                        bk[i] = v;
+                        lsum += v;
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");   // everyone has read the maxima
+                    xrow[g] = lsum;
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+                    const float4 p2 = *reinterpret_cast<const float4 *>(xrow);
+                    const float V2 = (p2.x + p2.y) + (p2.z + p2.w);
+                    const float rho = V2 > 0.f ? ERG_ALPHA_SCALE / V2 : 0.f;
+#pragma unroll
+                    for (int c = 0; c < NCH; c++) {
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const float2 v2 = make_float2(bk[16 * c + 2 * i] * rho, bk[16 * c + 2 * i + 1] * rho);
+                            hi[i] = pack_h2(v2);
+                            lo[i] = pack_h2(sub2(v2, unpack_h2(hi[i])));
+                        }
+                        tmem_st8(tmem_ahi + lane_sel + (uint32_t)(j0 + 16 * c) / 2u, hi);
+                        tmem_st8(tmem_alo + lane_sel + (uint32_t)(j0 + 16 * c) / 2u, lo);
+                    }
+                    if (act && alive) {
+                        if (V2 > 0.f) {
+                            V = ERG_ALPHA_SCALE;
+                            m = m2;
+                            lscale = (t >= 1 ? (float)ERG_W_SCALE : 1.f) * rho;
+                        } else {
+                            alive = false;                  // no state is reachable: probability zero
+                        }
+                    }
+                }
+                if (act && alive) {
+                    logz += (double)m - (double)logf(lscale);
+                    Vlast = V;
+                    kappa = ERG_ALPHA_SCALE / ((float)ERG_W_SCALE * V);
                 }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(barA_full);
             }
-            // an utterance longer than the promised max_T has no valid score
-            if (g == 0 && u < p.B) p.logprob[u] = (Tfull > p.maxT) ? __longlong_as_double(0x7ff8000000000000LL) : logp;
+            // log P = ln Z_{T-1} + ln sum_j (stored vector); an utterance longer than the promised max_T has no valid score
+            if (g == 0 && u < p.B)
+                p.logprob[u] = (Tfull > p.maxT) ? __longlong_as_double(0x7ff8000000000000LL) : (T <= 0 ? 0.0 : alive ? logz + (double)logf(Vlast) : (double)-INFINITY);
         }
     }
     tc_fence_before();
@@ -455,9 +534,10 @@ extern "C" int sapr_ergodic_score(sapr_ctx *ctx, sapr_models *m, int mi, const f
     prm.X = X; prm.ldx = ldx; prm.offsets = offsets; prm.B = B; prm.S = S; prm.D = D; prm.nck = nck; prm.maxT = max_T;
     prm.wimg = wimg; prm.eimg = eimg; prm.pif = pif; prm.sb = sb; prm.lf = lf; prm.rmax = rmax; prm.logprob = logprob;
     const size_t smem_e = e_b + (size_t)8 * nck * 4 + 64;
-    const size_t smem_f = w_b + (size_t)2 * TC_ROWS * TC_GROUPS * 4 + (size_t)S * 4 + 64;
+    const size_t smem_f = w_b + (size_t)3 * TC_ROWS * TC_GROUPS * 4 + (size_t)S * 4 + 64;
     SAPR_CUDA(ctx, cudaFuncSetAttribute(k_erg_emission_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
-    SAPR_CUDA(ctx, cudaFuncSetAttribute(k_erg_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+    void (*fwd)(const ErgParams) = S == 64 ? k_erg_forward_tc<1> : S == 128 ? k_erg_forward_tc<2> : S == 192 ? k_erg_forward_tc<3> : k_erg_forward_tc<4>;
+    SAPR_CUDA(ctx, cudaFuncSetAttribute(fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
     const int nblk = (max_T + ERG_FB - 1) / ERG_FB;
     for (int t0 = 0; t0 < ntiles; t0 += chunk) {
         prm.tile0 = t0; prm.ntiles = std::min(chunk, ntiles - t0);
@@ -468,7 +548,7 @@ extern "C" int sapr_ergodic_score(sapr_ctx *ctx, sapr_models *m, int mi, const f
         SAPR_LAUNCH_CHECK(ctx);
         {
             ProfScope ps(ctx, 5);
-            k_erg_forward_tc<<<std::min(prm.ntiles, ctx->sm_count), ERG_THREADS, smem_f, ctx->stream>>>(prm);
+            fwd<<<std::min(prm.ntiles, ctx->sm_count), ERG_THREADS, smem_f, ctx->stream>>>(prm);
         }
         SAPR_LAUNCH_CHECK(ctx);
     }

@@ -30,6 +30,15 @@ ev[0].record()
 for _ in range(n): run()
 ev[1].record(); torch.cuda.synchronize()
 ms = ev[0].elapsed_time(ev[1]) / n
+m.ctx.profile(True)
+run()
+e_ms, e_n = m.ctx.profile_read(4)
+f_ms, f_n = m.ctx.profile_read(5)
+m.ctx.profile(False)
+lf_gb = B * T * S * 4 / 1e9
+print(f"  emission kernel {e_ms:.3f} ms ({e_n} launches, {lf_gb / e_ms * 1e3:.0f} GB/s written)   "
+      f"forward kernel {f_ms:.3f} ms ({f_n} launches, {lf_gb / f_ms * 1e3:.0f} GB/s read, "
+      f"{4 * B * T * S * S / f_ms * 1e3 / 1e12:.0f} TFLOP/s)")
 upd = B * T * S * S
 print(f"ergodic tc: B={B} T={T} S={S}: {ms:.3f} ms/call  {upd / ms * 1e3:.3e} state-pair updates/s  "
       f"{4 * upd / ms * 1e3 / 1e12:.1f} fp16 TFLOP/s (hi+lo)")
