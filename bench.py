@@ -14,6 +14,8 @@ One "step" = one pass of the fused Viterbi path (sapr_viterbi through the C ABI)
             timed region; algorithmic bytes = 31 412 B per utterance x utterances per launch
   cpu_baseline: the CPU oracle port (oracle/sapr_oracle.c, OpenMP) on a bounded sample of the same tensors
   estep   : secondary headline (configs[2] shape): Baum-Welch E-step + statistics (+ all-reduce + M-step)
+  ergodic : configs[3] shape: N=256 fully connected states, D=39, T=1000, forward score with the emission and the
+            transition contraction on the tensor cores (sapr_ergodic_score)
 
 `--impl reference` times the reference's algorithm on the host cores instead (oracle port, all threads).
 """
@@ -154,6 +156,8 @@ def main():
     ap.add_argument("--impl", default="sapr_b200")
     ap.add_argument("--utts", type=int, default=100_000, help="utterances per GPU")
     ap.add_argument("--estep-utts", type=int, default=200_000, help="utterances per GPU for the E-step leg (0 = skip)")
+    ap.add_argument("--ergodic-utts", type=int, default=148 * 128,
+                    help="utterances per GPU for the cfg 4 leg (N=256 dense states, T=1000; 0 = skip)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -323,6 +327,70 @@ def main():
         models.mstep(stats, floor_v)
         torch.cuda.synchronize()
 
+    # ---- third leg (BASELINE configs[3]): large ergodic HMM, both contractions on the tensor cores ----
+    ergodic = None
+    if args.ergodic_utts > 0 and prec == engine.FP32:
+        try:
+            del Xe, be
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        Sg, Tg, Bg = 256, 1000, args.ergodic_utts
+        rngg = np.random.default_rng(SEED + 4)
+        g_means = 2.0 * rngg.standard_normal((Sg, DIM)); g_var = rngg.uniform(0.5, 1.5, (Sg, DIM)) ** 2
+        g_tm = rngg.dirichlet(np.ones(Sg), size=Sg); g_sp = rngg.dirichlet(np.ones(Sg))
+        gm = engine.WordModels(1, Sg, DIM, _lib.EMIT_DIAG, _lib.TOPO_DENSE, ctx=ctx)
+        gm.set(g_means, g_var, g_tm, g_sp)
+        gen = torch.Generator(device=dev); gen.manual_seed(SEED + 97 * rank)
+        mt = torch.tensor(g_means, dtype=torch.float32, device=dev)
+        sd = torch.tensor(np.sqrt(g_var), dtype=torch.float32, device=dev)
+        Xg = torch.empty(Bg * Tg, DIM, dtype=torch.float32, device=dev)
+        for a in range(0, Bg * Tg, 1 << 22):           # synthetic frames: a random emitting state per frame
+            n = min(1 << 22, Bg * Tg - a)
+            stt = torch.randint(0, Sg, (n,), device=dev, generator=gen)
+            Xg[a:a + n] = mt[stt] + sd[stt] * torch.randn(n, DIM, device=dev, generator=gen)
+        offg = torch.arange(0, Bg + 1, device=dev, dtype=torch.int64) * Tg
+        lpg = torch.zeros(Bg, dtype=torch.float64, device=dev)
+
+        def erg_iter():
+            ctx.check(ctx.lib.sapr_ergodic_score(ctx.h, gm.h, 0, _lib.ptr(Xg), DIM, _lib.ptr(offg), Bg, Tg, _lib.ptr(lpg)))
+
+        for _ in range(3):
+            erg_iter()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ctx.profile(True)
+        n_it = 5
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(n_it):
+            erg_iter()
+        a1.record()
+        torch.cuda.synchronize()
+        ee_ms, _ = ctx.profile_read(4)
+        ef_ms, _ = ctx.profile_read(5)
+        ctx.profile(False)
+        gms = torch.tensor([a0.elapsed_time(a1) / n_it], dtype=torch.float64, device=dev)
+        dist.max_(gms)
+        g_ms = float(gms.item())
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        tpeak = float(pk.get("bf16_tflops", 2250.0))
+        lf_bytes = 2.0 * Bg * Tg * Sg * 4            # emissions written once and read once
+        fwd_tf = 4.0 * Bg * Tg * Sg * Sg / (ef_ms / n_it / 1e3) / 1e12
+        ergodic = {"metric": "forward (score) state-pair updates/s, N=256 fully connected states",
+                   "workload": f"cfg4: {Bg} utterances/GPU x T={Tg}, N={Sg}, D={DIM}, one dense model", "unit": "updates/s",
+                   "value": world * Bg * Tg * Sg * Sg / (g_ms / 1e3), "ms_per_call": g_ms,
+                   "mean_logprob_per_frame": float(lpg.mean().item()) / Tg,
+                   "kernels": {"k_erg_emission_tc_ms": ee_ms / n_it, "k_erg_forward_tc_ms": ef_ms / n_it},
+                   "roofline": {"bound": "hbm", "achieved": lf_bytes / ((ee_ms + ef_ms) / n_it / 1e3) / 1e9, "peak": peak,
+                                "unit": "GB/s", "frac": lf_bytes / ((ee_ms + ef_ms) / n_it / 1e3) / 1e9 / peak,
+                                "note": "the two contractions are two kernels (TMEM cannot hold both 256-column accumulators "
+                                        "plus their A operands), coupled through fp32 emissions in HBM: 2 x N x 4 bytes per frame",
+                                "forward_tensor_tflops_fp16_hi_lo": fwd_tf, "tensor_peak_tflops": tpeak,
+                                "forward_tensor_frac": fwd_tf / tpeak}}
+        del Xg, lpg
+        torch.cuda.empty_cache()
+
     # ---- CPU baseline (rank 0, N = 1 only): oracle port on a bounded sample of the same tensors ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -349,7 +417,7 @@ def main():
                            "emission": "diagonal Gaussian", "sharding": f"utterances x{world}, no collective",
                            "l2": "inputs (3.2 GB/GPU) larger than L2; no flush needed"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "estep": estep}
+                "clocks": clocks, "estep": estep, "ergodic": ergodic}
         print(json.dumps(line), flush=True)
     dist.shutdown()
 
