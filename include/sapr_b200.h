@@ -164,7 +164,8 @@ int sapr_decode_compat(sapr_ctx *ctx, sapr_models *m, int mi, const float *X, in
 /* ---- hmmlearn-style (DENSE topology, all states emit): GaussianHMM.score / decode / fit E-step
  * as used by hmmlearn_hmm.py:103-104 and decoder.py:43.  float64.                                 */
 /* lf = log frame probabilities [sum_T][S] workspace-free API: returns per-utterance log-prob.
- * score / decode accept up to 1024 states (BASELINE cfg 4: N = 256 ergodic); hl_estep up to 32 (SAPR_E_RANGE beyond). */
+ * All three accept up to 1024 states (BASELINE cfg 4: N = 256 ergodic; SAPR_E_RANGE beyond): thread per utterance up to
+ * 32 states, CTA per utterance above. */
 int sapr_hl_score(sapr_ctx *ctx, sapr_models *m, int mi, const float *X, int ldx, const int64_t *offsets, int B,
                   int64_t total_frames, double *logprob);
 int sapr_hl_decode(sapr_ctx *ctx, sapr_models *m, int mi, const float *X, int ldx, const int64_t *offsets, int B,

@@ -5,8 +5,9 @@
 // viterbi with max-shifted logsumexp).  float64; one thread per utterance, state vectors in local
 // arrays (S <= 32) -- small-N ergodic models are latency bound by nature.  For 32 < S <= 1024 (BASELINE cfg 4: the
 // N = 256 ergodic model) score and decode run one CTA per utterance, one thread per state (k_hl_*_cta): same
-// arithmetic and summation order, so the two mappings agree bit for bit; the tensor-core forward-backward for
-// training such models is not built.
+// arithmetic and summation order, so the two mappings agree bit for bit.  The E-step for such models (k_hl_backward_stats_cta)
+// is the float64 verification mode too: CTA per utterance, thread per state; the posterior normaliser is a block tree sum.
+// The fp32 tensor-core forward of ergodic_tc.cu is the fast score path; a tensor-core backward / xi accumulation is not built.
 #include "common.cuh"
 
 #define HL_MAX_S 32
@@ -165,13 +166,16 @@ __global__ void k_hl_viterbi(const double *__restrict__ lf, const int64_t *__res
 #define HL_MAX_S_CTA 1024
 __global__ void k_hl_forward_cta(const double *__restrict__ lf, const int64_t *__restrict__ offsets, int S,
                                  const double *__restrict__ logpi, const double *__restrict__ logA,
-                                 double *__restrict__ logprob) {
+                                 double *__restrict__ fwd_out, double *__restrict__ logprob) {
     extern __shared__ double sh_prev[];   // [S]
     const int u = blockIdx.x, j = threadIdx.x;
     const int64_t off = offsets[u];
     const int T = (int)(offsets[u + 1] - off);
     if (T <= 0) { if (j == 0) logprob[u] = 0.0; return; }
-    if (j < S) sh_prev[j] = logpi[j] + lf[(size_t)off * S + j];
+    if (j < S) {
+        sh_prev[j] = logpi[j] + lf[(size_t)off * S + j];
+        if (fwd_out) fwd_out[(size_t)off * S + j] = sh_prev[j];
+    }
     __syncthreads();
     for (int t = 1; t < T; t++) {
         double cur = 0.0;
@@ -187,10 +191,100 @@ __global__ void k_hl_forward_cta(const double *__restrict__ lf, const int64_t *_
             cur = r + lf[(size_t)(off + t) * S + j];
         }
         __syncthreads();
-        if (j < S) sh_prev[j] = cur;
+        if (j < S) {
+            sh_prev[j] = cur;
+            if (fwd_out) fwd_out[(size_t)(off + t) * S + j] = cur;
+        }
         __syncthreads();
     }
     if (j == 0) logprob[u] = hl_lse(sh_prev, S);
+}
+
+// block-wide max / sum over the first S threads' values (fixed tree order: deterministic)
+__device__ __forceinline__ double hl_block_reduce(double v, bool is_max, double *sh_red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) {
+        const double x = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmax(v, x) : v + x;
+    }
+    __syncthreads();
+    if (lane == 0) sh_red[w] = v;
+    __syncthreads();
+    double r = sh_red[0];
+    for (int i = 1; i < nw; i++) r = is_max ? fmax(r, sh_red[i]) : r + sh_red[i];
+    return r;
+}
+
+// backward + posteriors + statistics, one CTA per utterance at a time (CTA b takes utterances b, b + grid, ...),
+// one thread per state; the CTA's partial statistics [start S | trans S*S | post S] accumulate in pc[b] (zeroed here).
+__global__ void k_hl_backward_stats_cta(const double *__restrict__ lf, const double *__restrict__ fwd,
+                                        const int64_t *__restrict__ offsets, int B, int S,
+                                        const double *__restrict__ logA, const double *__restrict__ logprob,
+                                        double *__restrict__ bwd_ws, double *__restrict__ post_out, double *__restrict__ pc) {
+    extern __shared__ double sh[];        // [S] next-frame term c_j = lf[t+1][j] + bwd[t+1][j]  |  [32] reduction scratch
+    double *sh_c = sh, *sh_red = sh + S;
+    const int j = threadIdx.x;
+    const int len = S + S * S + S;
+    double *p = pc + (size_t)blockIdx.x * len;
+    for (int k = j; k < len; k += blockDim.x) p[k] = 0.0;
+    __syncthreads();
+    for (int u = blockIdx.x; u < B; u += gridDim.x) {
+        const int64_t off = offsets[u];
+        const int T = (int)(offsets[u + 1] - off);
+        if (T <= 0) continue;
+        double *bw = bwd_ws + (size_t)off * S;
+        if (j < S) bw[(size_t)(T - 1) * S + j] = 0.0;
+        for (int t = T - 2; t >= 0; t--) {
+            __syncthreads();
+            if (j < S) sh_c[j] = lf[(size_t)(off + t + 1) * S + j] + bw[(size_t)(t + 1) * S + j];
+            __syncthreads();
+            if (j < S) {                                   // thread = source state i
+                const double *la = logA + (size_t)j * S;
+                double m = -INFINITY;
+                for (int k = 0; k < S; k++) { const double v = la[k] + sh_c[k]; if (v > m) m = v; }
+                double r = -INFINITY;
+                if (m > -INFINITY) {
+                    double sm = 0.0;
+                    for (int k = 0; k < S; k++) sm += exp(la[k] + sh_c[k] - m);
+                    r = log(sm) + m;
+                }
+                bw[(size_t)t * S + j] = r;
+            }
+        }
+        __syncthreads();
+        // posteriors = exp(log_normalize(fwd + bwd))
+        double g0 = 0.0, gsum = 0.0;
+        for (int t = 0; t < T; t++) {
+            const double w = (j < S) ? fwd[(size_t)(off + t) * S + j] + bw[(size_t)t * S + j] : -INFINITY;
+            const double mx = hl_block_reduce(w, true, sh_red);
+            const double e = (j < S && mx > -INFINITY) ? exp(w - mx) : 0.0;
+            const double sm = hl_block_reduce(e, false, sh_red);
+            const double g = (j < S && mx > -INFINITY) ? exp(w - (log(sm) + mx)) : 0.0;
+            if (j < S) post_out[(size_t)(off + t) * S + j] = g;
+            if (t == 0) g0 = g;
+            gsum += g;
+        }
+        if (j < S) { p[j] += g0; p[S + S * S + j] += gsum; }
+        // trans[i][j] += exp(logsumexp_t(fwd[t,i] + logA[i,j] + lf[t+1,j] + bwd[t+1,j] - logprob)); thread = destination j
+        if (T > 1 && j < S) {
+            const double lp = logprob[u];
+            for (int i = 0; i < S; i++) {
+                const double la_ = logA[(size_t)i * S + j];
+                if (!(la_ > -INFINITY)) continue;
+                double mx = -INFINITY;
+                for (int t = 0; t < T - 1; t++) {
+                    const double v = fwd[(size_t)(off + t) * S + i] + la_ + lf[(size_t)(off + t + 1) * S + j] + bw[(size_t)(t + 1) * S + j] - lp;
+                    if (v > mx) mx = v;
+                }
+                if (!(mx > -INFINITY)) continue;
+                double sm = 0.0;
+                for (int t = 0; t < T - 1; t++)
+                    sm += exp(fwd[(size_t)(off + t) * S + i] + la_ + lf[(size_t)(off + t + 1) * S + j] + bw[(size_t)(t + 1) * S + j] - lp - mx);
+                p[S + (size_t)i * S + j] += exp(log(sm) + mx);
+            }
+        }
+        __syncthreads();
+    }
 }
 
 __global__ void k_hl_viterbi_cta(const double *__restrict__ lf, const int64_t *__restrict__ offsets, int S,
@@ -256,7 +350,7 @@ extern "C" int sapr_hl_score(sapr_ctx *ctx, sapr_models *m, int mi, const float 
                                                             m->logA + (size_t)mi * S * S, nullptr, logprob);
     else
         k_hl_forward_cta<<<B, (S + 31) / 32 * 32, sizeof(double) * S, ctx->stream>>>(lf, offsets, S, m->logpi + (size_t)mi * S,
-                                                                                     m->logA + (size_t)mi * S * S, logprob);
+                                                                                     m->logA + (size_t)mi * S * S, nullptr, logprob);
     SAPR_LAUNCH_CHECK(ctx);
     return SAPR_OK;
 }
@@ -283,21 +377,30 @@ extern "C" int sapr_hl_estep(sapr_ctx *ctx, sapr_models *m, int mi, const float 
                              int B, int64_t total_frames, double *stats, double *logprob) {
     HL_CHECK("hl_estep");
     if (!stats || !logprob) return SAPR_E_INVALID;
-    if (m->S > HL_MAX_S)
-        SAPR_FAIL(ctx, SAPR_E_RANGE, "hl_estep: training with more than 32 states is not built (score / decode are)");
     const int S = m->S, D = m->D;
     const size_t lat = (size_t)total_frames * S;
     const int len = S + S * S + S;
-    int rc = sapr_ws_reserve(ctx, 4, sizeof(double) * (4 * lat + (size_t)B * len));
+    // partial statistics: one slot per utterance (S <= 32, thread per utterance) or per CTA (larger S, CTA per utterance)
+    const int nslots = S <= HL_MAX_S ? B : std::min(B, 2 * ctx->sm_count);
+    int rc = sapr_ws_reserve(ctx, 4, sizeof(double) * (4 * lat + (size_t)nslots * len));
     if (rc) return rc;
     double *lf = (double *)ctx->ws[4], *fwd = lf + lat, *bwd = fwd + lat, *post = bwd + lat, *pu = post + lat;
     if ((rc = sapr_emission_into(ctx, m, mi, X, ldx, offsets, B, total_frames, lf))) return rc;
     const double *logpi = m->logpi + (size_t)mi * S, *logA = m->logA + (size_t)mi * S * S;
-    k_hl_forward<<<(B + 31) / 32, 32, 0, ctx->stream>>>(lf, offsets, B, S, logpi, logA, fwd, logprob);
-    SAPR_LAUNCH_CHECK(ctx);
-    k_hl_backward_stats<<<(B + 31) / 32, 32, 0, ctx->stream>>>(lf, fwd, offsets, B, S, logA, logprob, bwd, post, pu);
-    SAPR_LAUNCH_CHECK(ctx);
-    k_hl_sum_pu<<<(len + 63) / 64, 64, 0, ctx->stream>>>(pu, B, len, stats);
+    if (S <= HL_MAX_S) {
+        k_hl_forward<<<(B + 31) / 32, 32, 0, ctx->stream>>>(lf, offsets, B, S, logpi, logA, fwd, logprob);
+        SAPR_LAUNCH_CHECK(ctx);
+        k_hl_backward_stats<<<(B + 31) / 32, 32, 0, ctx->stream>>>(lf, fwd, offsets, B, S, logA, logprob, bwd, post, pu);
+        SAPR_LAUNCH_CHECK(ctx);
+    } else {
+        const int threads = (S + 31) / 32 * 32;
+        k_hl_forward_cta<<<B, threads, sizeof(double) * S, ctx->stream>>>(lf, offsets, S, logpi, logA, fwd, logprob);
+        SAPR_LAUNCH_CHECK(ctx);
+        k_hl_backward_stats_cta<<<nslots, threads, sizeof(double) * (S + 32), ctx->stream>>>(lf, fwd, offsets, B, S, logA, logprob,
+                                                                                             bwd, post, pu);
+        SAPR_LAUNCH_CHECK(ctx);
+    }
+    k_hl_sum_pu<<<(len + 63) / 64, 64, 0, ctx->stream>>>(pu, nslots, len, stats);
     SAPR_LAUNCH_CHECK(ctx);
     k_hl_obs<<<(S * D + 63) / 64, 64, 0, ctx->stream>>>(X, ldx, total_frames, D, S, post, stats + len, stats + len + (size_t)S * D);
     SAPR_LAUNCH_CHECK(ctx);

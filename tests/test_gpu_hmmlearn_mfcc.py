@@ -57,7 +57,8 @@ def test_score_decode_vs_oracle(cuda, rung1_d13):
 
 def test_large_ergodic_score_decode_vs_oracle(cuda):
     """BASELINE cfg 4 shape at test size: N = 256 fully connected states (rows ~ Dirichlet(1)), D = 39 -- score and
-    Viterbi decode through the one-CTA-per-utterance kernels against the oracle restatement; fit must refuse loudly."""
+    Viterbi decode through the one-CTA-per-utterance kernels against the oracle restatement, then one Baum-Welch
+    iteration (CTA-per-utterance backward / posteriors / transition statistics) against the oracle's E-step + M-step."""
     from sapr_b200.hmmlearn_hmm import GaussianHMM
     rng = np.random.default_rng(4)
     S, D = 256, 39
@@ -79,8 +80,21 @@ def test_large_ergodic_score_decode_vs_oracle(cuda):
     lp, path = model.decode(X, lengths)
     assert abs(lp - tot_v) <= 1e-10 * abs(tot_v)
     assert np.array_equal(path, np.concatenate(paths))
-    with pytest.raises(Exception):
-        model.fit(X, lengths)
+    st = orc.hl_estep(X, offs.astype(np.int64), sp, tm, means, var)
+    sp2, tm2, means2, var2 = orc.hl_mstep(st, sp, tm)
+    model.tol = -np.inf
+    model.fit(X, lengths)
+    assert_close(np.array(model.monitor_.history), np.array([st["logprob"]]), 1e-10, what="history")
+    occupied = st["post"] > 1e-3                                   # states nobody visited keep prior-dominated values
+    assert_close(model.means_[occupied], means2[occupied], 1e-8, what="means")
+    assert_close(model._covars[occupied], var2[occupied], 1e-7, what="covars")
+    assert_close(model.transmat_, tm2, 1e-8, atol=1e-12, what="transmat")
+    assert_close(model.startprob_, sp2, 1e-10, atol=1e-15, what="startprob")
+    big = GaussianHMM(n_components=1025, covariance_type="diag", n_iter=1, init_params="")
+    big.means_, big.covars_ = np.zeros((1025, D)), np.ones((1025, D))
+    big.transmat_, big.startprob_ = np.full((1025, 1025), 1 / 1025), np.full(1025, 1 / 1025)
+    with pytest.raises(Exception):                                 # beyond 1024 states: refused loudly
+        big.score(X, lengths)
 
 
 @pytest.mark.parametrize("S,D,peaked", [(256, 39, False), (128, 13, False), (64, 39, False), (192, 39, True), (256, 39, True)])
