@@ -8,31 +8,44 @@
 //
 // Differences from the Viterbi kernel:
 //   * utterances are visited in model order (order[] grouped by word, every model's group padded to a multiple of
-//     32 rows), so the 32 rows of a TMEM lane quadrant share ONE model and a tile spans one or two adjacent
-//     models: the MMA is N = 16 (two models' states) instead of N = 96;
-//   * a persistent CTA sweeps its tile FORWARD (alpha-hat rows go to an L2-resident per-CTA scratch,
-//     [frame][state][row], 4 KB per frame) and then BACKWARD over the same tile (features are fetched a second time,
-//     emissions recomputed on the tensor core, beta / gamma / xi on the fly); only sum_t gamma, sum_t xi(j,j),
-//     gamma_t (for the feature statistics) and the log-likelihood leave the CTA;
-//   * warp roles: warps 0-3 run the recursions (one thread per utterance: the left-to-right chain of 8 states is
-//     register resident, log-sum-exp in the forward sweep, max-normalised linear sums in the backward sweep),
-//     warps 4-15 standardise / square / split the features into the A operand (three groups, each converting every
-//     third frame into its own A stage), warp 16 issues the MMAs, warps 17-19 issue the bulk copies.  (Giving the recursion warps the highest warp ids instead was measured: 7 % slower.)
+//     32 rows), so the 32 rows of a TMEM lane quadrant share ONE model and a tile spans one (rarely up to four)
+//     adjacent models.  Per model of the tile the MMA is N = 16: accumulator columns 0-7 take the products with the
+//     W_hi plane, columns 8-15 the products with the W_lo plane (the B descriptor's 8-row-group stride is the plane
+//     distance), so two passes (A_lo, then A_hi) of nck/2 K-steps replace the three of the Viterbi kernel and the
+//     large hi*hi sum sees only nck/2 truncating accumulations after the small lo*hi one;
+//   * the tensor-core pipeline (bulk copies -> converters -> MMA) runs the FORWARD sweep only.  The recursion thread
+//     of a row stores alpha-hat AND the emissions e'_t(j) = E[t,j] + ln A[j,j] of its frames to a per-(CTA, recursion
+//     group) scratch ([frame][16][row], 8 KB per frame); the BACKWARD sweep (beta / gamma / xi) is a thread-private
+//     loop over that scratch: no second feature read, no second conversion, no barriers.  Only sum_t gamma,
+//     sum_t xi(j,j), gamma_t (for the feature statistics) and the log-likelihood leave the CTA;
+//   * two recursion warpgroups alternate tiles: while group A sweeps tile k backward, the pipeline and group B are
+//     already in the forward sweep of tile k+1, so the converters / MMA warp never idle behind a backward sweep;
+//   * warp roles: warps 0-7 = the two recursion groups (one thread per utterance: the left-to-right chain of 8
+//     states is register resident, log-sum-exp in the forward sweep, max-normalised linear sums in the backward
+//     sweep), warps 8-15 standardise / square / split the features into the A operand (two groups, each converting
+//     every second frame into its own A stage), warp 16 issues the MMAs, warps 17-19 issue the bulk copies.  20 warps
+//     = 5 per scheduler keep 96 registers per thread: with 24 warps (three converter groups) the cap is 80, the
+//     backward sweep's one-frame-ahead scratch loads spill and stall on their own spill stores (measured), and
+//     setmaxnreg does not raise the allocator's cap.
 #include "tc_common.cuh"
 
-#define ET_REC_WARPS 4                            /* warps 0 .. 3 */
-#define ET_CONV_GROUPS 3
-#define ET_CONV_WARPS (4 * ET_CONV_GROUPS)         /* warps 4 .. 11 */
-#define ET_MMA_WARP (ET_REC_WARPS + ET_CONV_WARPS) /* 12 */
-#define ET_LOAD_WARP0 (ET_MMA_WARP + 1)           /* 13 .. 19 */
-#define ET_LOADERS (TC_THREADS / 32 - ET_LOAD_WARP0)
+#define ET_REC_WGS 2
+#define ET_REC_WARPS 4                                    /* per recursion group: warps 0-3, 4-7 */
+#define ET_CONV_GROUPS 2
+#define ET_CONV_WARP0 (4 * ET_REC_WGS)                     /* 8 */
+#define ET_CONV_WARPS (4 * ET_CONV_GROUPS)                 /* warps 8 .. 15 */
+#define ET_MMA_WARP (ET_CONV_WARP0 + ET_CONV_WARPS)        /* 16 */
+#define ET_LOAD_WARP0 (ET_MMA_WARP + 1)                    /* 17 .. 19 */
+#define ET_LOADERS 3
+#define ET_THREADS (32 * (ET_LOAD_WARP0 + ET_LOADERS))     /* 640 */
+#define ET_ACC_W 64                                        /* accumulator stage: up to 4 models x 16 columns */
 
 struct EtParams {
     const float *X; int ldx; const int64_t *offsets; int B;
     const int32_t *order; const int32_t *model_start;       // utterance ids grouped by model; [M+1] group starts
     int M, D, nck, ncols;
     const __half *wimg; const float *sb; const float4 *trp;
-    float *scratch; int maxT;                                // alpha-hat: [grid][maxT][8][128]
+    float *scratch; int maxT;                                // alpha-hat | e': [grid][2][maxT][16][128]
     float *gamma;                                            // [sum_T][8]
     float *ustats;                                           // [B][24] by position in order[]: G | Xi | occ
     double *loglik;                                          // [B] by utterance id
@@ -50,7 +63,7 @@ __host__ __device__ inline EtSmem et_smem_layout(int M, int nck, int ncols, int 
     L.sb = L.tr + (uint32_t)M * TC_TRQ * 16;
     L.pad = (L.sb + (uint32_t)8 * nck * 4 + 15u) & ~15u;        // int pad_start[16], cnt[16]
     L.bar = L.pad + 32 * 4;
-    L.total = L.bar + (2 * TC_MAX_STAGES + 10) * 8 + 16;
+    L.total = L.bar + (2 * TC_MAX_STAGES + 12) * 8 + 16;
     return L;
 }
 
@@ -76,7 +89,7 @@ __device__ __forceinline__ float fexp32(float x) {      // exp(x), x <= 0 or -in
 #define ET_TRACE_EVENTS 4
 #define ET_TRACE_ROLES 4
 template <bool TRACE, int NKS>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
+__global__ void __launch_bounds__(ET_THREADS, 1) k_estep_tc(const EtParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int nck = p.nck, ncols = p.ncols, M = p.M;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -90,19 +103,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
     const float4 *sS = reinterpret_cast<const float4 *>(smem + L.sb);
     int *sPad = reinterpret_cast<int *>(smem + L.pad);          // pad_start[0..M], then cnt[0..M-1] at +16
     uint64_t *sBar = reinterpret_cast<uint64_t *>(smem + L.bar);
-    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 2 * TC_MAX_STAGES + 10);
+    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 2 * TC_MAX_STAGES + 12);
     const uint32_t barRaw_full = smem_u32(sBar), barRaw_empty = barRaw_full + 8 * TC_MAX_STAGES;
-    const uint32_t barA_full = barRaw_empty + 8 * TC_MAX_STAGES, barA_free = barA_full + 24;   // [3], [3]
+    const uint32_t barA_full = barRaw_empty + 8 * TC_MAX_STAGES, barA_free = barA_full + 24;   // [<= 3], [<= 3]
     const uint32_t barAcc_full = barA_free + 24, barAcc_empty = barAcc_full + 16;               // [2], [2]
+    const uint32_t barTurn = barAcc_empty + 16;                                                 // [2]: forward-sweep hand-over between the recursion groups
 
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.wimg);
         uint4 *dst = reinterpret_cast<uint4 *>(sW);
-        for (uint32_t i = tid; i < 2 * w_plane / 16; i += TC_THREADS) dst[i] = src[i];
+        for (uint32_t i = tid; i < 2 * w_plane / 16; i += ET_THREADS) dst[i] = src[i];
         float4 *dtr = reinterpret_cast<float4 *>(smem + L.tr);
-        for (int i = tid; i < M * TC_TRQ; i += TC_THREADS) dtr[i] = p.trp[i];
+        for (int i = tid; i < M * TC_TRQ; i += ET_THREADS) dtr[i] = p.trp[i];
         float *dsb = reinterpret_cast<float *>(smem + L.sb);
-        for (int i = tid; i < 8 * nck; i += TC_THREADS) dsb[i] = p.sb[i];
+        for (int i = tid; i < 8 * nck; i += ET_THREADS) dsb[i] = p.sb[i];
     }
     if (tid == 0) {
         int acc = 0;
@@ -116,20 +130,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
             mbar_init(barRaw_full + 8 * s, 32 * ET_LOADERS);
             mbar_init(barRaw_empty + 8 * s, ET_CONV_WARPS);
         }
-        for (int s = 0; s < 3; s++) { mbar_init(barA_full + 8 * s, 4); mbar_init(barA_free + 8 * s, 1); }   // one converter group per A stage
-        for (int s = 0; s < 2; s++) { mbar_init(barAcc_full + 8 * s, 1); mbar_init(barAcc_empty + 8 * s, ET_REC_WARPS); }
+        for (int s = 0; s < ET_CONV_GROUPS; s++) { mbar_init(barA_full + 8 * s, 4); mbar_init(barA_free + 8 * s, 1); }   // one converter group per A stage
+        for (int s = 0; s < 2; s++) { mbar_init(barAcc_full + 8 * s, 1); mbar_init(barAcc_empty + 8 * s, ET_REC_WARPS); mbar_init(barTurn + 8 * s, ET_REC_WARPS); }
         fence_barrier_init();
     }
     const uint32_t a_cols = 8u * nck;
     uint32_t tcols = 32;
-    while (tcols < 2u * ncols + 3u * a_cols) tcols <<= 1;
+    while (tcols < 2u * ET_ACC_W + (uint32_t)ET_CONV_GROUPS * a_cols) tcols <<= 1;
     if (warp == ET_MMA_WARP) tmem_alloc(smem_u32(sTmem), tcols);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *sTmem;
-    const uint32_t tmem_acc = tmem_base, tmem_a = tmem_base + 2u * ncols;   // 2 accumulator stages (N <= ncols), then 3 A stages
+    const uint32_t tmem_acc = tmem_base, tmem_a = tmem_base + 2u * ET_ACC_W;   // 2 accumulator stages, then the A stages
 
     const int total_pad = sPad[M];
     const int ntiles = (total_pad + TC_ROWS - 1) / TC_ROWS;
@@ -155,16 +169,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
         for (int o = 16; o > 0; o >>= 1) Tt = max(Tt, __shfl_xor_sync(0xffffffffu, Tt, o));
         return Tt;
     };
-    // models a tile spans -> first model whose states the MMA covers, and N (16 .. ncols)
-    auto tile_models = [&](int tile, int &mbase) -> int {
-        int mf = 0, ml = 0;
+    // first model of a tile and how many adjacent models it spans (1 .. 4: every group is padded to 32 rows)
+    auto tile_models = [&](int tile, int &mf) -> int {
+        int ml;
         const int r0 = tile * TC_ROWS, r1 = min(r0 + TC_ROWS, total_pad) - 1;
+        mf = 0;
         while (mf + 1 < M && r0 >= sPad[mf + 1]) mf++;
         ml = mf;
         while (ml + 1 < M && r1 >= sPad[ml + 1]) ml++;
-        const int n = ((ml - mf + 1) * 8 + 15) / 16 * 16;
-        mbase = min(mf, (ncols - n) / 8);
-        return n;
+        return ml - mf + 1;
     };
 
     uint32_t f = 0, sg = 0;
@@ -174,57 +187,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
     };
 
     if (warp >= ET_LOAD_WARP0) {
-        // ===================== bulk-copy producers: forward sweep, then backward sweep of every tile =====================
+        // ===================== bulk-copy producers: the forward sweep of every tile =====================
         constexpr int RPL = (TC_ROWS + ET_LOADERS - 1) / ET_LOADERS;
+        constexpr int RPT = (RPL + 31) / 32;
         const int lw = warp - ET_LOAD_WARP0;
         const int rlo = lw * RPL, rhi = min(rlo + RPL, TC_ROWS);
-        const int rr[2] = {rlo + lane, rlo + lane + 32};
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int Tt = tile_frames(tile);
             const int nsg = (Tt + F - 1) >> p.Fshift;
-            int Te[2]; int64_t off[2];
+            int Te[RPT]; int64_t off[RPT];
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
+            for (int i = 0; i < RPT; i++) {
+                const int rr = rlo + lane + 32 * i;
                 int m, pos;
-                Te[i] = (rr[i] < rhi) ? row_info(tile * TC_ROWS + rr[i], m, pos, off[i]) : 0;
-                if (rr[i] >= rhi) off[i] = 0;
+                Te[i] = (rr < rhi) ? row_info(tile * TC_ROWS + rr, m, pos, off[i]) : 0;
+                if (rr >= rhi) off[i] = 0;
             }
-            for (int phase = 0; phase < 2; phase++)
-                for (int k = 0; k < nsg; k++, sg++) {
-                    const uint32_t slot = sg & (uint32_t)(nst - 1), ph = (sg >> p.nst_shift) & 1u;
-                    const uint32_t bar = barRaw_full + 8 * slot;
-                    int lo[2], nf[2];
+            for (int k = 0; k < nsg; k++, sg++) {
+                const uint32_t slot = sg & (uint32_t)(nst - 1), ph = (sg >> p.nst_shift) & 1u;
+                const uint32_t bar = barRaw_full + 8 * slot;
+                int nf[RPT], tot = 0;
 #pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        if (phase == 0) { lo[i] = k * F; nf[i] = min(max(Te[i] - k * F, 0), F); }
-                        else { const int hi = Te[i] - k * F; lo[i] = max(hi - F, 0); nf[i] = max(hi, 0) - lo[i]; }
-                    }
-                    if (lw == 0) trace(3, sg * 4 + 40, 0);
-                    mbar_wait(barRaw_empty + 8 * slot, ph ^ 1u);
-                    if (lw == 0) trace(3, sg * 4 + 40, 1);
-                    mbar_arrive_tx(bar, (uint32_t)(nf[0] + nf[1]) * rowbytes);
+                for (int i = 0; i < RPT; i++) { nf[i] = min(max(Te[i] - k * F, 0), F); tot += nf[i]; }
+                if (lw == 0) trace(3, sg * 4 + 40, 0);
+                mbar_wait(barRaw_empty + 8 * slot, ph ^ 1u);
+                if (lw == 0) trace(3, sg * 4 + 40, 1);
+                mbar_arrive_tx(bar, (uint32_t)tot * rowbytes);
 #pragma unroll
-                    for (int i = 0; i < 2; i++)
-                        if (nf[i] > 0)
-                            bulk_g2s(smem_u32(sRaw) + slot * stage_bytes + (uint32_t)rr[i] * rstride,
-                                     p.X + (size_t)(off[i] + lo[i]) * p.ldx, (uint32_t)nf[i] * rowbytes, bar);
-                    if (lw == 0) trace(3, sg * 4 + 40, 2);
-                }
+                for (int i = 0; i < RPT; i++)
+                    if (nf[i] > 0)
+                        bulk_g2s(smem_u32(sRaw) + slot * stage_bytes + (uint32_t)(rlo + lane + 32 * i) * rstride,
+                                 p.X + (size_t)(off[i] + k * F) * p.ldx, (uint32_t)nf[i] * rowbytes, bar);
+                if (lw == 0) trace(3, sg * 4 + 40, 2);
+            }
         }
     } else if (warp == ET_MMA_WARP) {
         // ===================== MMA issuer =====================
-        const uint32_t sW_hi = smem_u32(sW), sW_lo = sW_hi + w_plane;
+        const uint32_t sW_hi = smem_u32(sW);
         const uint32_t sboW = (uint32_t)nck * 128u;
         const int nks = nck / 2;
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);   // M = 128, N = 16
         uint32_t a3 = 0, aph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int Tt = tile_frames(tile);
-            int mbase;
-            const int n = tile_models(tile, mbase);
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
-            const uint64_t dW_hi = make_desc(sW_hi + (uint32_t)mbase * sboW, 128, sboW);
-            const uint64_t dW_lo = make_desc(sW_lo + (uint32_t)mbase * sboW, 128, sboW);
-            for (int t = 0; t < 2 * Tt; t++, f++) {
+            int mf;
+            const int nm = tile_models(tile, mf);
+            // B = [W_hi rows of model m | W_lo rows of model m]: the second 8-row group lies one plane further
+            const uint64_t dW0 = make_desc(sW_hi + (uint32_t)mf * sboW, 128, w_plane);
+            for (int t = 0; t < Tt; t++, f++) {
                 const uint32_t s = f & 1, ph = (f >> 1) & 1;
                 trace(0, f, 0);
                 mbar_wait(barA_full + 8 * a3, aph);
@@ -233,46 +243,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
                 trace(0, f, 2);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t d_tmem = tmem_acc + s * (uint32_t)ncols;
                     const uint32_t a_hi = tmem_a + a3 * a_cols, a_lo = a_hi + 8u;
-                    if (NKS > 0) {
+                    uint32_t d_tmem = tmem_acc + s * (uint32_t)ET_ACC_W;
+                    uint64_t dW = dW0;
+                    for (int mi = 0; mi < nm; mi++, d_tmem += 16u, dW += (uint64_t)(sboW >> 4)) {
+                        if (NKS > 0) {
 #pragma unroll
-                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_lo + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, ks > 0);   // lo * W_hi
+                            for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_lo + ks * 16, dW + (uint64_t)(16 * ks), idesc, ks > 0);   // lo * [W_hi | W_lo]
 #pragma unroll
-                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_lo + (uint64_t)(16 * ks), idesc, 1);        // hi * W_lo
-#pragma unroll
-                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, 1);        // hi * W_hi
-                    } else {
-                        uint64_t dh = dW_hi, dl = dW_lo;
-                        uint32_t a = a_lo;
-                        for (int ks = 0; ks < nks; ks++, a += 16, dh += 16) umma_f16_ts(d_tmem, a, dh, idesc, ks > 0);   // lo * W_hi
-                        a = a_hi;
-                        for (int ks = 0; ks < nks; ks++, a += 16, dl += 16) umma_f16_ts(d_tmem, a, dl, idesc, 1);        // hi * W_lo
-                        a = a_hi; dh = dW_hi;
-                        for (int ks = 0; ks < nks; ks++, a += 16, dh += 16) umma_f16_ts(d_tmem, a, dh, idesc, 1);        // hi * W_hi
+                            for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW + (uint64_t)(16 * ks), idesc, 1);        // hi * [W_hi | W_lo]
+                        } else {
+                            uint64_t dd = dW;
+                            uint32_t a = a_lo;
+                            for (int ks = 0; ks < nks; ks++, a += 16, dd += 16) umma_f16_ts(d_tmem, a, dd, idesc, ks > 0);
+                            a = a_hi; dd = dW;
+                            for (int ks = 0; ks < nks; ks++, a += 16, dd += 16) umma_f16_ts(d_tmem, a, dd, idesc, 1);
+                        }
                     }
                     umma_commit(barAcc_full + 8 * s);
                     umma_commit(barA_free + 8 * a3);
                 }
                 __syncwarp();
                 trace(0, f, 3);
-                if (++a3 == 3) { a3 = 0; aph ^= 1u; }
+                if (++a3 == ET_CONV_GROUPS) { a3 = 0; aph ^= 1u; }
             }
         }
     } else {
-        const int q = warp & 3, g = warp >> 2, r = q * 32 + lane;      // group 0 = recursion warps
+        const int q = warp & 3, r = q * 32 + lane;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         auto lds4 = [](uint32_t a) -> float4 {
             float4 v;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
             return v;
         };
-        if (g > 0) {
+        if (warp >= ET_CONV_WARP0) {
             // ===================== converters: features -> A operand in TMEM =====================
-            // Frame-parallel: converter group gi owns A stage gi and converts every third frame (all feature chunks of
-            // its row).  One conversion is a ~1000-cycle dependent chain (LDS -> FFMA2 -> F2FP -> ... -> tcgen05.st ->
-            // wait), so three frames in flight -- not more threads per frame -- is what raises the frame rate.
-            const uint32_t gi = (uint32_t)(g - 1);
+            // Frame-parallel: converter group gi owns A stage gi and converts every ET_CONV_GROUPS-th frame (all feature
+            // chunks of its row).  One conversion is a ~1000-cycle dependent chain (LDS -> FFMA2 -> F2FP -> ... ->
+            // tcgen05.st -> wait), so frames in flight -- not more threads per frame -- is what raises the frame rate.
+            const uint32_t gi = (uint32_t)((warp - ET_CONV_WARP0) >> 2);
             const int npairs = nck / 2;
             const uint32_t ta = tmem_a + lane_sel + gi * a_cols;
             const uint32_t raw0 = smem_u32(sRaw) + (uint32_t)r * rstride;
@@ -287,89 +296,89 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
                 lo[0] = pack_h2(sub2(a01, unpack_h2(hi[0]))); lo[1] = pack_h2(sub2(a23, unpack_h2(hi[1])));
                 lo[2] = pack_h2(sub2(q01, unpack_h2(hi[2]))); lo[3] = pack_h2(sub2(q23, unpack_h2(hi[3])));
             };
-            uint32_t fm3 = 0;                              // f % 3, kept incrementally
+            uint32_t fm3 = 0;                              // f % ET_CONV_GROUPS, kept incrementally
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int Tt = tile_frames(tile);
                 int m, pos; int64_t off;
                 const int Te = row_info(tile * TC_ROWS + r, m, pos, off);
-                for (int phase = 0; phase < 2; phase++) {
-                    bool waited = false;                   // raw_full of the current stage already observed by this warp
-                    for (int tau = 0; tau < Tt; tau++, f++) {
-                        const int kk = tau >> p.Fshift, fi = tau & (F - 1);
-                        const uint32_t slot = sg & (uint32_t)(nst - 1);
-                        if (fm3 == gi) {
-                            if (warp == 4) trace(1, f, 0);
-                            if (!waited) { mbar_wait(barRaw_full + 8 * slot, (sg >> p.nst_shift) & 1u); waited = true; }
-                            if (warp == 4) trace(1, f, 1);
-                            // frame of this row at tile time tau, and its position inside the staged block
-                            int t, rel;
-                            if (phase == 0) { t = tau; rel = fi; }
-                            else { t = Te - 1 - tau; rel = t - max(Te - (kk + 1) * F, 0); }
-                            const bool ok = tau < Te;
-                            const uint32_t rowp = raw0 + slot * stage_bytes + (uint32_t)(ok ? rel : 0) * rowbytes;
-                            // A stage free?  (the MMAs that read it three frames ago have completed)
-                            mbar_wait(barA_free + 8 * gi, cph ^ 1u);
-                            if (warp == 4) trace(1, f, 2);
-                            tc_fence_after();
+                bool waited = false;                   // raw_full of the current stage already observed by this warp
+                for (int tau = 0; tau < Tt; tau++, f++) {
+                    const int fi = tau & (F - 1);
+                    const uint32_t slot = sg & (uint32_t)(nst - 1);
+                    if (fm3 == gi) {
+                        if (warp == ET_CONV_WARP0) trace(1, f, 0);
+                        if (!waited) { mbar_wait(barRaw_full + 8 * slot, (sg >> p.nst_shift) & 1u); waited = true; }
+                        if (warp == ET_CONV_WARP0) trace(1, f, 1);
+                        const bool ok = tau < Te;
+                        const uint32_t rowp = raw0 + slot * stage_bytes + (uint32_t)(ok ? fi : 0) * rowbytes;
+                        // A stage free?  (the MMAs that read it ET_CONV_GROUPS frames ago have completed)
+                        mbar_wait(barA_free + 8 * gi, cph ^ 1u);
+                        if (warp == ET_CONV_WARP0) trace(1, f, 2);
+                        tc_fence_after();
 #pragma unroll 2
-                            for (int c = 0; c < npairs; c++) {
-                                float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-                                if (ok && 2 * c < nrd4) x0 = lds4(rowp + 32u * c);
-                                if (ok && 2 * c + 1 < nrd4) x1 = lds4(rowp + 32u * c + 16u);
-                                uint32_t v[16];
-                                split4(x0, lds4(sbS + 32u * c), lds4(sbB + 32u * c), v, v + 8);
-                                split4(x1, lds4(sbS + 32u * c + 16u), lds4(sbB + 32u * c + 16u), v + 4, v + 12);
-                                tmem_st16(ta + 16u * c, v);
-                            }
-                            tmem_st_wait();
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(barA_full + 8 * gi);
-                            cph ^= 1u;
-                            if (warp == 4) trace(1, f, 3);
+                        for (int c = 0; c < npairs; c++) {
+                            float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+                            if (ok && 2 * c < nrd4) x0 = lds4(rowp + 32u * c);
+                            if (ok && 2 * c + 1 < nrd4) x1 = lds4(rowp + 32u * c + 16u);
+                            uint32_t v[16];
+                            split4(x0, lds4(sbS + 32u * c), lds4(sbB + 32u * c), v, v + 8);
+                            split4(x1, lds4(sbS + 32u * c + 16u), lds4(sbB + 32u * c + 16u), v + 4, v + 12);
+                            tmem_st16(ta + 16u * c, v);
                         }
-                        if (fi == F - 1 || tau == Tt - 1) {      // leaving this stage: every converter warp releases it once
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(barRaw_empty + 8 * slot);
-                            sg++; waited = false;
-                        }
-                        if (++fm3 == 3) fm3 = 0;
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(barA_full + 8 * gi);
+                        cph ^= 1u;
+                        if (warp == ET_CONV_WARP0) trace(1, f, 3);
                     }
+                    if (fi == F - 1 || tau == Tt - 1) {      // leaving this stage: every converter warp releases it once
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(barRaw_empty + 8 * slot);
+                        sg++; waited = false;
+                    }
+                    if (++fm3 == ET_CONV_GROUPS) fm3 = 0;
                 }
             }
         } else {
-            // ===================== recursions: one thread per utterance =====================
-            float *scr = p.scratch + (size_t)blockIdx.x * p.maxT * 8 * TC_ROWS + r;      // [t][j][row]
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            // ===================== recursions: one thread per utterance, two groups alternating tiles =====================
+            const int wg = warp >> 2;
+            float *scr = p.scratch + (size_t)(blockIdx.x * ET_REC_WGS + wg) * p.maxT * 16 * TC_ROWS + r;      // [t][alpha-hat 0-7 | e' 8-15][row]
+            int kt = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, kt++) {
                 const int Tt = tile_frames(tile);
-                int mbase;
-                tile_models(tile, mbase);
+                if ((kt & 1) != wg) { f += (uint32_t)Tt; continue; }         // the other group's tile
+                // The accumulator barriers carry one parity bit: a group may only start waiting on them once the other group
+                // has consumed the last frame of the previous tile (its hand-over arrival), or a stale phase would pass.
+                if (kt > 0) mbar_wait(barTurn + 8 * wg, (uint32_t)(((kt - 1) >> 1) & 1));
+                int mf;
+                tile_models(tile, mf);
                 int m, pos; int64_t off;
                 const int T = row_info(tile * TC_ROWS + r, m, pos, off);
                 const int u = pos >= 0 ? p.order[pos] : 0;
-                const uint32_t acc_col = tmem_acc + lane_sel + (uint32_t)(m - mbase) * 8u;   // warp-uniform: one model per quadrant
+                const uint32_t acc_col = tmem_acc + lane_sel + (uint32_t)(m - mf) * 16u;   // warp-uniform: one model per quadrant
                 // transition constants of this thread's model stay in shared memory and are re-read every frame: holding the
                 // 25 of them in registers made the recursion spill (local-memory round trips inside a serial chain)
                 const uint32_t trM = smem_u32(sTr) + (uint32_t)m * (TC_TRQ * 16u);
                 const float lb0 = sTr[m * TC_TRQ + 2].y;
 
-                // e'_t(j) = E[t, j] + ln A[j, j] of this thread's model, frame counter fr.  (Fetching one frame ahead was
-                // measured: the extra live registers spill inside the serial recursion and the kernel gets 45 % slower.)
+                // e'_t(j) = E[t, j] + ln A[j, j] of this thread's model, frame counter fr: the W_hi and the W_lo products
+                // arrive in separate accumulator columns
                 auto fetch = [&](uint32_t fr, float (&e)[8]) {
                     const uint32_t s = fr & 1u;
                     if (warp == 0) trace(2, fr, 0);
                     mbar_wait(barAcc_full + 8 * s, (fr >> 1) & 1u);
                     if (warp == 0) trace(2, fr, 1);
                     tc_fence_after();
-                    uint32_t ev[8];
-                    tmem_ld8(acc_col + s * (uint32_t)ncols, ev);
+                    uint32_t ev[16];
+                    tmem_ld16(acc_col + s * (uint32_t)ET_ACC_W, ev);
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(barAcc_empty + 8 * s);
                     if (warp == 0) trace(2, fr, 2);
 #pragma unroll
-                    for (int j = 0; j < 8; j++) e[j] = __uint_as_float(ev[j]);
+                    for (int j = 0; j < 8; j++) e[j] = __uint_as_float(ev[j]) + __uint_as_float(ev[8 + j]);
                 };
 
                 // ---------------- forward (custom_hmm.py:176-211), U_j = alpha-hat_j + ln A[j,j] ----------------
@@ -386,6 +395,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
                         const float4 c03 = lds4(trM), c47 = lds4(trM + 16u), st03 = lds4(trM + 48u), st47 = lds4(trM + 64u);
                         const float cadv[8] = {0.f, c03.x, c03.y, c03.z, c03.w, c47.x, c47.y, c47.z};   // into state j from j-1 (U form)
                         const float stay[8] = {st03.x, st03.y, st03.z, st03.w, st47.x, st47.y, st47.z, st47.w};
+                        float *sp = scr + (size_t)t * 16 * TC_ROWS;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) sp[(8 + j) * TC_ROWS] = e[j];
                         if (t == 0) {
                             U[0] = lb0 + e[0];
                         } else {
@@ -417,14 +429,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
 #pragma unroll
                         for (int j = 0; j < 8; j++) { U[j] -= sh; a[j] -= sh; }
                         ax -= sh; base += sh;
-                        float *sp = scr + (size_t)t * 8 * TC_ROWS;
 #pragma unroll
                         for (int j = 0; j < 8; j++) sp[j * TC_ROWS] = a[j];
                     }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(barTurn + 8 * (wg ^ 1));              // forward sweep done: the other group's turn
                 if (pos >= 0 && T > 0) p.loglik[u] = ll;
 
-                // ---------------- backward + gamma + xi sums (custom_hmm.py:213-322) ----------------
+                // ---------------- backward + gamma + xi sums (custom_hmm.py:213-322): thread-private over the scratch ----------------
                 float gG[8], gX[8], b[8], en[8];
                 float glast = 0.f;                                 // gamma[T-1, j] of the emitting states (0 or NaN): occ = G + it
 #pragma unroll
@@ -434,79 +447,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_estep_tc(const EtParams p) {
 #pragma unroll
                 for (int j = 0; j < 8; j++) atn[j] = 0.f;
                 if (T >= 2) {
-                    const float *sp = scr + (size_t)(T - 2) * 8 * TC_ROWS;
+                    const float *sp = scr + (size_t)(T - 2) * 16 * TC_ROWS;
 #pragma unroll
                     for (int j = 0; j < 8; j++) atn[j] = sp[j * TC_ROWS];
                 }
-                for (int tau = 0; tau < Tt; tau++, f++) {
-                    float e[8];
-                    fetch(f, e);
-                    if (tau < T) {
-                        const int t = T - 1 - tau;
-                        float *go = p.gamma + (size_t)(off + t) * 8;
-                        if (tau == 0) {
-                            // gamma[T-1] is one-hot on the exit state unless alpha[T-1, exit] = -inf (then the row is NaN)
-                            const float gl = exit_ok ? 0.f : NAN;
-                            *reinterpret_cast<float4 *>(go) = make_float4(gl, gl, gl, gl);
-                            *reinterpret_cast<float4 *>(go + 4) = make_float4(gl, gl, gl, gl);
-                            glast = gl;
-                        } else {
-                            const float4 bd03 = lds4(trM + 80u), bd47 = lds4(trM + 96u);
-                            const float badv[7] = {bd03.x, bd03.y, bd03.z, bd03.w, bd47.x, bd47.y, bd47.z};
-                            float at[8], self[8], nb[8];
+                for (int t = T - 1; t >= 0; t--) {
+                    float e[8];                                    // e'_t: consumed at the end of this iteration (as e'_{t+1} of the next)
+                    {
+                        const float *sp = scr + (size_t)t * 16 * TC_ROWS;
 #pragma unroll
-                            for (int j = 0; j < 8; j++) { at[j] = atn[j]; self[j] = en[j] + b[j]; }   // ln A_jj + e_{t+1}(j) + beta_{t+1}(j)
-                            if (t >= 1) {
-                                const float *sp = scr + (size_t)(t - 1) * 8 * TC_ROWS;
+                        for (int j = 0; j < 8; j++) e[j] = sp[(8 + j) * TC_ROWS];
+                    }
+                    float *go = p.gamma + (size_t)(off + t) * 8;
+                    if (t == T - 1) {
+                        // gamma[T-1] is one-hot on the exit state unless alpha[T-1, exit] = -inf (then the row is NaN)
+                        const float gl = exit_ok ? 0.f : NAN;
+                        *reinterpret_cast<float4 *>(go) = make_float4(gl, gl, gl, gl);
+                        *reinterpret_cast<float4 *>(go + 4) = make_float4(gl, gl, gl, gl);
+                        glast = gl;
+                    } else {
+                        const float4 bd03 = lds4(trM + 80u), bd47 = lds4(trM + 96u);
+                        const float badv[7] = {bd03.x, bd03.y, bd03.z, bd03.w, bd47.x, bd47.y, bd47.z};
+                        float at[8], self[8], nb[8];
 #pragma unroll
-                                for (int j = 0; j < 8; j++) atn[j] = sp[j * TC_ROWS];
-                            }
+                        for (int j = 0; j < 8; j++) { at[j] = atn[j]; self[j] = en[j] + b[j]; }   // ln A_jj + e_{t+1}(j) + beta_{t+1}(j)
+                        if (t >= 1) {
+                            const float *sp = scr + (size_t)(t - 1) * 16 * TC_ROWS;
 #pragma unroll
-                            for (int j = 0; j < 7; j++) nb[j] = lae32(self[j], badv[j] + self[j + 1]);
-                            nb[7] = lae32(self[7], bd47.w + bx);                         // ln A[N, exit] + beta[t+1, exit]
-                            const float b0 = sTr[m * TC_TRQ + 7].x + self[0];            // beta[t, entry] = ln A01 - ln A11 + self_1
-                            float lg[8];
-#pragma unroll
-                            for (int j = 0; j < 8; j++) lg[j] = at[j] + nb[j];
-                            const float xs7 = at[7] + self[7];
-                            float mxl = fmaxf(fmaxf(lg[0], lg[1]), lg[2]);
-                            mxl = fmaxf(fmaxf(lg[3], lg[4]), mxl);
-                            mxl = fmaxf(fmaxf(lg[5], lg[6]), mxl);
-                            mxl = fmaxf(lg[7], mxl);
-                            const float ent = (t == 0) ? b0 : -INFINITY;                 // alpha[0, entry] = 0
-                            mxl = fmaxf(mxl, ent);
-                            float pj[8], sum = 0.f;
-#pragma unroll
-                            for (int j = 0; j < 8; j++) { pj[j] = fexp32(lg[j] - mxl); sum += pj[j]; }
-                            const float pe = fexp32(ent - mxl);
-                            // xi normaliser (:319-320): arcs (0,1), (i,i), (i,i+1) for i < N; the (N, exit) arc contributes 0
-                            const float q7 = fexp32(xs7 - mxl);
-                            const float xsum = (sum - pj[7]) + q7 + pe;
-                            sum += pe;
-                            const float inv = 1.0f / sum;                                // all -inf row -> NaN like the reference
-                            const float xinv = (mxl > -INFINITY && xsum > 0.f) ? 1.0f / xsum : 0.f;
-                            float gm[8];
-#pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                gm[j] = pj[j] * inv;
-                                gG[j] += gm[j];
-                                const float xq = (mxl > -INFINITY) ? fexp32((at[j] + self[j]) - mxl) : 0.f;
-                                gX[j] += xq * xinv;
-                            }
-                            *reinterpret_cast<float4 *>(go) = make_float4(gm[0], gm[1], gm[2], gm[3]);
-                            *reinterpret_cast<float4 *>(go + 4) = make_float4(gm[4], gm[5], gm[6], gm[7]);
-                            float mb = fmaxf(fmaxf(nb[0], nb[1]), nb[2]);
-                            mb = fmaxf(fmaxf(nb[3], nb[4]), mb);
-                            mb = fmaxf(fmaxf(nb[5], nb[6]), mb);
-                            mb = fmaxf(nb[7], mb);
-                            const bool fin = mb > -INFINITY && mb < INFINITY;
-#pragma unroll
-                            for (int j = 0; j < 8; j++) b[j] = fin ? nb[j] - mb : nb[j];
-                            bx = -INFINITY;
+                            for (int j = 0; j < 8; j++) atn[j] = sp[j * TC_ROWS];
                         }
 #pragma unroll
-                        for (int j = 0; j < 8; j++) en[j] = e[j];
+                        for (int j = 0; j < 7; j++) nb[j] = lae32(self[j], badv[j] + self[j + 1]);
+                        nb[7] = lae32(self[7], bd47.w + bx);                         // ln A[N, exit] + beta[t+1, exit]
+                        const float b0 = sTr[m * TC_TRQ + 7].x + self[0];            // beta[t, entry] = ln A01 - ln A11 + self_1
+                        float lg[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) lg[j] = at[j] + nb[j];
+                        const float xs7 = at[7] + self[7];
+                        float mxl = fmaxf(fmaxf(lg[0], lg[1]), lg[2]);
+                        mxl = fmaxf(fmaxf(lg[3], lg[4]), mxl);
+                        mxl = fmaxf(fmaxf(lg[5], lg[6]), mxl);
+                        mxl = fmaxf(lg[7], mxl);
+                        const float ent = (t == 0) ? b0 : -INFINITY;                 // alpha[0, entry] = 0
+                        mxl = fmaxf(mxl, ent);
+                        float pj[8], sum = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) { pj[j] = fexp32(lg[j] - mxl); sum += pj[j]; }
+                        const float pe = fexp32(ent - mxl);
+                        // xi normaliser (:319-320): arcs (0,1), (i,i), (i,i+1) for i < N; the (N, exit) arc contributes 0
+                        const float q7 = fexp32(xs7 - mxl);
+                        const float xsum = (sum - pj[7]) + q7 + pe;
+                        sum += pe;
+                        const float inv = 1.0f / sum;                                // all -inf row -> NaN like the reference
+                        const float xinv = (mxl > -INFINITY && xsum > 0.f) ? 1.0f / xsum : 0.f;
+                        float gm[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            gm[j] = pj[j] * inv;
+                            gG[j] += gm[j];
+                            const float xq = (mxl > -INFINITY) ? fexp32((at[j] + self[j]) - mxl) : 0.f;
+                            gX[j] += xq * xinv;
+                        }
+                        *reinterpret_cast<float4 *>(go) = make_float4(gm[0], gm[1], gm[2], gm[3]);
+                        *reinterpret_cast<float4 *>(go + 4) = make_float4(gm[4], gm[5], gm[6], gm[7]);
+                        float mb = fmaxf(fmaxf(nb[0], nb[1]), nb[2]);
+                        mb = fmaxf(fmaxf(nb[3], nb[4]), mb);
+                        mb = fmaxf(fmaxf(nb[5], nb[6]), mb);
+                        mb = fmaxf(nb[7], mb);
+                        const bool fin = mb > -INFINITY && mb < INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) b[j] = fin ? nb[j] - mb : nb[j];
+                        bx = -INFINITY;
                     }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) en[j] = e[j];
                 }
                 if (pos >= 0) {
                     float *us = p.ustats + (size_t)pos * 24;
@@ -549,7 +563,7 @@ int sapr_estep_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx,
     if (Fshift <= 1 && et_smem_layout(M, nck, ncols, 4, rstride).total <= budget) { nst = 4; nst_shift = 2; }
     L = et_smem_layout(M, nck, ncols, nst, rstride);
     const int grid = std::min((B + 31 * M + TC_ROWS - 1) / TC_ROWS, ctx->sm_count);
-    int rc = sapr_ws_reserve(ctx, 7, (size_t)grid * max_T * 8 * TC_ROWS * sizeof(float));
+    int rc = sapr_ws_reserve(ctx, 7, (size_t)grid * ET_REC_WGS * max_T * 16 * TC_ROWS * sizeof(float));
     if (rc) return rc;
     EtParams prm;
     prm.X = X; prm.ldx = ldx; prm.offsets = offsets; prm.B = B; prm.order = order; prm.model_start = model_start;
@@ -578,7 +592,7 @@ int sapr_estep_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx,
         SAPR_CUDA(ctx, cudaMemsetAsync(dtr, 0, nrec * sizeof(long long), ctx->stream));
         prm.trace = dtr;
         SAPR_CUDA(ctx, cudaFuncSetAttribute(k_estep_tc<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        k_estep_tc<true, 0><<<grid, TC_THREADS, L.total, ctx->stream>>>(prm);
+        k_estep_tc<true, 0><<<grid, ET_THREADS, L.total, ctx->stream>>>(prm);
         SAPR_LAUNCH_CHECK(ctx);
         std::vector<long long> h(nrec);
         cudaMemcpyAsync(h.data(), dtr, nrec * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
@@ -599,7 +613,7 @@ int sapr_estep_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx,
     SAPR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     {
         ProfScope ps(ctx, 2);
-        kern<<<grid, TC_THREADS, L.total, ctx->stream>>>(prm);
+        kern<<<grid, ET_THREADS, L.total, ctx->stream>>>(prm);
     }
     SAPR_LAUNCH_CHECK(ctx);
     return SAPR_OK;

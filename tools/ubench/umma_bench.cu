@@ -86,7 +86,7 @@ int main() {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     const int iters = 600;
     for (int mode = 0; mode < 4; mode++)
-        for (int N : {32, 48, 64, 96, 128, 192, 256}) {
+        for (int N : {16, 32, 48, 64, 96, 128, 192, 256}) {
             for (int rep = 0; rep < 2; rep++) {
                 k<<<1, 128, 64 * 1024>>>(N, mode, iters, d);
                 cudaError_t e = cudaDeviceSynchronize();
