@@ -372,10 +372,13 @@ __device__ __forceinline__ float2 st_sub2(float2 a, float2 b) {
     return *reinterpret_cast<float2 *>(&d);
 }
 
-// Shared-memory staged: a producer warp bulk-copies chunks of up to STATS2_CF consecutive frames of one utterance
-// (feature rows and gamma rows are both contiguous in HBM) into a 3-stage ring; the ndp x 32 consumer threads read
-// their two dims and gamma from shared memory.  blockDim.x = ndp * STATS2_SLOTS; thread 0 doubles as the producer
-// (it requests chunk k + 2 before it consumes chunk k).
+// Shared-memory staged.  All utterances of a tile belong to one model, so the tile's frames are ONE stream: a
+// dedicated producer warp bulk-copies it, STATS2_CF frames per stage (a stage may span utterance boundaries: one copy
+// of feature rows + one of gamma rows per piece; both are contiguous in HBM), into a STATS2_STAGES-deep ring.
+// Consumer thread = (dim quad, state half, frame slot): 4 dims x 4 states x 2 moments = 32 packed accumulators, per
+// frame one LDS.128 of features, one of gamma, and 20 FFMA2/FMUL2.  When D < Dp the first padding dim carries the
+// constant 1, so its first-moment column is sum_t gamma (the occupancy the re-pivot needs) at no extra cost.
+// blockDim.x = (Dp / 4) * 2 * STATS2_SLOTS consumers + 32 (producer warp).
 #define STATS2_CF 128
 #define STATS2_STAGES 6
 __device__ __forceinline__ uint32_t st_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -387,18 +390,19 @@ __device__ __forceinline__ void st_wait(uint32_t bar, uint32_t parity) {
         ::"r"(bar), "r"(parity) : "memory");
 }
 
-__global__ void __launch_bounds__(640, 1)
+__global__ void __launch_bounds__(672, 1)
 k_stats_diag8(const float *__restrict__ X, int ldx, const int64_t *__restrict__ offsets, const int32_t *__restrict__ order,
               const int32_t *__restrict__ model_start, int M, int D, int Dp, int S, int upc, const double *__restrict__ mean,
               const float *__restrict__ gamma, double *__restrict__ partial) {
-    constexpr int N = 8;
-    __shared__ int s_m, s_tim;
+    constexpr int N = 8, NH = 4;
+    __shared__ int s_m, s_tim, s_ftot;
     __shared__ int64_t s_off[STATS2_MAXUPC];
     __shared__ int s_T[STATS2_MAXUPC];
     __shared__ __align__(8) uint64_t s_bar[2 * STATS2_STAGES];
-    const int ndp = Dp / 2, ncons = ndp * STATS2_SLOTS, tid = threadIdx.x;
+    const int ndq = Dp / 4, ncons = ndq * 2 * STATS2_SLOTS, tid = threadIdx.x;
     const bool consumer = tid < ncons;
-    const int dp = tid % ndp, slot = tid / ndp, d0 = 2 * dp;
+    const int dq = tid % ndq, sh = (tid / ndq) & 1, slot = tid / (2 * ndq), d0 = 4 * dq;
+    const bool ones = Dp > D;                                    // dim D (padding) carries the constant 1
     extern __shared__ __align__(16) unsigned char s_dyn[];
     // the ring; at the end of the tile it is reused for the per-slot partials S1, S2 [STATS2_SLOTS][2][N][Dp], G [STATS2_SLOTS][N]
     float *s_acc = reinterpret_cast<float *>(s_dyn);
@@ -417,13 +421,13 @@ k_stats_diag8(const float *__restrict__ X, int ldx, const int64_t *__restrict__ 
     }
     __syncthreads();
     const int m = s_m;
-    float *mine = s_acc + (size_t)slot * 2 * N * Dp + d0;       // element (k, j, q) at mine[(k * N + j) * Dp + q]
-    float2 s1[N], s2[N], gs[N / 2];
+    float2 s1[NH][2], s2[NH][2], gs[NH / 2];
 #pragma unroll
-    for (int j = 0; j < N; j++) { s1[j] = make_float2(0.f, 0.f); s2[j] = make_float2(0.f, 0.f); }
+    for (int j = 0; j < NH; j++)
 #pragma unroll
-    for (int j = 0; j < N / 2; j++) gs[j] = make_float2(0.f, 0.f);
-    (void)consumer;
+        for (int h = 0; h < 2; h++) { s1[j][h] = make_float2(0.f, 0.f); s2[j][h] = make_float2(0.f, 0.f); }
+#pragma unroll
+    for (int j = 0; j < NH / 2; j++) gs[j] = make_float2(0.f, 0.f);
     int nutt = 0;
     if (m >= 0) {
         const int pbeg = model_start[m] + s_tim * upc;
@@ -431,73 +435,80 @@ k_stats_diag8(const float *__restrict__ X, int ldx, const int64_t *__restrict__ 
         for (int i = tid; i < nutt; i += blockDim.x) {      // the tile's utterance table: frame offset and length
             const int u = order[pbeg + i];
             const int64_t o = offsets[u];
-            s_off[i] = o; s_T[i] = (int)(offsets[u + 1] - o);
+            s_off[i] = o; s_T[i] = max((int)(offsets[u + 1] - o), 0);
         }
     }
     __syncthreads();
-    // pivot g: mean of the model's state means, rounded to fp32 (the same value is used in the float64 re-pivot)
-    float2 g = make_float2(0.f, 0.f);
-    if (m >= 0) {
-        double gx = 0.0, gy = 0.0;
-        for (int j = 0; j < N; j++) {
-            if (d0 < D) gx += mean[((size_t)m * S + j + 1) * D + d0];
-            if (d0 + 1 < D) gy += mean[((size_t)m * S + j + 1) * D + d0 + 1];
-        }
-        g = make_float2((float)(gx / N), (float)(gy / N));
+    if (tid == 0) {
+        int ft = 0;
+        for (int i = 0; i < nutt; i++) ft += s_T[i];
+        s_ftot = ft;
     }
-    if (m >= 0 && nutt > 0) {
-        // producer state (thread 0): next chunk to request
-        int ppi = 0, pc0 = 0;
-        uint32_t pk = 0;
-        auto issue_next = [&]() {
-            if (ppi >= nutt) return;
-            const int T = s_T[ppi];
-            const uint32_t st = pk % STATS2_STAGES, ph = (pk / STATS2_STAGES) & 1u;
-            const int n = min(STATS2_CF, T - pc0);
-            st_wait(bar_empty + 8 * st, ph ^ 1u);
-            const uint32_t dst = st_smem(s_stage) + st * stage_bytes;
-            const uint32_t bx = (uint32_t)n * rowbytes, bg = (uint32_t)n * 32u;
-            asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n\t}"
-                         ::"r"(bar_full + 8 * st), "r"(bx + bg) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(X + (size_t)(s_off[ppi] + pc0) * ldx), "r"(bx), "r"(bar_full + 8 * st) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst + STATS2_CF * rowbytes), "l"(gamma + (size_t)(s_off[ppi] + pc0) * N), "r"(bg),
-                         "r"(bar_full + 8 * st) : "memory");
-            pk++; pc0 += STATS2_CF;
-            while (ppi < nutt && pc0 >= s_T[ppi]) { pc0 = 0; ppi++; }
-        };
-        if (tid == 0) {
-            while (ppi < nutt && s_T[ppi] <= 0) ppi++;
-            for (int i = 0; i < STATS2_STAGES - 1; i++) issue_next();
-        }
-        const float2 kk = make_float2((d0 < D) ? 1.f : 0.f, (d0 + 1 < D) ? 1.f : 0.f);
-        const float2 ng = make_float2(-g.x * kk.x, -g.y * kk.y);
-        uint32_t k = 0;
-        for (int pi = 0; pi < nutt; pi++) {
-            const int T = s_T[pi];
-            for (int c0 = 0; c0 < T; c0 += STATS2_CF, k++) {
-                const uint32_t st = k % STATS2_STAGES, ph = (k / STATS2_STAGES) & 1u;
-                const int n = min(STATS2_CF, T - c0);
-                if (tid == 0) issue_next();
-                st_wait(bar_full + 8 * st, ph);
-                const unsigned char *sx = s_stage + st * stage_bytes;
-                const unsigned char *sg = sx + STATS2_CF * rowbytes;
-                auto frame = [&](int fi) {
-                    const float2 xr = *reinterpret_cast<const float2 *>(sx + (size_t)fi * rowbytes + 8 * dp);
-                    const float4 g0 = *reinterpret_cast<const float4 *>(sg + fi * 32);
-                    const float4 g1 = *reinterpret_cast<const float4 *>(sg + fi * 32 + 16);
-                    const float2 x = st_fma2(xr, kk, ng);            // x' = x - g (0 for padded dims)
-                    const float2 q = st_mul2(x, x);
-                    const float gj[N] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-                    for (int j = 0; j < N; j++) {
-                        const float2 gg = make_float2(gj[j], gj[j]);
-                        s1[j] = st_fma2(gg, x, s1[j]);
-                        s2[j] = st_fma2(gg, q, s2[j]);
+    __syncthreads();
+    const int ftot = s_ftot;
+    const int nstage = (ftot + STATS2_CF - 1) / STATS2_CF;
+    if (m >= 0 && nstage > 0) {
+        if (!consumer) {
+            // ---------------- producer warp: lane 0 walks the tile's frame stream ----------------
+            if ((tid & 31) == 0) {
+                int ppi = 0, pc0 = 0;
+                while (ppi < nutt && s_T[ppi] <= 0) ppi++;
+                for (int k = 0; k < nstage; k++) {
+                    const uint32_t st = (uint32_t)k % STATS2_STAGES, ph = ((uint32_t)k / STATS2_STAGES) & 1u;
+                    const int n = min(STATS2_CF, ftot - k * STATS2_CF);
+                    st_wait(bar_empty + 8 * st, ph ^ 1u);
+                    const uint32_t dst = st_smem(s_stage) + st * stage_bytes;
+                    asm volatile("{\n\t.reg .b64 t;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1;\n\t}"
+                                 ::"r"(bar_full + 8 * st), "r"((uint32_t)n * (rowbytes + 32u)) : "memory");
+                    int filled = 0;
+                    while (filled < n) {
+                        const int piece = min(s_T[ppi] - pc0, n - filled);
+                        const size_t row = (size_t)(s_off[ppi] + pc0);
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(dst + (uint32_t)filled * rowbytes), "l"(X + row * ldx), "r"((uint32_t)piece * rowbytes),
+                                     "r"(bar_full + 8 * st) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(dst + STATS2_CF * rowbytes + (uint32_t)filled * 32u), "l"(gamma + row * N),
+                                     "r"((uint32_t)piece * 32u), "r"(bar_full + 8 * st) : "memory");
+                        filled += piece; pc0 += piece;
+                        while (ppi < nutt && pc0 >= s_T[ppi]) { pc0 = 0; ppi++; }
                     }
-                    gs[0].x += g0.x; gs[0].y += g0.y; gs[1].x += g0.z; gs[1].y += g0.w;
-                    gs[2].x += g1.x; gs[2].y += g1.y; gs[3].x += g1.z; gs[3].y += g1.w;
+                }
+            }
+        } else {
+            // pivot g: mean of the model's state means, rounded to fp32 (the same value is used in the float64 re-pivot)
+            float gp[4], kk[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                double gx = 0.0;
+                if (d0 + q < D)
+                    for (int j = 0; j < N; j++) gx += mean[((size_t)m * S + j + 1) * D + d0 + q];
+                kk[q] = (d0 + q < D) ? 1.f : 0.f;
+                gp[q] = -(float)(gx / N) * kk[q];
+                if (ones && d0 + q == D) gp[q] = 1.f;                        // x' = x * 0 + 1
+            }
+            const float2 kk01 = make_float2(kk[0], kk[1]), kk23 = make_float2(kk[2], kk[3]);
+            const float2 ng01 = make_float2(gp[0], gp[1]), ng23 = make_float2(gp[2], gp[3]);
+            for (int k = 0; k < nstage; k++) {
+                const uint32_t st = (uint32_t)k % STATS2_STAGES, ph = ((uint32_t)k / STATS2_STAGES) & 1u;
+                const int n = min(STATS2_CF, ftot - k * STATS2_CF);
+                st_wait(bar_full + 8 * st, ph);
+                const unsigned char *sx = s_stage + st * stage_bytes + 16 * dq;
+                const unsigned char *sg = s_stage + st * stage_bytes + STATS2_CF * rowbytes + 16 * sh;
+                auto frame = [&](int fi) {
+                    const float4 xr = *reinterpret_cast<const float4 *>(sx + (size_t)fi * rowbytes);
+                    const float4 g0 = *reinterpret_cast<const float4 *>(sg + fi * 32);
+                    const float2 x01 = st_fma2(make_float2(xr.x, xr.y), kk01, ng01);      // x' = x - g (0 for padded dims)
+                    const float2 x23 = st_fma2(make_float2(xr.z, xr.w), kk23, ng23);
+                    const float2 q01 = st_mul2(x01, x01), q23 = st_mul2(x23, x23);
+                    const float gj[NH] = {g0.x, g0.y, g0.z, g0.w};
+#pragma unroll
+                    for (int j = 0; j < NH; j++) {
+                        const float2 gg = make_float2(gj[j], gj[j]);
+                        s1[j][0] = st_fma2(gg, x01, s1[j][0]); s1[j][1] = st_fma2(gg, x23, s1[j][1]);
+                        s2[j][0] = st_fma2(gg, q01, s2[j][0]); s2[j][1] = st_fma2(gg, q23, s2[j][1]);
+                    }
+                    if (!ones) { gs[0].x += g0.x; gs[0].y += g0.y; gs[1].x += g0.z; gs[1].y += g0.w; }
                 };
                 if (n == STATS2_CF) {
 #pragma unroll
@@ -512,11 +523,22 @@ k_stats_diag8(const float *__restrict__ X, int ldx, const int64_t *__restrict__ 
         }
     }
     __syncthreads();            // every chunk consumed: the ring is free, reuse it for the per-slot partials
+    if (consumer) {
+        float *mine = s_acc + (size_t)slot * 2 * N * Dp + d0;       // element (k, j, q) at mine[(k * N + j) * Dp + q]
 #pragma unroll
-    for (int j = 0; j < N; j++) {
-        mine[(0 * N + j) * Dp] = s1[j].x; mine[(0 * N + j) * Dp + 1] = s1[j].y;
-        mine[(1 * N + j) * Dp] = s2[j].x; mine[(1 * N + j) * Dp + 1] = s2[j].y;
-        if (dp == 0) s_g[slot * N + j] = (j & 1) ? gs[j >> 1].y : gs[j >> 1].x;
+        for (int j = 0; j < NH; j++) {
+            const int js = NH * sh + j;
+            *reinterpret_cast<float4 *>(mine + (0 * N + js) * Dp) = make_float4(s1[j][0].x, s1[j][0].y, s1[j][1].x, s1[j][1].y);
+            *reinterpret_cast<float4 *>(mine + (1 * N + js) * Dp) = make_float4(s2[j][0].x, s2[j][0].y, s2[j][1].x, s2[j][1].y);
+            if (ones) {
+                if (D >= d0 && D < d0 + 4) {
+                    const int q = D - d0;
+                    s_g[slot * N + js] = (q == 0) ? s1[j][0].x : (q == 1) ? s1[j][0].y : (q == 2) ? s1[j][1].x : s1[j][1].y;
+                }
+            } else if (dq == 0) {
+                s_g[slot * N + js] = (j & 1) ? gs[j >> 1].y : gs[j >> 1].x;
+            }
+        }
     }
     __syncthreads();
     // fixed-order reduction over the frame slots and float64 re-pivot to the state means: one thread per output element
@@ -674,8 +696,8 @@ static int launch_estep(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, 
     // feature statistics over the whole batch
     const int ntiles = ntile_max;
     if (std::is_same<R, float>::value && N == 8) {
-        const int ncons = (Dp / 2) * STATS2_SLOTS;
-        dim3 sb2(ncons);
+        const int ncons = (Dp / 4) * 2 * STATS2_SLOTS;
+        dim3 sb2(ncons + 32);                          // + the producer warp
         const size_t ssm2 = std::max(sizeof(float) * STATS2_SLOTS * (2 * N * Dp + N), (size_t)STATS2_STAGES * STATS2_CF * (ldx * 4 + 32));
         if (ssm2 <= 227 * 1024 && ncons <= 640 && ncons % 32 == 0 && upc <= STATS2_MAXUPC) {
             SAPR_CUDA(ctx, cudaFuncSetAttribute(k_stats_diag8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm2));

@@ -38,6 +38,7 @@
 #define ET_LOAD_WARP0 (ET_MMA_WARP + 1)                    /* 17 .. 19 */
 #define ET_LOADERS 3
 #define ET_THREADS (32 * (ET_LOAD_WARP0 + ET_LOADERS))     /* 640 */
+#define ET_PF 3                                             /* backward sweep: L1 prefetch distance in frames */
 #define ET_ACC_W 64                                        /* accumulator stage: up to 4 models x 16 columns */
 
 struct EtParams {
@@ -51,6 +52,7 @@ struct EtParams {
     double *loglik;                                          // [B] by utterance id
     int Fshift, nst_shift; uint32_t rstride;
     int pair0[TC_GROUPS], npair[TC_GROUPS];                  // chunk pairs of the converting groups (group 0: none)
+    int pf;                                                  // backward sweep: L1 prefetch distance in frames
     long long *trace;                                        // [ET_TRACE_ROLES][ET_TRACE_FRAMES][ET_TRACE_EVENTS] or null
 };
 
@@ -452,6 +454,14 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_estep_tc(const EtParams p) {
                     for (int j = 0; j < 8; j++) atn[j] = sp[j * TC_ROWS];
                 }
                 for (int t = T - 1; t >= 0; t--) {
+                    // The scratch rows of this tile left L2 long ago (1.6 MB per group, 296 groups): one iteration does not
+                    // cover a DRAM round trip and registers for a deeper prefetch are not there, so the lines of frame
+                    // t - ET_PF are pulled into L1 now (one 128-byte line per state and warp) and the loads below hit there.
+                    if (t >= p.pf) {
+                        const float *pp = scr + (size_t)(t - p.pf) * 16 * TC_ROWS;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) asm volatile("prefetch.global.L1 [%0];" ::"l"(pp + j * TC_ROWS));
+                    }
                     float e[8];                                    // e'_t: consumed at the end of this iteration (as e'_{t+1} of the next)
                     {
                         const float *sp = scr + (size_t)t * 16 * TC_ROWS;
@@ -583,6 +593,7 @@ int sapr_estep_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx,
             prm.pair0[gI] = pa; prm.npair[gI] = cnt; pa += cnt;
         }
     }
+    prm.pf = getenv("SAPR_ET_PF") ? atoi(getenv("SAPR_ET_PF")) : ET_PF;      // tuning aid
     prm.trace = nullptr;
     const char *trace_path = getenv("SAPR_ET_TRACE");
     if (trace_path) {       // tuning aid: one traced launch, timestamps to a text file
