@@ -318,12 +318,12 @@ def main():
         estep = {"metric": "Baum-Welch E-step frame*state updates/s (fwd-bwd + statistics + all-reduce)",
                  "value": e_val, "unit": "updates/s", "ms_per_iteration": float(em.item()), "utterances_per_gpu": Be,
                  "roofline": {"bound": "hbm", "achieved": e_gbs, "peak": peak, "unit": "GB/s", "frac": e_gbs / peak,
-                              "kernels": ("k_estep_tc (tcgen05 emission, forward + backward sweep per tile) + k_stats_diag8"
+                              "kernels": ("k_estep_tc (tcgen05 emission in the forward sweep, alpha-hat + emissions to scratch, thread-private backward sweep) + k_stats_diag8"
                                           if tc else "k_estep_fused + k_stats_diag"),
                               "fwdbwd_kernel_ms": fb_ms / n_it, "stats_kernel_ms": st_ms / n_it,
                               "alg_bytes_per_iteration": ESTEP_BYTES_PER_UTT * Be, "traffic": e_traffic,
-                              "note": "the implementation reads the features three times (forward, backward, statistics); "
-                                      "algorithmic bytes count one read"}}
+                              "note": "the implementation reads the features twice (forward sweep, statistics) and round-trips 64 B per "
+                                      "frame of alpha-hat / emission scratch plus 32 B of gamma; algorithmic bytes count one feature read"}}
         models.mstep(stats, floor_v)
         torch.cuda.synchronize()
 

@@ -88,6 +88,7 @@ __device__ __forceinline__ float fexp32(float x) {      // exp(x), x <= 0 or -in
 
 // TRACE: CTA 0 records clock64() at its pipeline events (tuning aid, SAPR_ET_TRACE=file)
 #define ET_TRACE_FRAMES 64
+#define ET_TRACE_F0 440                           /* third tile of CTA 0: steady state, a backward sweep runs alongside */
 #define ET_TRACE_EVENTS 4
 #define ET_TRACE_ROLES 4
 template <bool TRACE, int NKS>
@@ -184,8 +185,8 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_estep_tc(const EtParams p) {
 
     uint32_t f = 0, sg = 0;
     auto trace = [&](int role, uint32_t frame, int ev) {
-        if (TRACE && blockIdx.x == 0 && lane == 0 && frame >= 40 && frame < 40 + ET_TRACE_FRAMES)
-            p.trace[((size_t)role * ET_TRACE_FRAMES + (frame - 40)) * ET_TRACE_EVENTS + ev] = clock64();
+        if (TRACE && blockIdx.x == 0 && lane == 0 && frame >= ET_TRACE_F0 && frame < ET_TRACE_F0 + ET_TRACE_FRAMES)
+            p.trace[((size_t)role * ET_TRACE_FRAMES + (frame - ET_TRACE_F0)) * ET_TRACE_EVENTS + ev] = clock64();
     };
 
     if (warp >= ET_LOAD_WARP0) {
@@ -211,16 +212,16 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_estep_tc(const EtParams p) {
                 int nf[RPT], tot = 0;
 #pragma unroll
                 for (int i = 0; i < RPT; i++) { nf[i] = min(max(Te[i] - k * F, 0), F); tot += nf[i]; }
-                if (lw == 0) trace(3, sg * 4 + 40, 0);
+                if (lw == 0) trace(3, sg * 4 + ET_TRACE_F0, 0);
                 mbar_wait(barRaw_empty + 8 * slot, ph ^ 1u);
-                if (lw == 0) trace(3, sg * 4 + 40, 1);
+                if (lw == 0) trace(3, sg * 4 + ET_TRACE_F0, 1);
                 mbar_arrive_tx(bar, (uint32_t)tot * rowbytes);
 #pragma unroll
                 for (int i = 0; i < RPT; i++)
                     if (nf[i] > 0)
                         bulk_g2s(smem_u32(sRaw) + slot * stage_bytes + (uint32_t)(rlo + lane + 32 * i) * rstride,
                                  p.X + (size_t)(off[i] + k * F) * p.ldx, (uint32_t)nf[i] * rowbytes, bar);
-                if (lw == 0) trace(3, sg * 4 + 40, 2);
+                if (lw == 0) trace(3, sg * 4 + ET_TRACE_F0, 2);
             }
         }
     } else if (warp == ET_MMA_WARP) {
@@ -612,7 +613,7 @@ int sapr_estep_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx,
         if (FILE *fp = fopen(trace_path, "w")) {
             for (int ro = 0; ro < ET_TRACE_ROLES; ro++)
                 for (int fr = 0; fr < ET_TRACE_FRAMES; fr++) {
-                    fprintf(fp, "%d %d", ro, fr + 40);
+                    fprintf(fp, "%d %d", ro, fr + ET_TRACE_F0);
                     for (int e = 0; e < ET_TRACE_EVENTS; e++) fprintf(fp, " %lld", h[((size_t)ro * ET_TRACE_FRAMES + fr) * ET_TRACE_EVENTS + e]);
                     fprintf(fp, "\n");
                 }

@@ -8,7 +8,7 @@ os.environ["SAPR_ET_TRACE"] = out
 import torch
 from sapr_b200 import engine, synth
 dev = torch.device("cuda", 0)
-B = 148 * 128 * 2
+B = 148 * 128 * 4
 X, offsets, labels, mu, sd = synth.device_corpus(B, 11, 8, 39, 200, 12345, dev)
 A, means, var = synth.truth_models(mu, sd, 0.9)
 m = engine.WordModels(11, 8, 39); m.set(means, var, A)
