@@ -135,3 +135,20 @@ def test_mfcc_oracle_basic_properties():
     assert m.shape == (13, 1 + sr // 220) and np.all(np.isfinite(m))
     W = mfcc_oracle.mel_filterbank(sr, 2048, 128, 0.0, sr / 2, True)
     assert W.shape == (128, 1025) and np.all(W >= 0) and np.all(W.sum(axis=1) > 0)
+
+
+def test_eval_metrics_match_sklearn():
+    """eval.py:28-38 calls sklearn's confusion_matrix / accuracy_score without labels=: rows are the labels that occur."""
+    sk = pytest.importorskip("sklearn.metrics")
+    from sapr_b200.eval import calculate_metrics, extract_labels
+    vocab = ["heed", "hid", "head", "had", "hard", "hud", "hod", "hoard", "hood", "whod", "heard"]
+    rng = np.random.default_rng(3)
+    for present in (vocab, vocab[:4] + vocab[6:7]):                       # a case where some words never occur
+        t = [present[i] for i in rng.integers(0, len(present), 200)]
+        p = [present[i] for i in rng.integers(0, len(present), 200)]
+        cm, acc = calculate_metrics(t, p, vocab)
+        ti = [vocab.index(w) for w in t]; pi = [vocab.index(w) for w in p]
+        assert np.array_equal(cm, sk.confusion_matrix(ti, pi))
+        assert acc == pytest.approx(sk.accuracy_score(ti, pi))
+    res = {"heed": [{"true_word": "heed", "predicted_word": "hid"}], "hid": [{"true_word": "hid", "predicted_word": "hid"}]}
+    assert extract_labels(res) == (["heed", "hid"], ["hid", "hid"])
