@@ -34,63 +34,134 @@ __global__ void k_mfcc_init_max(int *umax, int B) {
     if (i < B) umax[i] = float_to_ordered(-INFINITY);
 }
 
-__global__ void k_mfcc_logmel(const float *__restrict__ audio, const int64_t *__restrict__ sample_off,
-                              const int64_t *__restrict__ frame_off, const int32_t *__restrict__ utt_of_frame,
-                              int n_fft, int log2n, int hop, int center, float preemph,
-                              const float *__restrict__ window, const float2 *__restrict__ twiddle, int n_mels,
-                              const int32_t *__restrict__ mel_lo, const int32_t *__restrict__ mel_hi,
-                              const int32_t *__restrict__ mel_ptr, const float *__restrict__ mel_w, int log_db,
-                              float *__restrict__ logmel, int *__restrict__ umax) {
-    extern __shared__ float2 s_x[];   // n_fft complex, then n_fft/2+1 power values overlay
-    const int64_t f = blockIdx.x;
-    const int u = utt_of_frame[f];
-    const int64_t s0 = sample_off[u], len = sample_off[u + 1] - s0;
-    const int64_t fi = f - frame_off[u];
-    const int64_t start = fi * hop - (center ? n_fft / 2 : 0);
-    for (int i = threadIdx.x; i < n_fft; i += blockDim.x) {
-        const int64_t s = start + i;
-        float v = 0.0f;
-        if (s >= 0 && s < len) {
-            v = audio[s0 + s];
-            if (preemph != 0.0f && s > 0) v -= preemph * audio[s0 + s - 1];
-        }
-        v *= window[i];
-        const int r = __brev((unsigned)i) >> (32 - log2n);
-        s_x[r] = make_float2(v, 0.0f);
+// frame -> utterance by binary search over the frame offsets (replaces a host-built table of one int per frame)
+__global__ void k_mfcc_utt_of_frame(const int64_t *__restrict__ frame_off, int B, int64_t total_frames, int32_t *__restrict__ uof) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= total_frames) return;
+    int lo = 0, hi = B;                       // largest u with frame_off[u] <= f
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (frame_off[mid] <= f) lo = mid; else hi = mid;
     }
+    uof[f] = lo;
+}
+
+// One WARP per PAIR of frames (blockDim.x / 32 pairs per CTA).  Frame a goes into the real part and frame b into the
+// imaginary part of ONE complex transform (both spectra fall out of Z[k] and conj(Z[N-k])), the radix-2 stages are taken
+// two at a time in registers (same butterflies, half the shared-memory passes), and only __syncwarp separates the passes.
+__global__ void __launch_bounds__(256)
+k_mfcc_logmel(const float *__restrict__ audio, const int64_t *__restrict__ sample_off,
+              const int64_t *__restrict__ frame_off, const int32_t *__restrict__ utt_of_frame, int64_t total_frames,
+              int n_fft, int log2n, int hop, int center, float preemph,
+              const float *__restrict__ g_window, const float2 *__restrict__ g_twiddle, int n_mels,
+              const int32_t *__restrict__ g_mel_lo, const int32_t *__restrict__ g_mel_hi,
+              const int32_t *__restrict__ g_mel_ptr, const float *__restrict__ g_mel_w, int n_mel_w, int log_db,
+              float *__restrict__ logmel, int *__restrict__ umax) {
+    extern __shared__ float2 s_all[];   // tables, then per warp: n_fft complex (one pad slot per 16: index i -> i + i / 16) and 2 x (n_fft/2 + 1) power values
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const int nb = n_fft / 2 + 1;
+    // persistent CTA: the parameter tables are staged in shared memory once, then the warps loop over frame pairs
+    float2 *twiddle = s_all;                                             // n_fft / 2
+    float *window = reinterpret_cast<float *>(twiddle + n_fft / 2);      // n_fft
+    float *mel_w = window + n_fft;                                       // n_mel_w
+    int *mel_lo = reinterpret_cast<int *>(mel_w + n_mel_w), *mel_hi = mel_lo + n_mels, *mel_ptr = mel_hi + n_mels;
+    const size_t tab_f2 = ((size_t)n_fft + n_fft + n_mel_w + 3 * n_mels + 1) / 2 + 1;      // table size in float2 units (8-byte aligned)
+    for (int i = threadIdx.x; i < n_fft / 2; i += blockDim.x) twiddle[i] = g_twiddle[i];
+    for (int i = threadIdx.x; i < n_fft; i += blockDim.x) window[i] = g_window[i];
+    for (int i = threadIdx.x; i < n_mel_w; i += blockDim.x) mel_w[i] = g_mel_w[i];
+    for (int i = threadIdx.x; i < n_mels; i += blockDim.x) { mel_lo[i] = g_mel_lo[i]; mel_hi[i] = g_mel_hi[i]; mel_ptr[i] = g_mel_ptr[i]; }
     __syncthreads();
-    for (int st = 1; st <= log2n; st++) {
-        const int half = 1 << (st - 1);
-        for (int k = threadIdx.x; k < n_fft / 2; k += blockDim.x) {
-            const int grp = k / half, pos = k % half;
-            const int i0 = grp * 2 * half + pos, i1 = i0 + half;
-            const float2 w = twiddle[pos * (n_fft / (2 * half))];
-            const float2 a = s_x[i0], b = s_x[i1];
-            const float2 t = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
+    const size_t per_warp = (size_t)n_fft + (size_t)(n_fft / 16) + (size_t)((2 * nb + 1) / 2);   // in float2 units
+    float2 *s_x = s_all + tab_f2 + (size_t)warp * per_warp;
+    float *pw = reinterpret_cast<float *>(s_x + n_fft + n_fft / 16);                          // pw[which * nb + k]
+    auto P = [](int i) { return i + (i >> 4); };      // padded index: the strided passes and the bit-reversed scatter hit distinct banks
+    auto cmul = [](float2 b, float2 w) { return make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x); };
+    for (int64_t fa = ((int64_t)blockIdx.x * wpc + warp) * 2; fa < total_frames; fa += (int64_t)gridDim.x * wpc * 2) {
+    const bool two = fa + 1 < total_frames;
+    int uu[2]; int64_t s0[2], len[2], start[2];
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+        const int64_t f = (w == 0 || two) ? fa + w : fa;
+        uu[w] = utt_of_frame[f];
+        s0[w] = sample_off[uu[w]]; len[w] = sample_off[uu[w] + 1] - s0[w];
+        start[w] = (f - frame_off[uu[w]]) * hop - (center ? n_fft / 2 : 0);
+    }
+    for (int i = lane; i < n_fft; i += 32) {
+        const float wv = window[i];
+        float v[2] = {0.0f, 0.0f};
+        if (wv != 0.0f) {
+#pragma unroll
+            for (int w = 0; w < 2; w++) {
+                const int64_t s = start[w] + i;
+                if ((w == 0 || two) && s >= 0 && s < len[w]) {
+                    float x = audio[s0[w] + s];
+                    if (preemph != 0.0f && s > 0) x -= preemph * audio[s0[w] + s - 1];
+                    v[w] = x * wv;
+                }
+            }
+        }
+        const int r = __brev((unsigned)i) >> (32 - log2n);
+        s_x[r + (r >> 4)] = make_float2(v[0], v[1]);
+    }
+    __syncwarp();
+    int st = 1;
+    for (; st + 1 <= log2n; st += 2) {          // stages st and st + 1 on the 4 elements p, p+h, p+2h, p+3h of a block of 4h
+        const int h = 1 << (st - 1);
+        for (int k = lane; k < n_fft / 4; k += 32) {
+            const int pos = k & (h - 1);
+            const int i0 = ((k - pos) << 2) + pos;
+            const float2 w1 = twiddle[pos * (n_fft >> st)];
+            const float2 w2 = twiddle[pos * (n_fft >> (st + 1))], w3 = twiddle[(pos + h) * (n_fft >> (st + 1))];
+            const int j0 = P(i0), j1 = P(i0 + h), j2 = P(i0 + 2 * h), j3 = P(i0 + 3 * h);
+            const float2 a0 = s_x[j0], a1 = s_x[j1], a2 = s_x[j2], a3 = s_x[j3];
+            float2 t = cmul(a1, w1);
+            const float2 b0 = make_float2(a0.x + t.x, a0.y + t.y), b1 = make_float2(a0.x - t.x, a0.y - t.y);
+            t = cmul(a3, w1);
+            const float2 b2 = make_float2(a2.x + t.x, a2.y + t.y), b3 = make_float2(a2.x - t.x, a2.y - t.y);
+            t = cmul(b2, w2);
+            s_x[j0] = make_float2(b0.x + t.x, b0.y + t.y);
+            s_x[j2] = make_float2(b0.x - t.x, b0.y - t.y);
+            t = cmul(b3, w3);
+            s_x[j1] = make_float2(b1.x + t.x, b1.y + t.y);
+            s_x[j3] = make_float2(b1.x - t.x, b1.y - t.y);
+        }
+        __syncwarp();
+    }
+    if (st <= log2n) {                           // odd number of stages: one plain radix-2 stage is left
+        const int half = 1 << (st - 1), tws = n_fft >> st;
+        for (int k = lane; k < n_fft / 2; k += 32) {
+            const int pos = k & (half - 1);
+            const int i0 = P(((k - pos) << 1) + pos), i1 = P(((k - pos) << 1) + pos + half);
+            const float2 t = cmul(s_x[i1], twiddle[pos * tws]);
+            const float2 a = s_x[i0];
             s_x[i0] = make_float2(a.x + t.x, a.y + t.y);
             s_x[i1] = make_float2(a.x - t.x, a.y - t.y);
         }
-        __syncthreads();
+        __syncwarp();
     }
-    float *pw = reinterpret_cast<float *>(s_x);   // power spectrum overlays the first half of the buffer
-    const int nb = n_fft / 2 + 1;
-    // pw[k] aliases s_x[k/2]: thread k writes float index k after reading complex index k >= k/2, so go
-    // through registers and a barrier
-    float pv[16];
-    int cnt = 0;
-    for (int k = threadIdx.x; k < nb; k += blockDim.x) { const float2 c = s_x[k]; pv[cnt++] = c.x * c.x + c.y * c.y; }
-    __syncthreads();
-    cnt = 0;
-    for (int k = threadIdx.x; k < nb; k += blockDim.x) pw[k] = pv[cnt++];
-    __syncthreads();
-    for (int mth = threadIdx.x; mth < n_mels; mth += blockDim.x) {
+    // split the two real spectra: A[k] = (Z[k] + conj(Z[N-k])) / 2, B[k] = (Z[k] - conj(Z[N-k])) / (2i)
+    for (int k = lane; k < nb; k += 32) {
+        const float2 z = s_x[P(k)], zn = s_x[P((n_fft - k) & (n_fft - 1))];
+        const float ar = 0.5f * (z.x + zn.x), ai = 0.5f * (z.y - zn.y);
+        const float br = 0.5f * (z.y + zn.y), bi = 0.5f * (zn.x - z.x);
+        pw[k] = ar * ar + ai * ai;
+        pw[nb + k] = br * br + bi * bi;
+    }
+    __syncwarp();
+    for (int e = lane; e < 2 * n_mels; e += 32) {
+        const int w = e / n_mels, mth = e - w * n_mels;
+        if (w == 1 && !two) break;
         float acc = 0.0f;
-        const float *w = mel_w + mel_ptr[mth];
-        for (int k = mel_lo[mth]; k < mel_hi[mth]; k++) acc += w[k - mel_lo[mth]] * pw[k];
+        const int lo = mel_lo[mth];
+        const float *wt = mel_w + mel_ptr[mth];
+        const float *pp = pw + w * nb;
+        for (int k = lo; k < mel_hi[mth]; k++) acc += wt[k - lo] * pp[k];
         acc = fmaxf(acc, 1e-10f);
         const float lv = log_db ? 10.0f * log10f(acc) : logf(acc);
-        logmel[f * n_mels + mth] = lv;
-        atomicMax(umax + u, float_to_ordered(lv));
+        logmel[(fa + w) * n_mels + mth] = lv;
+        if (log_db) atomicMax(umax + uu[w], float_to_ordered(lv));       // only the top_db clamp reads it
+    }
+    __syncwarp();                                 // the next pair reuses this warp's buffers
     }
 }
 
@@ -176,9 +247,7 @@ extern "C" int sapr_mfcc(sapr_ctx *ctx, const sapr_mfcc_params *p, const float *
     const int64_t total_frames = foff[B];
     memcpy(feat_offsets_host, foff.data(), sizeof(int64_t) * (B + 1));
     if (total_frames <= 0) return SAPR_OK;
-    std::vector<int32_t> uof(total_frames);
-    for (int u = 0; u < B; u++) for (int64_t f = foff[u]; f < foff[u + 1]; f++) uof[f] = u;
-    // ---- device tables: one workspace blob ----
+    // ---- device tables: one workspace blob (parameter tables, per-call offsets, frame -> utterance, log-mel) ----
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     size_t o_win = 0, o_tw = o_win + al(sizeof(float) * n_fft), o_lo = o_tw + al(sizeof(float2) * (n_fft / 2));
     size_t o_hi = o_lo + al(sizeof(int32_t) * n_mels), o_ptr = o_hi + al(sizeof(int32_t) * n_mels);
@@ -189,26 +258,34 @@ extern "C" int sapr_mfcc(sapr_ctx *ctx, const sapr_mfcc_params *p, const float *
     int rc = sapr_ws_reserve(ctx, 7, total);
     if (rc) return rc;
     char *base = (char *)ctx->ws[7];
+    // pageable sources: cudaMemcpyAsync returns once they are staged, so the vectors may go out of scope afterwards
 #define UP(off, vec, T) SAPR_CUDA(ctx, cudaMemcpyAsync(base + off, vec.data(), sizeof(T) * vec.size(), cudaMemcpyHostToDevice, ctx->stream))
     UP(o_win, window, float); UP(o_tw, tw, float2); UP(o_lo, lo, int32_t); UP(o_hi, hi, int32_t); UP(o_ptr, ptr, int32_t);
-    UP(o_w, w, float); UP(o_dct, dct, float); UP(o_foff, foff, int64_t); UP(o_uof, uof, int32_t);
+    UP(o_w, w, float); UP(o_dct, dct, float); UP(o_foff, foff, int64_t);
 #undef UP
     SAPR_CUDA(ctx, cudaMemcpyAsync(base + o_soff, sample_offsets_host, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, ctx->stream));
-    SAPR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the std::vectors above go out of scope
     int *umax = (int *)(base + o_umax);
     float *logmel = (float *)(base + o_lm);
+    int32_t *uof = (int32_t *)(base + o_uof);
     k_mfcc_init_max<<<(B + 127) / 128, 128, 0, ctx->stream>>>(umax, B);
     SAPR_LAUNCH_CHECK(ctx);
-    const int threads = std::min(256, n_fft / 2);
-    if ((nb + threads - 1) / threads > 16) SAPR_FAIL(ctx, SAPR_E_RANGE, "mfcc: n_fft too large for the register staging");
-    k_mfcc_logmel<<<(unsigned)total_frames, threads, sizeof(float2) * n_fft, ctx->stream>>>(
-        audio, (const int64_t *)(base + o_soff), (const int64_t *)(base + o_foff), (const int32_t *)(base + o_uof), n_fft,
+    k_mfcc_utt_of_frame<<<(unsigned)((total_frames + 255) / 256), 256, 0, ctx->stream>>>((const int64_t *)(base + o_foff), B, total_frames, uof);
+    SAPR_LAUNCH_CHECK(ctx);
+    int wpc = 8;                                           // frame pairs (warps) per CTA: as many as 96 KB of shared memory hold
+    const size_t per_warp = sizeof(float2) * ((size_t)n_fft + n_fft / 16 + (2 * nb + 1) / 2);
+    const size_t tab = sizeof(float2) * (((size_t)n_fft + n_fft + w.size() + 3 * n_mels + 1) / 2 + 1);
+    while (wpc > 1 && tab + per_warp * wpc > 100 * 1024) wpc >>= 1;
+    const size_t smem = tab + per_warp * wpc;
+    SAPR_CUDA(ctx, cudaFuncSetAttribute(k_mfcc_logmel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int cta_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (32 * wpc), (220 * 1024) / (smem + 1024)));   // resident CTAs: one wave
+    k_mfcc_logmel<<<(unsigned)std::min<int64_t>((total_frames + 2 * wpc - 1) / (2 * wpc), (int64_t)ctx->sm_count * cta_per_sm), 32 * wpc, smem, ctx->stream>>>(
+        audio, (const int64_t *)(base + o_soff), (const int64_t *)(base + o_foff), uof, total_frames, n_fft,
         log2n, p->hop_length, p->center, p->preemph, (const float *)(base + o_win), (const float2 *)(base + o_tw), n_mels,
         (const int32_t *)(base + o_lo), (const int32_t *)(base + o_hi), (const int32_t *)(base + o_ptr),
-        (const float *)(base + o_w), p->log_db, logmel, umax);
+        (const float *)(base + o_w), (int)w.size(), p->log_db, logmel, umax);
     SAPR_LAUNCH_CHECK(ctx);
     const int64_t n = total_frames * n_mfcc;
-    k_mfcc_dct<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(logmel, (const int32_t *)(base + o_uof), umax, n_mels,
+    k_mfcc_dct<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(logmel, uof, umax, n_mels,
                                                                     n_mfcc, p->log_db ? p->top_db : 0.0f,
                                                                     (const float *)(base + o_dct), feats, ld_out,
                                                                     total_frames);
