@@ -16,6 +16,7 @@ One "step" = one pass of the fused Viterbi path (sapr_viterbi through the C ABI)
   estep   : secondary headline (configs[2] shape): Baum-Welch E-step + statistics (+ all-reduce + M-step)
   ergodic : configs[3] shape: N=256 fully connected states, D=39, T=1000, forward score with the emission and the
             transition contraction on the tensor cores (sapr_ergodic_score)
+  cfg1    : configs[0]: the reference's own size (330 utterances, D=13), drop-in classes and the batched engine, wall time
   audio   : configs[4] shape: 16 kHz synthetic audio -> fused MFCC kernel -> Viterbi recognition on the device
 
 `--impl reference` times the reference's algorithm on the host cores instead (oracle port, all threads).
@@ -161,6 +162,7 @@ def main():
                     help="utterances per GPU for the cfg 4 leg (N=256 dense states, T=1000; 0 = skip)")
     ap.add_argument("--audio-utts", type=int, default=8192,
                     help="utterances per GPU for the cfg 5 leg (2 s of 16 kHz audio each -> MFCC kernel -> Viterbi; 0 = skip)")
+    ap.add_argument("--no-cfg1", action="store_true", help="skip the reference-scale leg (330 utterances, D=13)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -470,6 +472,67 @@ def main():
         del audio, feats
         torch.cuda.empty_cache()
 
+
+    # ---- fifth leg (BASELINE configs[0], the reference's own CPU-runnable case): 11 words x 30 utterances, T ~ U{80..120}, D = 13,
+    # flat start, 15 Baum-Welch iterations per word, then Viterbi of all 330 x 11 -- latency-bound, reported as wall time ----
+    cfg1 = None
+    if rank == 0 and not args.no_cfg1 and prec == engine.FP32:
+        import contextlib, io
+        from sapr_b200.custom_hmm import HMM
+        feats1, lab1, _, _ = synth.make_corpus(330, M_WORDS, N_STATES, 13, 80, 120, seed=20241118 + 1)
+        frames1 = int(sum(f.shape[1] for f in feats1))
+        per_word = [[f for f, w in zip(feats1, lab1) if w == m] for m in range(M_WORDS)]
+
+        def run_cfg1(semantics):
+            t0 = time.perf_counter()
+            hm = []
+            with contextlib.redirect_stdout(io.StringIO()):
+                for m in range(M_WORDS):
+                    h = HMM(N_STATES, 13, feats1, model_name=f"w{m}", semantics=semantics)     # train.py:111-112
+                    h.baum_welch(per_word[m], 15)
+                    hm.append(h)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                for f in feats1[:33]:
+                    for h in hm:
+                        h.decode(f)                                                        # decoder.py:42-47, per-sequence loop
+            torch.cuda.synchronize()
+            return t1 - t0, (time.perf_counter() - t1) * 10.0
+
+        run_cfg1("standard")                                                              # warm-up (workspaces, module load)
+        tr_std, de_std = run_cfg1("standard")
+        tr_sapr, de_sapr = run_cfg1("sapr")
+        # whole vocabulary at once: one batched E-step per iteration (engine.train_words), one fused Viterbi launch
+        b1 = engine.PackedBatch.from_features(feats1, labels=lab1)
+        lab1_t = torch.as_tensor(np.asarray(lab1, dtype=np.int32), device=dev)
+        gmean, gvar, gA, floor1 = engine.init_flat_start(b1, N_STATES)
+        def run_batched():
+            wm = engine.WordModels(M_WORDS, N_STATES, 13, ctx=ctx)
+            S1 = N_STATES + 2
+            mm = np.zeros((M_WORDS, S1, 13)); vv = np.ones((M_WORDS, S1, 13))
+            mm[:, 1:-1] = gmean; vv[:, 1:-1] = gvar
+            wm.set(mm, vv, np.broadcast_to(gA, (M_WORDS, S1, S1)).copy())
+            t0 = time.perf_counter()
+            engine.train_words(wm, b1, lab1_t, 15, floor1, prec, tol=0.0)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            wm.viterbi(b1, None, prec, 0, want_scores=False, want_path=True)
+            torch.cuda.synchronize()
+            return t1 - t0, time.perf_counter() - t1
+        run_batched()
+        tr_b, de_b = run_batched()
+        est_upd = 15 * frames1 * N_STATES                                                 # E-step updates of one full training run
+        cfg1 = {"workload": f"cfg1: 330 utterances (30 per word), T ~ U{{80..120}} ({frames1} frames), D = 13, N = 8, 15 Baum-Welch "
+                            "iterations per word from a flat start, Viterbi of 330 x 11",
+                "drop_in_standard": {"train_s": tr_std, "decode_330x11_s": de_std, "train_updates_per_s": est_upd / tr_std},
+                "drop_in_as_written": {"train_s": tr_sapr, "decode_330x11_s": de_sapr, "train_updates_per_s": est_upd / tr_sapr,
+                                       "note": "custom_hmm.py as written (Gram-matrix emission, full covariances, float64 compat kernels)"},
+                "batched_whole_vocabulary": {"train_s": tr_b, "decode_330x11_s": de_b, "train_updates_per_s": est_upd / tr_b},
+                "reference_python": "BASELINE.md section 2: ~3.5e4 updates/s for baum_welch, ~1 ms per (utterance, model) decode on 8 vCPUs",
+                "note": "latency-bound at this size (one kernel launch set per word and iteration); decode timed on 33 utterances x 11 "
+                        "models and scaled to 330"}
+
     # ---- CPU baseline (rank 0, N = 1 only): oracle port on a bounded sample of the same tensors ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -496,7 +559,7 @@ def main():
                            "emission": "diagonal Gaussian", "sharding": f"utterances x{world}, no collective",
                            "l2": "inputs (3.2 GB/GPU) larger than L2; no flush needed"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "estep": estep, "ergodic": ergodic, "audio": audio_leg}
+                "clocks": clocks, "estep": estep, "ergodic": ergodic, "audio": audio_leg, "cfg1": cfg1}
         print(json.dumps(line), flush=True)
     dist.shutdown()
 

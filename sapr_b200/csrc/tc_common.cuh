@@ -35,6 +35,7 @@ __device__ __forceinline__ void mbar_arrive_tx(uint32_t bar, uint32_t bytes) {
 // bounded wait: a protocol bug traps (error to the host) instead of hanging the GPU.  try_wait suspends the
 // thread in hardware up to the time hint, so a waiting warp costs almost no issue slots.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef SAPR_WAIT_HINT
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
         "mov.u32 n, 0;\n\t"
@@ -53,6 +54,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra LAB_WAIT;\n\t"
         "DONE:\n\t}"
         ::"r"(bar), "r"(parity), "r"(2000u) : "memory");
+#else
+    // no suspend-time hint: a failed try is TRYWAIT + branch (2 SASS instructions); with the hint the compiler adds a
+    // NANOSLEEP.SYNCS and a re-check per try, and every barrier event in the CTA wakes the sleeper (measured: 23 % of the
+    // Viterbi kernel's issued instructions were such polls)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.gt.u32 p, n, 16000000;\n\t"
+        "@p trap;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ bool elect_one() {
     uint32_t e;
