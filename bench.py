@@ -400,138 +400,143 @@ def main():
     # ---- fourth leg (BASELINE configs[4]): 16 kHz audio -> fused MFCC kernel -> Viterbi recognition, all on the device ----
     audio_leg = None
     if args.audio_utts > 0 and prec == engine.FP32:
-        import ctypes as C
-        from sapr_b200 import mfcc_extract as mx
-        Ba, sr, ns = args.audio_utts, 16000, 32000
-        gen = torch.Generator(device=dev); gen.manual_seed(SEED + 5 + 131 * rank)
-        tt = torch.arange(ns, device=dev, dtype=torch.float32) / sr
-        audio = torch.empty(Ba * ns, dtype=torch.float32, device=dev)
-        for a in range(0, Ba, 1024):                  # three formant-like sinusoids + noise per utterance
-            n = min(1024, Ba - a)
-            fr = 200.0 + 2800.0 * torch.rand(n, 3, device=dev, generator=gen)
-            ph = 6.0 * torch.rand(n, 3, device=dev, generator=gen)
-            y = 0.05 * torch.randn(n, ns, device=dev, generator=gen)
-            for k, amp in enumerate((0.5, 0.3, 0.2)):
-                y += amp * torch.sin(2 * np.pi * fr[:, k:k + 1] * tt[None, :] + ph[:, k:k + 1])
-            audio[a * ns:(a + n) * ns] = y.reshape(-1)
-            del y
-        pa = mx.cfg5_params()
-        so = np.arange(Ba + 1, dtype=np.int64) * ns
-        nfr = int(ctx.lib.sapr_mfcc_num_frames(C.byref(pa), ns))
-        feats = torch.zeros(Ba * nfr, 16, dtype=torch.float32, device=dev)
-        fo = np.zeros(Ba + 1, dtype=np.int64)
+        try:
+            import ctypes as C
+            from sapr_b200 import mfcc_extract as mx
+            Ba, sr, ns = args.audio_utts, 16000, 32000
+            gen = torch.Generator(device=dev); gen.manual_seed(SEED + 5 + 131 * rank)
+            tt = torch.arange(ns, device=dev, dtype=torch.float32) / sr
+            audio = torch.empty(Ba * ns, dtype=torch.float32, device=dev)
+            for a in range(0, Ba, 1024):                  # three formant-like sinusoids + noise per utterance
+                n = min(1024, Ba - a)
+                fr = 200.0 + 2800.0 * torch.rand(n, 3, device=dev, generator=gen)
+                ph = 6.0 * torch.rand(n, 3, device=dev, generator=gen)
+                y = 0.05 * torch.randn(n, ns, device=dev, generator=gen)
+                for k, amp in enumerate((0.5, 0.3, 0.2)):
+                    y += amp * torch.sin(2 * np.pi * fr[:, k:k + 1] * tt[None, :] + ph[:, k:k + 1])
+                audio[a * ns:(a + n) * ns] = y.reshape(-1)
+                del y
+            pa = mx.cfg5_params()
+            so = np.arange(Ba + 1, dtype=np.int64) * ns
+            nfr = int(ctx.lib.sapr_mfcc_num_frames(C.byref(pa), ns))
+            feats = torch.zeros(Ba * nfr, 16, dtype=torch.float32, device=dev)
+            fo = np.zeros(Ba + 1, dtype=np.int64)
 
-        def mfcc_call():
-            ctx.check(ctx.lib.sapr_mfcc(ctx.h, C.byref(pa), _lib.ptr(audio), _lib.ptr(so), Ba, _lib.ptr(feats), 16, _lib.ptr(fo)))
+            def mfcc_call():
+                ctx.check(ctx.lib.sapr_mfcc(ctx.h, C.byref(pa), _lib.ptr(audio), _lib.ptr(so), Ba, _lib.ptr(feats), 16, _lib.ptr(fo)))
 
-        mfcc_call()
-        torch.cuda.synchronize()
-        Fm = feats[:, :13]
-        mu_a, sd_a = Fm.mean(0).cpu().numpy().astype(np.float64), Fm.std(0).cpu().numpy().astype(np.float64) + 1e-3
-        rnga = np.random.default_rng(SEED + 6)
-        a_means = np.zeros((M_WORDS, N_STATES + 2, 13)); a_var = np.ones((M_WORDS, N_STATES + 2, 13))
-        a_means[:, 1:-1] = mu_a + sd_a * rnga.standard_normal((M_WORDS, N_STATES, 13))
-        a_var[:, 1:-1] = (sd_a * rnga.uniform(0.7, 1.3, (M_WORDS, N_STATES, 13))) ** 2
-        a_A = synth.truth_models(np.zeros((M_WORDS, N_STATES, 13)), np.ones((M_WORDS, N_STATES, 13)), 0.9)[0]
-        am = engine.WordModels(M_WORDS, N_STATES, 13, ctx=ctx)
-        am.set(a_means, a_var, a_A)
-        ab = engine.PackedBatch(feats, torch.as_tensor(fo, device=dev), 13, fo)
-
-        def audio_iter():
             mfcc_call()
-            return am.viterbi(ab, None, prec, 0, want_scores=False, want_path=True)
+            torch.cuda.synchronize()
+            Fm = feats[:, :13]
+            mu_a, sd_a = Fm.mean(0).cpu().numpy().astype(np.float64), Fm.std(0).cpu().numpy().astype(np.float64) + 1e-3
+            rnga = np.random.default_rng(SEED + 6)
+            a_means = np.zeros((M_WORDS, N_STATES + 2, 13)); a_var = np.ones((M_WORDS, N_STATES + 2, 13))
+            a_means[:, 1:-1] = mu_a + sd_a * rnga.standard_normal((M_WORDS, N_STATES, 13))
+            a_var[:, 1:-1] = (sd_a * rnga.uniform(0.7, 1.3, (M_WORDS, N_STATES, 13))) ** 2
+            a_A = synth.truth_models(np.zeros((M_WORDS, N_STATES, 13)), np.ones((M_WORDS, N_STATES, 13)), 0.9)[0]
+            am = engine.WordModels(M_WORDS, N_STATES, 13, ctx=ctx)
+            am.set(a_means, a_var, a_A)
+            ab = engine.PackedBatch(feats, torch.as_tensor(fo, device=dev), 13, fo)
 
-        for _ in range(3):
-            audio_iter()
-        dist.barrier()
-        torch.cuda.synchronize()
-        n_it = 5
-        a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        m_ms = 0.0
-        a0.record()
-        for _ in range(n_it):
-            audio_iter()
-        a1.record()
-        for _ in range(n_it):
-            mfcc_call()
-        a2.record()
-        torch.cuda.synchronize()
-        tot = torch.tensor([a0.elapsed_time(a1) / n_it], dtype=torch.float64, device=dev)
-        dist.max_(tot)
-        t_ms, m_ms = float(tot.item()), a1.elapsed_time(a2) / n_it
-        mf_bytes = (160 * 4 + 13 * 4) * Ba * nfr          # 692 B per frame
-        audio_leg = {"metric": "audio -> MFCC -> Viterbi recognition, frames/s and frame*state updates/s",
-                     "workload": f"cfg5: {Ba} utterances/GPU x 2 s of 16 kHz audio ({nfr} frames each), 25 ms / 10 ms Hamming, 512-pt FFT, "
-                                 "26 mel, DCT-13, pre-emphasis 0.97 -> 11 word models x 8 states",
-                     "frames_per_s": world * Ba * nfr / (t_ms / 1e3), "value": world * Ba * nfr * N_STATES * M_WORDS / (t_ms / 1e3),
-                     "unit": "updates/s", "ms_per_call": t_ms, "mfcc_ms": m_ms, "viterbi_ms": t_ms - m_ms,
-                     "roofline": {"bound": "hbm", "kernel": "k_mfcc_logmel + k_mfcc_dct", "achieved": mf_bytes / (m_ms / 1e3) / 1e9,
-                                  "peak": peak, "unit": "GB/s", "frac": mf_bytes / (m_ms / 1e3) / 1e9 / peak,
-                                  "note": "algorithmic bytes = 160 new samples + 13 coefficients per frame (692 B); the kernel is "
-                                          "bound by the in-shared-memory FFT arithmetic, not by HBM"}}
-        del audio, feats
-        torch.cuda.empty_cache()
+            def audio_iter():
+                mfcc_call()
+                return am.viterbi(ab, None, prec, 0, want_scores=False, want_path=True)
 
+            for _ in range(3):
+                audio_iter()
+            dist.barrier()
+            torch.cuda.synchronize()
+            n_it = 5
+            a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            m_ms = 0.0
+            a0.record()
+            for _ in range(n_it):
+                audio_iter()
+            a1.record()
+            for _ in range(n_it):
+                mfcc_call()
+            a2.record()
+            torch.cuda.synchronize()
+            tot = torch.tensor([a0.elapsed_time(a1) / n_it], dtype=torch.float64, device=dev)
+            dist.max_(tot)
+            t_ms, m_ms = float(tot.item()), a1.elapsed_time(a2) / n_it
+            mf_bytes = (160 * 4 + 13 * 4) * Ba * nfr          # 692 B per frame
+            audio_leg = {"metric": "audio -> MFCC -> Viterbi recognition, frames/s and frame*state updates/s",
+                         "workload": f"cfg5: {Ba} utterances/GPU x 2 s of 16 kHz audio ({nfr} frames each), 25 ms / 10 ms Hamming, 512-pt FFT, "
+                                     "26 mel, DCT-13, pre-emphasis 0.97 -> 11 word models x 8 states",
+                         "frames_per_s": world * Ba * nfr / (t_ms / 1e3), "value": world * Ba * nfr * N_STATES * M_WORDS / (t_ms / 1e3),
+                         "unit": "updates/s", "ms_per_call": t_ms, "mfcc_ms": m_ms, "viterbi_ms": t_ms - m_ms,
+                         "roofline": {"bound": "hbm", "kernel": "k_mfcc_logmel + k_mfcc_dct", "achieved": mf_bytes / (m_ms / 1e3) / 1e9,
+                                      "peak": peak, "unit": "GB/s", "frac": mf_bytes / (m_ms / 1e3) / 1e9 / peak,
+                                      "note": "algorithmic bytes = 160 new samples + 13 coefficients per frame (692 B); the kernel is "
+                                              "bound by the in-shared-memory FFT arithmetic, not by HBM"}}
+            del audio, feats
+            torch.cuda.empty_cache()
+        except Exception as ex:          # a secondary leg must not take the headline line down
+            audio_leg = {"error": repr(ex)}
 
     # ---- fifth leg (BASELINE configs[0], the reference's own CPU-runnable case): 11 words x 30 utterances, T ~ U{80..120}, D = 13,
     # flat start, 15 Baum-Welch iterations per word, then Viterbi of all 330 x 11 -- latency-bound, reported as wall time ----
     cfg1 = None
     if rank == 0 and not args.no_cfg1 and prec == engine.FP32:
-        import contextlib, io
-        from sapr_b200.custom_hmm import HMM
-        feats1, lab1, _, _ = synth.make_corpus(330, M_WORDS, N_STATES, 13, 80, 120, seed=20241118 + 1)
-        frames1 = int(sum(f.shape[1] for f in feats1))
-        per_word = [[f for f, w in zip(feats1, lab1) if w == m] for m in range(M_WORDS)]
+        try:
+            import contextlib, io
+            from sapr_b200.custom_hmm import HMM
+            feats1, lab1, _, _ = synth.make_corpus(330, M_WORDS, N_STATES, 13, 80, 120, seed=20241118 + 1)
+            frames1 = int(sum(f.shape[1] for f in feats1))
+            per_word = [[f for f, w in zip(feats1, lab1) if w == m] for m in range(M_WORDS)]
 
-        def run_cfg1(semantics):
-            t0 = time.perf_counter()
-            hm = []
-            with contextlib.redirect_stdout(io.StringIO()):
-                for m in range(M_WORDS):
-                    h = HMM(N_STATES, 13, feats1, model_name=f"w{m}", semantics=semantics)     # train.py:111-112
-                    h.baum_welch(per_word[m], 15)
-                    hm.append(h)
-            torch.cuda.synchronize()
-            t1 = time.perf_counter()
-            with contextlib.redirect_stdout(io.StringIO()):
-                for f in feats1[:33]:
-                    for h in hm:
-                        h.decode(f)                                                        # decoder.py:42-47, per-sequence loop
-            torch.cuda.synchronize()
-            return t1 - t0, (time.perf_counter() - t1) * 10.0
+            def run_cfg1(semantics):
+                t0 = time.perf_counter()
+                hm = []
+                with contextlib.redirect_stdout(io.StringIO()):
+                    for m in range(M_WORDS):
+                        h = HMM(N_STATES, 13, feats1, model_name=f"w{m}", semantics=semantics)     # train.py:111-112
+                        h.baum_welch(per_word[m], 15)
+                        hm.append(h)
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    for f in feats1[:33]:
+                        for h in hm:
+                            h.decode(f)                                                        # decoder.py:42-47, per-sequence loop
+                torch.cuda.synchronize()
+                return t1 - t0, (time.perf_counter() - t1) * 10.0
 
-        run_cfg1("standard")                                                              # warm-up (workspaces, module load)
-        tr_std, de_std = run_cfg1("standard")
-        tr_sapr, de_sapr = run_cfg1("sapr")
-        # whole vocabulary at once: one batched E-step per iteration (engine.train_words), one fused Viterbi launch
-        b1 = engine.PackedBatch.from_features(feats1, labels=lab1)
-        lab1_t = torch.as_tensor(np.asarray(lab1, dtype=np.int32), device=dev)
-        gmean, gvar, gA, floor1 = engine.init_flat_start(b1, N_STATES)
-        def run_batched():
-            wm = engine.WordModels(M_WORDS, N_STATES, 13, ctx=ctx)
-            S1 = N_STATES + 2
-            mm = np.zeros((M_WORDS, S1, 13)); vv = np.ones((M_WORDS, S1, 13))
-            mm[:, 1:-1] = gmean; vv[:, 1:-1] = gvar
-            wm.set(mm, vv, np.broadcast_to(gA, (M_WORDS, S1, S1)).copy())
-            t0 = time.perf_counter()
-            engine.train_words(wm, b1, lab1_t, 15, floor1, prec, tol=0.0)
-            torch.cuda.synchronize()
-            t1 = time.perf_counter()
-            wm.viterbi(b1, None, prec, 0, want_scores=False, want_path=True)
-            torch.cuda.synchronize()
-            return t1 - t0, time.perf_counter() - t1
-        run_batched()
-        tr_b, de_b = run_batched()
-        est_upd = 15 * frames1 * N_STATES                                                 # E-step updates of one full training run
-        cfg1 = {"workload": f"cfg1: 330 utterances (30 per word), T ~ U{{80..120}} ({frames1} frames), D = 13, N = 8, 15 Baum-Welch "
-                            "iterations per word from a flat start, Viterbi of 330 x 11",
-                "drop_in_standard": {"train_s": tr_std, "decode_330x11_s": de_std, "train_updates_per_s": est_upd / tr_std},
-                "drop_in_as_written": {"train_s": tr_sapr, "decode_330x11_s": de_sapr, "train_updates_per_s": est_upd / tr_sapr,
-                                       "note": "custom_hmm.py as written (Gram-matrix emission, full covariances, float64 compat kernels)"},
-                "batched_whole_vocabulary": {"train_s": tr_b, "decode_330x11_s": de_b, "train_updates_per_s": est_upd / tr_b},
-                "reference_python": "BASELINE.md section 2: ~3.5e4 updates/s for baum_welch, ~1 ms per (utterance, model) decode on 8 vCPUs",
-                "note": "latency-bound at this size (one kernel launch set per word and iteration); decode timed on 33 utterances x 11 "
-                        "models and scaled to 330"}
+            run_cfg1("standard")                                                              # warm-up (workspaces, module load)
+            tr_std, de_std = run_cfg1("standard")
+            tr_sapr, de_sapr = run_cfg1("sapr")
+            # whole vocabulary at once: one batched E-step per iteration (engine.train_words), one fused Viterbi launch
+            b1 = engine.PackedBatch.from_features(feats1, labels=lab1)
+            lab1_t = torch.as_tensor(np.asarray(lab1, dtype=np.int32), device=dev)
+            gmean, gvar, gA, floor1 = engine.init_flat_start(b1, N_STATES)
+            def run_batched():
+                wm = engine.WordModels(M_WORDS, N_STATES, 13, ctx=ctx)
+                S1 = N_STATES + 2
+                mm = np.zeros((M_WORDS, S1, 13)); vv = np.ones((M_WORDS, S1, 13))
+                mm[:, 1:-1] = gmean; vv[:, 1:-1] = gvar
+                wm.set(mm, vv, np.broadcast_to(gA, (M_WORDS, S1, S1)).copy())
+                t0 = time.perf_counter()
+                engine.train_words(wm, b1, lab1_t, 15, floor1, prec, tol=0.0)
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                wm.viterbi(b1, None, prec, 0, want_scores=False, want_path=True)
+                torch.cuda.synchronize()
+                return t1 - t0, time.perf_counter() - t1
+            run_batched()
+            tr_b, de_b = run_batched()
+            est_upd = 15 * frames1 * N_STATES                                                 # E-step updates of one full training run
+            cfg1 = {"workload": f"cfg1: 330 utterances (30 per word), T ~ U{{80..120}} ({frames1} frames), D = 13, N = 8, 15 Baum-Welch "
+                                "iterations per word from a flat start, Viterbi of 330 x 11",
+                    "drop_in_standard": {"train_s": tr_std, "decode_330x11_s": de_std, "train_updates_per_s": est_upd / tr_std},
+                    "drop_in_as_written": {"train_s": tr_sapr, "decode_330x11_s": de_sapr, "train_updates_per_s": est_upd / tr_sapr,
+                                           "note": "custom_hmm.py as written (Gram-matrix emission, full covariances, float64 compat kernels)"},
+                    "batched_whole_vocabulary": {"train_s": tr_b, "decode_330x11_s": de_b, "train_updates_per_s": est_upd / tr_b},
+                    "reference_python": "BASELINE.md section 2: ~3.5e4 updates/s for baum_welch, ~1 ms per (utterance, model) decode on 8 vCPUs",
+                    "note": "latency-bound at this size (one kernel launch set per word and iteration); decode timed on 33 utterances x 11 "
+                            "models and scaled to 330"}
+        except Exception as ex:
+            cfg1 = {"error": repr(ex)}
 
     # ---- CPU baseline (rank 0, N = 1 only): oracle port on a bounded sample of the same tensors ----
     cpu = None

@@ -78,27 +78,31 @@ k_mfcc_logmel(const float *__restrict__ audio, const int64_t *__restrict__ sampl
     auto cmul = [](float2 b, float2 w) { return make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x); };
     for (int64_t fa = ((int64_t)blockIdx.x * wpc + warp) * 2; fa < total_frames; fa += (int64_t)gridDim.x * wpc * 2) {
     const bool two = fa + 1 < total_frames;
-    int uu[2]; int64_t s0[2], len[2], start[2];
+    int uu[2], len[2], start[2];
+    const float *ap[2];                              // utterance base pointers; sample indices inside an utterance fit 32 bits
 #pragma unroll
     for (int w = 0; w < 2; w++) {
         const int64_t f = (w == 0 || two) ? fa + w : fa;
         uu[w] = utt_of_frame[f];
-        s0[w] = sample_off[uu[w]]; len[w] = sample_off[uu[w] + 1] - s0[w];
-        start[w] = (f - frame_off[uu[w]]) * hop - (center ? n_fft / 2 : 0);
+        const int64_t s0 = sample_off[uu[w]];
+        ap[w] = audio + s0;
+        len[w] = (w == 0 || two) ? (int)(sample_off[uu[w] + 1] - s0) : 0;
+        start[w] = (int)(f - frame_off[uu[w]]) * hop - (center ? n_fft / 2 : 0);
     }
+    // branch-free loads (clamped index, masked value), four iterations in flight
+#pragma unroll 4
     for (int i = lane; i < n_fft; i += 32) {
         const float wv = window[i];
-        float v[2] = {0.0f, 0.0f};
-        if (wv != 0.0f) {
+        float v[2];
 #pragma unroll
-            for (int w = 0; w < 2; w++) {
-                const int64_t s = start[w] + i;
-                if ((w == 0 || two) && s >= 0 && s < len[w]) {
-                    float x = audio[s0[w] + s];
-                    if (preemph != 0.0f && s > 0) x -= preemph * audio[s0[w] + s - 1];
-                    v[w] = x * wv;
-                }
-            }
+        for (int w = 0; w < 2; w++) {
+            const int sidx = start[w] + i;
+            const bool in = sidx >= 0 && sidx < len[w] && wv != 0.0f;
+            const int c = min(max(sidx, 0), max(len[w] - 1, 0));
+            float x = in ? ap[w][c] : 0.0f;
+            const float xp = (in && sidx > 0) ? ap[w][c - 1] : 0.0f;
+            x = fmaf(-preemph, xp, x);
+            v[w] = x * wv;
         }
         const int r = __brev((unsigned)i) >> (32 - log2n);
         s_x[r + (r >> 4)] = make_float2(v[0], v[1]);

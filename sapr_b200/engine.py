@@ -119,7 +119,8 @@ class WordModels:
         best_word = torch.empty(B, dtype=torch.int32, device=dev)
         best_score = torch.empty(B, dtype=torch.float64, device=dev)
         scores = torch.empty((B, nslots), dtype=torch.float64, device=dev) if want_scores else None
-        path = torch.zeros(batch.total_frames, dtype=torch.uint8, device=dev) if want_path else None
+        # every frame of every utterance is written when all frames are walked; the as-written mode (first_frames > 0) walks fewer
+        path = (torch.zeros if first_frames > 0 else torch.empty)(batch.total_frames, dtype=torch.uint8, device=dev) if want_path else None
         allp = torch.zeros((nslots, batch.total_frames), dtype=torch.uint8, device=dev) if all_paths else None
         self.ctx.check(self.lib.sapr_viterbi(self.ctx.h, self.h, ptr(batch.X), batch.ldx, ptr(batch.offsets), B,
                                              batch.total_frames, batch.max_T, ptr(model_of_utt), precision, first_frames,
