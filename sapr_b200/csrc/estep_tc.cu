@@ -51,7 +51,6 @@ struct EtParams {
     float *ustats;                                           // [B][24] by position in order[]: G | Xi | occ
     double *loglik;                                          // [B] by utterance id
     int Fshift, nst_shift; uint32_t rstride;
-    int pair0[TC_GROUPS], npair[TC_GROUPS];                  // chunk pairs of the converting groups (group 0: none)
     int pf;                                                  // backward sweep: L1 prefetch distance in frames
     long long *trace;                                        // [ET_TRACE_ROLES][ET_TRACE_FRAMES][ET_TRACE_EVENTS] or null
 };
@@ -585,15 +584,6 @@ int sapr_estep_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx,
     prm.scratch = (float *)ctx->ws[7]; prm.maxT = max_T;
     prm.gamma = gamma; prm.ustats = ustats; prm.loglik = loglik;
     prm.Fshift = Fshift; prm.nst_shift = nst_shift; prm.rstride = rstride;
-    {   // chunk pairs over the converting groups (group 0 runs the recursions)
-        const int npairs = nck / 2;
-        int pa = 0;
-        prm.pair0[0] = 0; prm.npair[0] = 0;
-        for (int gI = 1; gI < TC_GROUPS; gI++) {
-            const int cnt = (gI <= ET_CONV_GROUPS) ? npairs / ET_CONV_GROUPS + ((gI - 1) < npairs % ET_CONV_GROUPS ? 1 : 0) : 0;
-            prm.pair0[gI] = pa; prm.npair[gI] = cnt; pa += cnt;
-        }
-    }
     prm.pf = getenv("SAPR_ET_PF") ? atoi(getenv("SAPR_ET_PF")) : ET_PF;      // tuning aid
     prm.trace = nullptr;
     const char *trace_path = getenv("SAPR_ET_TRACE");

@@ -299,3 +299,28 @@ def test_launch_counter_and_errors(eng):
     assert ctx.launches() >= n0
     with pytest.raises(_lib.SaprError):
         eng.WordModels(1, 0, 13)
+
+
+@pytest.mark.parametrize("D", [12, 13, 40, 44])
+def test_estep_feature_dims_vs_oracle(eng, D):
+    """E-step statistics for feature dimensions with (13) and without (12, 40, 44: D a multiple of 4) a padding column: the
+    statistics kernel takes sum_t gamma from a constant-1 padding dim when there is one and from explicit sums otherwise.
+    Several tiles per model, ragged lengths; tensor-core path against the float64 oracle."""
+    import torch
+    from sapr_b200 import synth
+    feats, labels, mu, sd = synth.make_corpus(1500, 11, 8, D, 30, 50, seed=100 + D)
+    A, means, var = synth.truth_models(mu, sd, 0.9)
+    m = eng.WordModels(11, 8, D)
+    m.set(means, var, A)
+    batch = eng.PackedBatch.from_features(feats)
+    X, offs = orc.pack(feats)
+    lab = torch.as_tensor(labels, device="cuda")
+    ost, oll = orc.estep_batch(X, offs, labels, A, means, var)
+    S = 10
+    scale = np.maximum(1.0, np.abs(ost))
+    for P, rl, ra in ((eng.FP64, 1e-12, 1e-9), (eng.FP32, 1e-6, 2e-4)):
+        stats, ll, _ = m.estep(batch, lab, None, P)
+        assert_close(ll.cpu().numpy(), oll, rl, what=f"loglik D={D}")
+        st = stats.cpu().numpy()
+        assert np.max(np.abs(st[:, :3 * S] - ost[:, :3 * S]) / scale[:, :3 * S]) < ra, "occupancies"
+        assert np.max(np.abs(st[:, 3 * S:] - ost[:, 3 * S:]) / scale[:, 3 * S:]) < ra * 10, "feature sums"
