@@ -525,6 +525,28 @@ def main():
                 return t1 - t0, time.perf_counter() - t1
             run_batched()
             tr_b, de_b = run_batched()
+            # the reference's default implementation (train.py:82, decoder.py:13): the hmmlearn-style classes, float64 kernels
+            from sapr_b200.hmmlearn_hmm import HMMLearnModel
+
+            def run_hl():
+                t0 = time.perf_counter()
+                hl = []
+                with contextlib.redirect_stdout(io.StringIO()):
+                    for m in range(M_WORDS):
+                        h = HMMLearnModel(num_states=N_STATES, model_name=f"w{m}", n_iter=15, feature_set=feats1)
+                        h.fit(per_word[m])
+                        hl.append(h)
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                correct = 0
+                for f, w in zip(feats1[:33], lab1[:33]):
+                    sc = [h.model.decode(np.ascontiguousarray(f.T))[0] for h in hl]           # decoder.py:42-47
+                    correct += int(int(np.argmax(sc)) == int(w))
+                torch.cuda.synchronize()
+                return t1 - t0, (time.perf_counter() - t1) * 10.0, correct / 33.0
+
+            run_hl()
+            tr_h, de_h, acc_h = run_hl()
             est_upd = 15 * frames1 * N_STATES                                                 # E-step updates of one full training run
             cfg1 = {"workload": f"cfg1: 330 utterances (30 per word), T ~ U{{80..120}} ({frames1} frames), D = 13, N = 8, 15 Baum-Welch "
                                 "iterations per word from a flat start, Viterbi of 330 x 11",
@@ -532,6 +554,9 @@ def main():
                     "drop_in_as_written": {"train_s": tr_sapr, "decode_330x11_s": de_sapr, "train_updates_per_s": est_upd / tr_sapr,
                                            "note": "custom_hmm.py as written (Gram-matrix emission, full covariances, float64 compat kernels)"},
                     "batched_whole_vocabulary": {"train_s": tr_b, "decode_330x11_s": de_b, "train_updates_per_s": est_upd / tr_b},
+                    "drop_in_hmmlearn_style": {"train_s": tr_h, "decode_330x11_s": de_h, "train_updates_per_s": est_upd * 10 / 8 / tr_h,
+                                               "accuracy_33_training_utterances": acc_h,
+                                               "note": "GaussianHMM-style class, 10 emitting states, float64 kernels (csrc/hmmlearn.cu)"},
                     "reference_python": "BASELINE.md section 2: ~3.5e4 updates/s for baum_welch, ~1 ms per (utterance, model) decode on 8 vCPUs",
                     "note": "latency-bound at this size (one kernel launch set per word and iteration); decode timed on 33 utterances x 11 "
                             "models and scaled to 330"}
