@@ -102,19 +102,31 @@ __global__ void k_hl_backward_stats(const double *__restrict__ lf, const double 
     }
 }
 
-// obs = post^T X, obs2 = post^T X^2: one thread per (state, dim), frames in order
-__global__ void k_hl_obs(const float *__restrict__ X, int ldx, int64_t total_frames, int D, int S,
-                         const double *__restrict__ post, double *__restrict__ obs, double *__restrict__ obs2) {
+// obs = post^T X, obs2 = post^T X^2: one thread per (state, dim) and frame chunk (HL_OBS_CHUNK frames in order), then a
+// fixed-order sum over the chunks -- deterministic, and parallel over frames (one thread per output walking every frame
+// serially took seconds at 10^7 frames)
+#define HL_OBS_CHUNK 512
+__global__ void k_hl_obs_partial(const float *__restrict__ X, int ldx, int64_t total_frames, int D, int S,
+                                 const double *__restrict__ post, double *__restrict__ part) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= S * D) return;
     const int j = idx / D, d = idx % D;
+    const int64_t f0 = (int64_t)blockIdx.y * HL_OBS_CHUNK, f1 = min(f0 + HL_OBS_CHUNK, total_frames);
     double a = 0.0, b = 0.0;
-    for (int64_t f = 0; f < total_frames; f++) {
+    for (int64_t f = f0; f < f1; f++) {
         const double g = post[f * S + j];
         const double x = (double)X[f * ldx + d];
         a += g * x;
         b += g * x * x;
     }
+    part[((size_t)blockIdx.y * 2 + 0) * S * D + idx] = a;
+    part[((size_t)blockIdx.y * 2 + 1) * S * D + idx] = b;
+}
+__global__ void k_hl_obs_reduce(const double *__restrict__ part, int nchunk, int SD, double *__restrict__ obs, double *__restrict__ obs2) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= SD) return;
+    double a = 0.0, b = 0.0;
+    for (int c = 0; c < nchunk; c++) { a += part[((size_t)c * 2 + 0) * SD + idx]; b += part[((size_t)c * 2 + 1) * SD + idx]; }
     obs[idx] = a; obs2[idx] = b;
 }
 
@@ -335,6 +347,10 @@ __global__ void k_hl_viterbi_cta(const double *__restrict__ lf, const int64_t *_
         SAPR_FAIL(ctx, SAPR_E_INVALID, fn ": needs DENSE topology + DIAG emission");             \
     if (m->S > HL_MAX_S_CTA) SAPR_FAIL(ctx, SAPR_E_RANGE, fn ": more than 1024 states")
 
+// thread per utterance needs thousands of utterances to fill the GPU; below that (the reference's 30 utterances per word) one
+// CTA per utterance with a thread per state is the faster mapping
+static bool hl_thread_per_utt(const sapr_ctx *ctx, int S, int B) { return S <= HL_MAX_S && B >= 16 * ctx->sm_count; }
+
 extern "C" int64_t sapr_hl_stats_len(int S, int D) { return (int64_t)S + (int64_t)S * S + S + 2 * (int64_t)S * D; }
 
 extern "C" int sapr_hl_score(sapr_ctx *ctx, sapr_models *m, int mi, const float *X, int ldx, const int64_t *offsets,
@@ -345,7 +361,7 @@ extern "C" int sapr_hl_score(sapr_ctx *ctx, sapr_models *m, int mi, const float 
     if (rc) return rc;
     double *lf = (double *)ctx->ws[4];
     if ((rc = sapr_emission_into(ctx, m, mi, X, ldx, offsets, B, total_frames, lf))) return rc;
-    if (S <= HL_MAX_S)
+    if (hl_thread_per_utt(ctx, S, B))
         k_hl_forward<<<(B + 31) / 32, 32, 0, ctx->stream>>>(lf, offsets, B, S, m->logpi + (size_t)mi * S,
                                                             m->logA + (size_t)mi * S * S, nullptr, logprob);
     else
@@ -363,7 +379,7 @@ extern "C" int sapr_hl_decode(sapr_ctx *ctx, sapr_models *m, int mi, const float
     if (rc) return rc;
     double *lf = (double *)ctx->ws[4], *dl = lf + (size_t)total_frames * S;
     if ((rc = sapr_emission_into(ctx, m, mi, X, ldx, offsets, B, total_frames, lf))) return rc;
-    if (S <= HL_MAX_S)
+    if (hl_thread_per_utt(ctx, S, B))
         k_hl_viterbi<<<(B + 31) / 32, 32, 0, ctx->stream>>>(lf, offsets, B, S, m->logpi + (size_t)mi * S,
                                                             m->logA + (size_t)mi * S * S, dl, logprob, path);
     else
@@ -381,13 +397,14 @@ extern "C" int sapr_hl_estep(sapr_ctx *ctx, sapr_models *m, int mi, const float 
     const size_t lat = (size_t)total_frames * S;
     const int len = S + S * S + S;
     // partial statistics: one slot per utterance (S <= 32, thread per utterance) or per CTA (larger S, CTA per utterance)
-    const int nslots = S <= HL_MAX_S ? B : std::min(B, 2 * ctx->sm_count);
+    const bool tpu = hl_thread_per_utt(ctx, S, B);
+    const int nslots = tpu ? B : std::min(B, 2 * ctx->sm_count);
     int rc = sapr_ws_reserve(ctx, 4, sizeof(double) * (4 * lat + (size_t)nslots * len));
     if (rc) return rc;
     double *lf = (double *)ctx->ws[4], *fwd = lf + lat, *bwd = fwd + lat, *post = bwd + lat, *pu = post + lat;
     if ((rc = sapr_emission_into(ctx, m, mi, X, ldx, offsets, B, total_frames, lf))) return rc;
     const double *logpi = m->logpi + (size_t)mi * S, *logA = m->logA + (size_t)mi * S * S;
-    if (S <= HL_MAX_S) {
+    if (tpu) {
         k_hl_forward<<<(B + 31) / 32, 32, 0, ctx->stream>>>(lf, offsets, B, S, logpi, logA, fwd, logprob);
         SAPR_LAUNCH_CHECK(ctx);
         k_hl_backward_stats<<<(B + 31) / 32, 32, 0, ctx->stream>>>(lf, fwd, offsets, B, S, logA, logprob, bwd, post, pu);
@@ -402,7 +419,13 @@ extern "C" int sapr_hl_estep(sapr_ctx *ctx, sapr_models *m, int mi, const float 
     }
     k_hl_sum_pu<<<(len + 63) / 64, 64, 0, ctx->stream>>>(pu, nslots, len, stats);
     SAPR_LAUNCH_CHECK(ctx);
-    k_hl_obs<<<(S * D + 63) / 64, 64, 0, ctx->stream>>>(X, ldx, total_frames, D, S, post, stats + len, stats + len + (size_t)S * D);
+    const int nchunk = (int)((total_frames + HL_OBS_CHUNK - 1) / HL_OBS_CHUNK);
+    if ((rc = sapr_ws_reserve(ctx, 5, sizeof(double) * (size_t)std::max(nchunk, 1) * 2 * S * D))) return rc;
+    if (nchunk > 0) {
+        k_hl_obs_partial<<<dim3((S * D + 63) / 64, nchunk), 64, 0, ctx->stream>>>(X, ldx, total_frames, D, S, post, (double *)ctx->ws[5]);
+        SAPR_LAUNCH_CHECK(ctx);
+    }
+    k_hl_obs_reduce<<<(S * D + 63) / 64, 64, 0, ctx->stream>>>((const double *)ctx->ws[5], nchunk, S * D, stats + len, stats + len + (size_t)S * D);
     SAPR_LAUNCH_CHECK(ctx);
     return SAPR_OK;
 }

@@ -226,3 +226,31 @@ def test_cfg5_audio_to_words_on_device(cuda):
     o32 = m.viterbi(batch, None, engine.FP32, 0, want_scores=True)      # tensor-core path, D = 13
     assert_close(o32["scores"].cpu().numpy(), sc, 1e-6, what="scores32")
     assert np.mean(o32["best_word"].cpu().numpy() == bw) >= 0.95
+
+
+def test_large_batch_thread_per_utterance_vs_oracle(cuda, rung1_d13):
+    """2500 short utterances: enough for the thread-per-utterance kernels (small batches run one CTA per utterance) and for
+    many chunks in the frame-parallel observation statistics; score / decode / one fit iteration against the oracle."""
+    model, X0, lengths0, (means, var, tm, sp) = _setup(rung1_d13)
+    rng = np.random.default_rng(11)
+    lengths = rng.integers(10, 19, size=2500)
+    offs = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+    X = (means[rng.integers(1, 9, size=int(offs[-1]))] + np.sqrt(var[1]) * rng.standard_normal((int(offs[-1]), 13))).astype(np.float32).astype(np.float64)
+    tot, tot_v, paths = 0.0, 0.0, []
+    for a, b in zip(offs[:-1], offs[1:]):
+        lf = orc.emission_diag(X[a:b].T, means, var, all_emit=True)
+        tot += orc.hl_forward(lf, sp, tm)[0]
+        lp, p = orc.hl_viterbi(lf, sp, tm)
+        tot_v += lp; paths.append(p)
+    assert abs(model.score(X, list(lengths)) - tot) <= 1e-10 * abs(tot)
+    lp, path = model.decode(X, list(lengths))
+    assert abs(lp - tot_v) <= 1e-10 * abs(tot_v)
+    assert np.array_equal(path, np.concatenate(paths))
+    st = orc.hl_estep(X, offs, sp, tm, means, var)
+    sp2, tm2, means2, var2 = orc.hl_mstep(st, sp, tm)
+    model.n_iter = 1
+    model.fit(X, list(lengths))
+    assert_close(np.array(model.monitor_.history), np.array([st["logprob"]]), 1e-10, what="history")
+    assert_close(model.means_, means2, 1e-9, what="means")
+    assert_close(model._covars, var2, 1e-8, what="covars")
+    assert_close(model.transmat_, tm2, 1e-9, atol=1e-12, what="transmat")
