@@ -48,7 +48,7 @@ __global__ void k_mfcc_utt_of_frame(const int64_t *__restrict__ frame_off, int B
 
 // One WARP per PAIR of frames (blockDim.x / 32 pairs per CTA).  Frame a goes into the real part and frame b into the
 // imaginary part of ONE complex transform (both spectra fall out of Z[k] and conj(Z[N-k])), the radix-2 stages are taken
-// two at a time in registers (same butterflies, half the shared-memory passes), and only __syncwarp separates the passes.
+// three at a time in registers (same butterflies, a third of the shared-memory passes), and only __syncwarp separates the passes.
 __global__ void __launch_bounds__(256)
 k_mfcc_logmel(const float *__restrict__ audio, const int64_t *__restrict__ sample_off,
               const int64_t *__restrict__ frame_off, const int32_t *__restrict__ utt_of_frame, int64_t total_frames,
@@ -109,6 +109,45 @@ k_mfcc_logmel(const float *__restrict__ audio, const int64_t *__restrict__ sampl
     }
     __syncwarp();
     int st = 1;
+    for (; st + 2 <= log2n; st += 3) {          // stages st .. st + 2 on the 8 elements p + q h (q = 0..7) of a block of 8h, in registers
+        const int h = 1 << (st - 1);
+        for (int k = lane; k < n_fft / 8; k += 32) {
+            const int pos = k & (h - 1);
+            const int i0 = ((k - pos) << 3) + pos;
+            float2 a[8];
+            int j[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) { j[q] = P(i0 + q * h); a[q] = s_x[j[q]]; }
+            {   // stage st: pairs (0,1) (2,3) (4,5) (6,7), one twiddle
+                const float2 w = twiddle[pos * (n_fft >> st)];
+#pragma unroll
+                for (int q = 0; q < 8; q += 2) {
+                    const float2 t = cmul(a[q + 1], w), x = a[q];
+                    a[q] = make_float2(x.x + t.x, x.y + t.y); a[q + 1] = make_float2(x.x - t.x, x.y - t.y);
+                }
+            }
+            {   // stage st + 1: pairs (0,2) (1,3) (4,6) (5,7), twiddles at pos and pos + h
+                const float2 w0 = twiddle[pos * (n_fft >> (st + 1))], w1 = twiddle[(pos + h) * (n_fft >> (st + 1))];
+#pragma unroll
+                for (int q = 0; q < 8; q += 4) {
+                    float2 t = cmul(a[q + 2], w0), x = a[q];
+                    a[q] = make_float2(x.x + t.x, x.y + t.y); a[q + 2] = make_float2(x.x - t.x, x.y - t.y);
+                    t = cmul(a[q + 3], w1); x = a[q + 1];
+                    a[q + 1] = make_float2(x.x + t.x, x.y + t.y); a[q + 3] = make_float2(x.x - t.x, x.y - t.y);
+                }
+            }
+            {   // stage st + 2: pairs (q, q + 4), twiddles at pos + q h
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float2 t = cmul(a[q + 4], twiddle[(pos + q * h) * (n_fft >> (st + 2))]), x = a[q];
+                    a[q] = make_float2(x.x + t.x, x.y + t.y); a[q + 4] = make_float2(x.x - t.x, x.y - t.y);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) s_x[j[q]] = a[q];
+        }
+        __syncwarp();
+    }
     for (; st + 1 <= log2n; st += 2) {          // stages st and st + 1 on the 4 elements p, p+h, p+2h, p+3h of a block of 4h
         const int h = 1 << (st - 1);
         for (int k = lane; k < n_fft / 4; k += 32) {
