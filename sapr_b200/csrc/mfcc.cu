@@ -89,23 +89,47 @@ k_mfcc_logmel(const float *__restrict__ audio, const int64_t *__restrict__ sampl
         len[w] = (w == 0 || two) ? (int)(sample_off[uu[w] + 1] - s0) : 0;
         start[w] = (int)(f - frame_off[uu[w]]) * hop - (center ? n_fft / 2 : 0);
     }
-    // branch-free loads (clamped index, masked value), four iterations in flight
+    // four consecutive samples per lane and step: one 16-byte load per frame when the chunk is aligned and inside the
+    // utterance (the common case), element-wise guarded loads at the utterance boundaries; all chunks of a lane are in flight
+    // together (n_fft / 128 steps)
+    bool al16[2];
+#pragma unroll
+    for (int w = 0; w < 2; w++) al16[w] = ((reinterpret_cast<uintptr_t>(ap[w] + start[w]) & 15) == 0);
 #pragma unroll 4
-    for (int i = lane; i < n_fft; i += 32) {
-        const float wv = window[i];
-        float v[2];
+    for (int c = lane; c < n_fft / 4; c += 32) {
+        const int i = 4 * c;
+        const float4 wv = *reinterpret_cast<const float4 *>(window + i);
+        const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
+        float y[2][4];
+        const bool any = (wv.x != 0.0f) || (wv.y != 0.0f) || (wv.z != 0.0f) || (wv.w != 0.0f);
 #pragma unroll
         for (int w = 0; w < 2; w++) {
             const int sidx = start[w] + i;
-            const bool in = sidx >= 0 && sidx < len[w] && wv != 0.0f;
-            const int c = min(max(sidx, 0), max(len[w] - 1, 0));
-            float x = in ? ap[w][c] : 0.0f;
-            const float xp = (in && sidx > 0) ? ap[w][c - 1] : 0.0f;
-            x = fmaf(-preemph, xp, x);
-            v[w] = x * wv;
+            float x[4], xp;
+            if (!any || len[w] == 0) {
+                x[0] = x[1] = x[2] = x[3] = 0.0f; xp = 0.0f;
+            } else if (al16[w] && sidx >= 1 && sidx + 3 < len[w]) {
+                const float4 v = *reinterpret_cast<const float4 *>(ap[w] + sidx);
+                x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+                xp = ap[w][sidx - 1];
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; e++) { const int sx = sidx + e; x[e] = (sx >= 0 && sx < len[w]) ? ap[w][sx] : 0.0f; }
+                xp = (sidx >= 1 && sidx - 1 < len[w]) ? ap[w][sidx - 1] : 0.0f;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int sx = sidx + e;
+                const float prev = (e == 0) ? xp : x[e - 1];
+                const float v = (sx >= 0 && sx < len[w]) ? fmaf(-preemph, (sx > 0) ? prev : 0.0f, x[e]) : 0.0f;
+                y[w][e] = v * wq[e];
+            }
         }
-        const int r = __brev((unsigned)i) >> (32 - log2n);
-        s_x[r + (r >> 4)] = make_float2(v[0], v[1]);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int r = __brev((unsigned)(i + e)) >> (32 - log2n);
+            s_x[r + (r >> 4)] = make_float2(y[0][e], y[1][e]);
+        }
     }
     __syncwarp();
     int st = 1;
