@@ -152,3 +152,27 @@ def test_eval_metrics_match_sklearn():
         assert acc == pytest.approx(sk.accuracy_score(ti, pi))
     res = {"heed": [{"true_word": "heed", "predicted_word": "hid"}], "hid": [{"true_word": "hid", "predicted_word": "hid"}]}
     assert extract_labels(res) == (["heed", "hid"], ["hid", "hid"])
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines kept under profiles/ (written by bench.py on a B200) carry every key of the measurement contract."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    line = json.loads(open(os.path.join(root, "profiles", "r01_bench_s4.json")).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in line, k
+    assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["higher_is_better"] is True and line["scaling"] == "weak"
+    assert "workload" in line["config"] and "model" not in line["config"]
+    r = line["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] is not None
+    c = line["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    e = line["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < line["value"]
+    assert line["gpu_launches"] > 0
+    assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    ref = json.loads(open(os.path.join(root, "profiles", "r01_bench_ref_s4.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
