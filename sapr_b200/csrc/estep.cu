@@ -401,7 +401,8 @@ k_stats_diag8(const float *__restrict__ X, int ldx, const int64_t *__restrict__ 
     __shared__ __align__(8) uint64_t s_bar[2 * STATS2_STAGES];
     const int ndq = Dp / 4, ncons = ndq * 2 * STATS2_SLOTS, tid = threadIdx.x;
     const bool consumer = tid < ncons;
-    const int dq = tid % ndq, sh = (tid / ndq) & 1, slot = tid / (2 * ndq), d0 = 4 * dq;
+    // a warp covers ~3 adjacent frame slots of ONE state half, so a half without posterior mass in those frames can be skipped as a warp
+    const int dq = tid % ndq, slot = (tid / ndq) % STATS2_SLOTS, sh = tid / (ndq * STATS2_SLOTS), d0 = 4 * dq;
     const bool ones = Dp > D;                                    // dim D (padding) carries the constant 1
     extern __shared__ __align__(16) unsigned char s_dyn[];
     // the ring; at the end of the tile it is reused for the per-slot partials S1, S2 [STATS2_SLOTS][2][N][Dp], G [STATS2_SLOTS][N]
@@ -489,15 +490,24 @@ k_stats_diag8(const float *__restrict__ X, int ldx, const int64_t *__restrict__ 
             }
             const float2 kk01 = make_float2(kk[0], kk[1]), kk23 = make_float2(kk[2], kk[3]);
             const float2 ng01 = make_float2(gp[0], gp[1]), ng23 = make_float2(gp[2], gp[3]);
+            int dense_left = 0;                     // stages this warp still runs without the sparsity test
             for (int k = 0; k < nstage; k++) {
                 const uint32_t st = (uint32_t)k % STATS2_STAGES, ph = ((uint32_t)k / STATS2_STAGES) & 1u;
                 const int n = min(STATS2_CF, ftot - k * STATS2_CF);
                 st_wait(bar_full + 8 * st, ph);
                 const unsigned char *sx = s_stage + st * stage_bytes + 16 * dq;
                 const unsigned char *sg = s_stage + st * stage_bytes + STATS2_CF * rowbytes + 16 * sh;
-                auto frame = [&](int fi) {
-                    const float4 xr = *reinterpret_cast<const float4 *>(sx + (size_t)fi * rowbytes);
+                // Posteriors of a left-to-right model are sparse: most frames have exactly zero mass in one half of the states.
+                // A zero gamma contributes exactly nothing, so when every lane of the warp sees an all-zero half the frame is
+                // skipped (bit-identical sums).  The test costs 4 instructions; a warp that found nothing to skip in a stage
+                // runs the next seven stages without the test (dense posteriors, e.g. right after a flat start).
+                auto frame = [&](int fi, bool probe) -> bool {
                     const float4 g0 = *reinterpret_cast<const float4 *>(sg + fi * 32);
+                    if (probe) {
+                        const uint32_t any = (__float_as_uint(g0.x) | __float_as_uint(g0.y) | __float_as_uint(g0.z) | __float_as_uint(g0.w)) << 1;
+                        if (__all_sync(0xffffffffu, any == 0u)) return true;
+                    }
+                    const float4 xr = *reinterpret_cast<const float4 *>(sx + (size_t)fi * rowbytes);
                     const float2 x01 = st_fma2(make_float2(xr.x, xr.y), kk01, ng01);      // x' = x - g (0 for padded dims)
                     const float2 x23 = st_fma2(make_float2(xr.z, xr.w), kk23, ng23);
                     const float2 q01 = st_mul2(x01, x01), q23 = st_mul2(x23, x23);
@@ -509,12 +519,16 @@ k_stats_diag8(const float *__restrict__ X, int ldx, const int64_t *__restrict__ 
                         s2[j][0] = st_fma2(gg, q01, s2[j][0]); s2[j][1] = st_fma2(gg, q23, s2[j][1]);
                     }
                     if (!ones) { gs[0].x += g0.x; gs[0].y += g0.y; gs[1].x += g0.z; gs[1].y += g0.w; }
+                    return false;
                 };
                 if (n == STATS2_CF) {
+                    const bool probe = dense_left == 0;
+                    bool skipped = false;
 #pragma unroll
-                    for (int i = 0; i < STATS2_CF / STATS2_SLOTS; i++) frame(slot + i * STATS2_SLOTS);
+                    for (int i = 0; i < STATS2_CF / STATS2_SLOTS; i++) skipped |= frame(slot + i * STATS2_SLOTS, probe);
+                    if (probe) { if (!skipped) dense_left = 7; } else dense_left--;
                 } else {
-                    for (int fi = slot; fi < n; fi += STATS2_SLOTS) frame(fi);
+                    for (int fi = slot; fi < n; fi += STATS2_SLOTS) frame(fi, false);
                 }
                 __syncwarp();
                 if ((tid & 31) == 0)
