@@ -42,32 +42,41 @@ __global__ void k_prepare_tc(int M, int S, int D, int nck, int ncols, const doub
                              __half *__restrict__ wimg, float *__restrict__ sb, float4 *__restrict__ trp) {
     extern __shared__ double s_gs[];   // [2][4*nck]: effective centre g, scale s
     const int N = S - 2, nd = 4 * nck;
-    for (int d = threadIdx.x; d < nd; d += blockDim.x) {
+    // one warp per feature dim, lanes stride over the (model, state) pairs, fixed-order shuffle tree; every CTA recomputes
+    // these cheap constants and block 0 writes them (one thread per dim walking all states made this kernel 0.18 ms)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    auto wsum = [](double v) {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
+    for (int d = warp; d < nd; d += nwarp) {
         double g = 0.0, sc = 0.0;
         float sf = 0.f, bf = 0.f;
         if (d < D) {
             double sm = 0.0;
-            for (int m = 0; m < M; m++) for (int j = 1; j <= N; j++) sm += mean[((size_t)m * S + j) * D + d];
-            g = sm / (M * N);
+            for (int q = lane; q < M * N; q += 32) sm += mean[((size_t)(q / N) * S + (q % N) + 1) * D + d];
+            g = wsum(sm) / (M * N);
             double v = 0.0;
-            for (int m = 0; m < M; m++)
-                for (int j = 1; j <= N; j++) {
-                    const double df = mean[((size_t)m * S + j) * D + d] - g;
-                    v += var[((size_t)m * S + j) * D + d] + df * df;
-                }
-            v /= (M * N);
+            for (int q = lane; q < M * N; q += 32) {
+                const size_t o = ((size_t)(q / N) * S + (q % N) + 1) * D + d;
+                const double df = mean[o] - g;
+                v += var[o] + df * df;
+            }
+            v = wsum(v) / (M * N);
             sc = (v > 0 && v < 1e300) ? 4.0 / sqrt(v) : 1.0;
             sf = (float)sc; bf = (float)(-g * sc);
             sc = (double)sf; g = -(double)bf / sc;   // the kernel standardises in fp32 with exactly (sf, bf)
         } else if (d == D) {
             sf = 0.f; bf = 1.f;                       // constant slot: x' = 1
         }
-        s_gs[d] = g; s_gs[nd + d] = sc;
-        sb[d] = sf; sb[nd + d] = bf;
+        if (lane == 0) {
+            s_gs[d] = g; s_gs[nd + d] = sc;
+            if (blockIdx.x == 0) { sb[d] = sf; sb[nd + d] = bf; }
+        }
     }
     __syncthreads();
     const size_t plane = (size_t)(ncols / 8) * nck * 64;
-    for (int idx = threadIdx.x; idx < ncols * nd; idx += blockDim.x) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ncols * nd; idx += gridDim.x * blockDim.x) {
         const int n = idx / nd, d = idx % nd;
         const int m = n / 8, j = (n % 8) + 1;
         double wx = 0.0, wx2 = 0.0;
@@ -98,7 +107,7 @@ __global__ void k_prepare_tc(int M, int S, int D, int nck, int ncols, const doub
         wimg[plane + o] = __double2half(wx - (double)__half2float(hx));
         wimg[plane + o + 4] = __double2half(wx2 - (double)__half2float(hx2));
     }
-    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    for (int m = threadIdx.x; m < M && blockIdx.x == 0; m += blockDim.x) {
         const double *a = la + (size_t)m * S, *b = lb + (size_t)m * S;
         float v[20];
         for (int j = 1; j <= 7; j++) v[j - 1] = (j + 1 <= N) ? (float)(b[j] - a[j]) : -INFINITY;   // c_{j+1}: into state j+1
@@ -625,7 +634,7 @@ int sapr_tc_prepare(sapr_models *m) {
     __half *wimg = (__half *)m->tc_image;
     float *sb = (float *)((char *)m->tc_image + w);
     float4 *trp = (float4 *)((char *)m->tc_image + w + g);
-    k_prepare_tc<<<1, 256, sizeof(double) * 2 * 4 * nck, ctx->stream>>>(m->M, m->S, m->D, nck, ncols, m->mean, m->cov, m->la64,
+    k_prepare_tc<<<std::max(1, std::min(32, (ncols * 4 * nck + 255) / 256)), 256, sizeof(double) * 2 * 4 * nck, ctx->stream>>>(m->M, m->S, m->D, nck, ncols, m->mean, m->cov, m->la64,
                                                                          m->lb64, wimg, sb, trp);
     SAPR_LAUNCH_CHECK(ctx);
     return SAPR_OK;
