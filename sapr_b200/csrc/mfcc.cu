@@ -15,6 +15,7 @@
 #include "common.cuh"
 
 #define MFCC_PI 3.14159265358979323846
+#define MFCC_PW_REG 9        /* power-spectrum values per lane held in registers when n_fft <= 512 */
 
 extern "C" int64_t sapr_mfcc_num_frames(const sapr_mfcc_params *p, int64_t n_samples) {
     if (!p || p->hop_length <= 0) return 0;
@@ -71,9 +72,10 @@ k_mfcc_logmel(const float *__restrict__ audio, const int64_t *__restrict__ sampl
     for (int i = threadIdx.x; i < n_mel_w; i += blockDim.x) mel_w[i] = g_mel_w[i];
     for (int i = threadIdx.x; i < n_mels; i += blockDim.x) { mel_lo[i] = g_mel_lo[i]; mel_hi[i] = g_mel_hi[i]; mel_ptr[i] = g_mel_ptr[i]; }
     __syncthreads();
-    const size_t per_warp = (size_t)n_fft + (size_t)(n_fft / 16) + (size_t)((2 * nb + 1) / 2);   // in float2 units
+    const bool pw_alias = nb <= 32 * MFCC_PW_REG;                                            // power values overwrite the transform buffer
+    const size_t per_warp = (size_t)n_fft + (size_t)(n_fft / 16) + (pw_alias ? 0 : (size_t)((2 * nb + 1) / 2));   // in float2 units
     float2 *s_x = s_all + tab_f2 + (size_t)warp * per_warp;
-    float *pw = reinterpret_cast<float *>(s_x + n_fft + n_fft / 16);                          // pw[which * nb + k]
+    float *pw = reinterpret_cast<float *>(pw_alias ? s_x : s_x + n_fft + n_fft / 16);          // pw[which * nb + k]
     auto P = [](int i) { return i + (i >> 4); };      // padded index: the strided passes and the bit-reversed scatter hit distinct banks
     auto cmul = [](float2 b, float2 w) { return make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x); };
     for (int64_t fa = ((int64_t)blockIdx.x * wpc + warp) * 2; fa < total_frames; fa += (int64_t)gridDim.x * wpc * 2) {
@@ -206,13 +208,35 @@ k_mfcc_logmel(const float *__restrict__ audio, const int64_t *__restrict__ sampl
         }
         __syncwarp();
     }
-    // split the two real spectra: A[k] = (Z[k] + conj(Z[N-k])) / 2, B[k] = (Z[k] - conj(Z[N-k])) / (2i)
-    for (int k = lane; k < nb; k += 32) {
-        const float2 z = s_x[P(k)], zn = s_x[P((n_fft - k) & (n_fft - 1))];
-        const float ar = 0.5f * (z.x + zn.x), ai = 0.5f * (z.y - zn.y);
-        const float br = 0.5f * (z.y + zn.y), bi = 0.5f * (zn.x - z.x);
-        pw[k] = ar * ar + ai * ai;
-        pw[nb + k] = br * br + bi * bi;
+    // split the two real spectra: A[k] = (Z[k] + conj(Z[N-k])) / 2, B[k] = (Z[k] - conj(Z[N-k])) / (2i).  For n_fft <= 512 the
+    // power values go through registers and overwrite the transform buffer (2 KB less shared memory per warp = more warps per SM)
+    if (pw_alias) {
+        float pa[MFCC_PW_REG], pb[MFCC_PW_REG];
+#pragma unroll
+        for (int q = 0; q < MFCC_PW_REG; q++) {
+            const int k = lane + 32 * q;
+            pa[q] = 0.0f; pb[q] = 0.0f;
+            if (k < nb) {
+                const float2 z = s_x[P(k)], zn = s_x[P((n_fft - k) & (n_fft - 1))];
+                const float ar = 0.5f * (z.x + zn.x), ai = 0.5f * (z.y - zn.y);
+                const float br = 0.5f * (z.y + zn.y), bi = 0.5f * (zn.x - z.x);
+                pa[q] = ar * ar + ai * ai; pb[q] = br * br + bi * bi;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < MFCC_PW_REG; q++) {
+            const int k = lane + 32 * q;
+            if (k < nb) { pw[k] = pa[q]; pw[nb + k] = pb[q]; }
+        }
+    } else {
+        for (int k = lane; k < nb; k += 32) {
+            const float2 z = s_x[P(k)], zn = s_x[P((n_fft - k) & (n_fft - 1))];
+            const float ar = 0.5f * (z.x + zn.x), ai = 0.5f * (z.y - zn.y);
+            const float br = 0.5f * (z.y + zn.y), bi = 0.5f * (zn.x - z.x);
+            pw[k] = ar * ar + ai * ai;
+            pw[nb + k] = br * br + bi * bi;
+        }
     }
     __syncwarp();
     for (int e = lane; e < 2 * n_mels; e += 32) {
@@ -339,12 +363,14 @@ extern "C" int sapr_mfcc(sapr_ctx *ctx, const sapr_mfcc_params *p, const float *
     k_mfcc_utt_of_frame<<<(unsigned)((total_frames + 255) / 256), 256, 0, ctx->stream>>>((const int64_t *)(base + o_foff), B, total_frames, uof);
     SAPR_LAUNCH_CHECK(ctx);
     int wpc = 8;                                           // frame pairs (warps) per CTA: as many as 96 KB of shared memory hold
-    const size_t per_warp = sizeof(float2) * ((size_t)n_fft + n_fft / 16 + (2 * nb + 1) / 2);
+    const size_t per_warp = sizeof(float2) * ((size_t)n_fft + n_fft / 16 + (nb <= 32 * MFCC_PW_REG ? 0 : (2 * nb + 1) / 2));
     const size_t tab = sizeof(float2) * (((size_t)n_fft + n_fft + w.size() + 3 * n_mels + 1) / 2 + 1);
     while (wpc > 1 && tab + per_warp * wpc > 100 * 1024) wpc >>= 1;
     const size_t smem = tab + per_warp * wpc;
     SAPR_CUDA(ctx, cudaFuncSetAttribute(k_mfcc_logmel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int cta_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (32 * wpc), (220 * 1024) / (smem + 1024)));   // resident CTAs: one wave
+    int cta_per_sm = 1;                                    // resident CTAs (registers and shared memory): the grid is one wave
+    SAPR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cta_per_sm, k_mfcc_logmel, 32 * wpc, smem));
+    cta_per_sm = std::max(cta_per_sm, 1);
     k_mfcc_logmel<<<(unsigned)std::min<int64_t>((total_frames + 2 * wpc - 1) / (2 * wpc), (int64_t)ctx->sm_count * cta_per_sm), 32 * wpc, smem, ctx->stream>>>(
         audio, (const int64_t *)(base + o_soff), (const int64_t *)(base + o_foff), uof, total_frames, n_fft,
         log2n, p->hop_length, p->center, p->preemph, (const float *)(base + o_win), (const float2 *)(base + o_tw), n_mels,
