@@ -373,14 +373,14 @@ __device__ __forceinline__ float2 st_sub2(float2 a, float2 b) {
 }
 
 // Shared-memory staged.  All utterances of a tile belong to one model, so the tile's frames are ONE stream: a
-// dedicated producer warp bulk-copies it, STATS2_CF frames per stage (a stage may span utterance boundaries: one copy
+// dedicated producer warp bulk-copies it, STATS2_CF frames per stage (256: at 128 the per-stage hand-shakes cost 15 %) (a stage may span utterance boundaries: one copy
 // of feature rows + one of gamma rows per piece; both are contiguous in HBM), into a STATS2_STAGES-deep ring.
 // Consumer thread = (dim quad, state half, frame slot): 4 dims x 4 states x 2 moments = 32 packed accumulators, per
 // frame one LDS.128 of features, one of gamma, and 20 FFMA2/FMUL2.  When D < Dp the first padding dim carries the
 // constant 1, so its first-moment column is sum_t gamma (the occupancy the re-pivot needs) at no extra cost.
 // blockDim.x = (Dp / 4) * 2 * STATS2_SLOTS consumers + 32 (producer warp).
-#define STATS2_CF 128
-#define STATS2_STAGES 6
+#define STATS2_CF 256
+#define STATS2_STAGES 4
 __device__ __forceinline__ uint32_t st_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void st_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
