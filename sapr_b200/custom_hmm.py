@@ -56,11 +56,13 @@ class HMM:
     def __getstate__(self):
         st = dict(self.__dict__)
         st["_dev"] = None
+        st.pop("_dev_key", None)
         return st
 
     def __setstate__(self, st):
         self.__dict__.update(st)
         self._dev = None
+        self._dev_key = None
 
     # ---- device plumbing ----
     def _prec(self):
@@ -74,10 +76,18 @@ class HMM:
         cov = np.asarray(self.B["covariance"], dtype=np.float64)
         if emission == EMIT_DIAG:
             cov = np.ascontiguousarray(np.diagonal(cov, axis1=1, axis2=2)) if cov.ndim == 3 else cov
-        self._dev.set(self.B["mean"], cov, self.A)
+        # the per-sequence decode loop of decoder.py calls this once per utterance and model: skip the upload (and the
+        # device-side image preparation) when the parameters are byte-identical to what is already on the device
+        mean = np.ascontiguousarray(self.B["mean"], dtype=np.float64)
+        A = np.ascontiguousarray(self.A, dtype=np.float64)
+        key = (id(self._dev), hash(mean.tobytes()), hash(np.ascontiguousarray(cov).tobytes()), hash(A.tobytes()))
+        if getattr(self, "_dev_key", None) != key:
+            self._dev.set(mean, cov, A)
+            self._dev_key = key
         return self._dev
 
     def _pull(self):
+        self._dev_key = None                      # the device parameters changed under the key
         means, cov, A, _ = self._dev.get()
         self.A = A[0]
         if self._dev.emission == EMIT_DIAG:

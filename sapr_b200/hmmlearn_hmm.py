@@ -81,11 +81,13 @@ class GaussianHMM:
     def __getstate__(self):
         st = dict(self.__dict__)
         st["_dev"] = None
+        st.pop("_dev_key", None)
         return st
 
     def __setstate__(self, st):
         self.__dict__.update(st)
         self._dev = None
+        self._dev_key = None
 
     def _check(self):
         sp = np.asarray(self.startprob_, dtype=np.float64)
@@ -105,7 +107,12 @@ class GaussianHMM:
         S, D = self.means_.shape
         if self._dev is None or (self._dev.S, self._dev.D) != (S, D):
             self._dev = WordModels(1, S, D, EMIT_DIAG, TOPO_DENSE)
-        self._dev.set(self.means_, self._covars, self.transmat_, self.startprob_)
+        # decode / score are called once per utterance and model by decoder.py: upload only when the parameters changed
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (self.means_, self._covars, self.transmat_, self.startprob_)]
+        key = (id(self._dev),) + tuple(hash(a.tobytes()) for a in arrs)
+        if getattr(self, "_dev_key", None) != key:
+            self._dev.set(*arrs)
+            self._dev_key = key
         return self._dev
 
     @staticmethod
