@@ -105,3 +105,24 @@ def test_cfg3_estep_full_size_properties(big):
         s, _, _ = m.estep(sub, labels[a:b].contiguous(), None, eng.FP64)
         tot = s if tot is None else tot + s
     assert_close(tot.cpu().numpy(), s64.cpu().numpy(), 1e-10, atol=1e-7, what="sharded stats")
+
+
+def test_estep_and_viterbi_are_run_to_run_deterministic():
+    """Fixed-order reductions everywhere (per-slot partials, per-tile float64 sums, tree over utterances): two runs over the
+    same 40 000-utterance batch (several tiles per CTA, both recursion groups busy) give bit-identical statistics,
+    log-likelihoods, posteriors, words and paths -- what makes the 1-vs-N-GPU comparison meaningful."""
+    import torch
+    from sapr_b200 import engine, synth
+    dev = torch.device("cuda", 0)
+    X, offsets, labels, mu, sd = synth.device_corpus(40000, 11, 8, 39, 60, 4242, dev)
+    A, means, var = synth.truth_models(mu, sd, 0.9)
+    m = engine.WordModels(11, 8, 39); m.set(means, var, A)
+    batch = engine.PackedBatch(X, offsets, 39, offsets.cpu().numpy(), labels)
+    order = engine.group_by_model(labels)
+    runs = []
+    for _ in range(2):
+        st, ll, g = m.estep(batch, labels, order, engine.FP32, want_gamma=True)
+        v = m.viterbi(batch, None, engine.FP32, 0, want_scores=True)
+        runs.append([t.cpu().numpy() for t in (st, ll, g, v["best_word"], v["scores"], v["path"])])
+    for a, b in zip(*runs):
+        assert np.array_equal(a, b, equal_nan=True)
