@@ -177,6 +177,10 @@ def main():
     dist = Dist()
     rank, world = dist.rank, dist.world
     torch.cuda.set_device(dist.local_rank)
+    numa = None
+    if world > 1 and os.environ.get("SAPR_NUMA_BIND", "1") != "0":
+        from sapr_b200.dist import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(dist.local_rank)      # node-local pinned buffers for the end-to-end leg
     dev = torch.device("cuda", dist.local_rank)
     ctx = _lib.default_context()
     prec = engine.FP64 if args.precision == "fp64" else engine.FP32
@@ -273,7 +277,7 @@ def main():
                "h2d_bytes_per_step": int(Xh_np.nbytes + offs_host.nbytes),
                "d2h_bytes_per_step": int(res["best_word"].nbytes + res["best_score"].nbytes + res["path"].nbytes),
                "ms_per_step": float(e_ms.item()), "steps": e_steps, "matches_device_path": same,
-               "call": "sapr_viterbi_host (chunked H2D on a copy stream overlapped with decoding)"}
+               "call": "sapr_viterbi_host (chunked H2D on a copy stream overlapped with decoding)", "numa_node_rank0": numa}
         del Xh
 
     # ---- secondary leg: Baum-Welch E-step (+ all-reduce + M-step) ----

@@ -176,3 +176,12 @@ def test_committed_bench_lines_follow_the_contract():
     ref = json.loads(open(os.path.join(root, "profiles", "r01_bench_ref_s4.json")).read().strip().splitlines()[-1])
     assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"]
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
+
+
+def test_cpulist_parser_and_numa_bind_is_harmless_without_topology():
+    from sapr_b200.dist import _parse_cpulist, bind_to_gpu_numa_node
+    assert _parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert _parse_cpulist("5") == [5]
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None          # no GPU / no sysfs entry here: nothing changes
+    assert os.sched_getaffinity(0) == before
