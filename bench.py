@@ -94,10 +94,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_threads():
+    """Host cores this process may use -- NOT omp_get_max_threads(): torch.distributed.run exports OMP_NUM_THREADS=1,
+    which made the round-1 reference arm single-threaded at N >= 2.  The oracle takes the count explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(corpus_host, offs_host, labels_host, A, means, var, leg, target_s=12.0):
     """Time the oracle port on a bounded sample of the bench tensors, all host threads."""
     from oracle import oracle as orc
-    nthreads = orc.num_threads()
+    nthreads = host_threads()
     B = len(offs_host) - 1
     probe = min(B, 64 * max(1, nthreads))
 
@@ -125,7 +134,7 @@ def reference_arm(args):
         return
     from oracle import oracle as orc
     from sapr_b200 import synth
-    nthreads = orc.num_threads()
+    nthreads = host_threads()
     nu = 192 * max(1, nthreads)
     feats, labels, mu, sd = synth.make_corpus(nu, M_WORDS, N_STATES, DIM, T_FRAMES, T_FRAMES, seed=SEED)
     A, means, var = synth.truth_models(mu, sd, 0.9)

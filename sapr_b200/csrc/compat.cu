@@ -246,9 +246,9 @@ __global__ void k_sum_per_utt(const double *__restrict__ per_utt, int B, int len
 
 // update_A (custom_hmm.py:351-364)
 __global__ void k_update_A(int S, const double *__restrict__ agg_xi, const double *__restrict__ agg_gamma, double *A) {
-    const int i = threadIdx.x;
-    if (i == 0) { A[0 * S + 1] = 1.0; A[(size_t)(S - 1) * S + S - 1] = 1.0; }
-    if (i >= 1 && i < S - 1 && agg_gamma[i] > 0) {
+    if (threadIdx.x == 0) { A[0 * S + 1] = 1.0; A[(size_t)(S - 1) * S + S - 1] = 1.0; }
+    for (int i = threadIdx.x; i < S - 1; i += blockDim.x) {   // any number of states
+        if (i < 1 || !(agg_gamma[i] > 0)) continue;
         const double aii = agg_xi[(size_t)i * S + i] / agg_gamma[i];
         A[(size_t)i * S + i] = aii;
         A[(size_t)i * S + i + 1] = 1.0 - aii;

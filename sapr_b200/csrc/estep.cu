@@ -647,7 +647,7 @@ static int launch_estep(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, 
         SAPR_LAUNCH_CHECK(ctx);
         order = order_ws;
     }
-    k_model_start<<<1, 64, 0, ctx->stream>>>(model_of_utt, order, B, M, model_start);
+    k_model_start<<<(M + 1 + 63) / 64, 64, 0, ctx->stream>>>(model_of_utt, order, B, M, model_start);
     SAPR_LAUNCH_CHECK(ctx);
     // gamma workspace (or the caller's debug buffer)
     R *gamma = (R *)gamma_out;

@@ -8,9 +8,10 @@
 // BASELINE cfg 5 (16 kHz, 400/160, 512-pt, 26 HTK mels, pre-emphasis 0.97, natural log) is the
 // same kernel.
 //
-// k_mfcc_logmel: one CTA per frame: samples (+pre-emphasis, window) -> shared memory, in-place
-//                radix-2 FFT in shared memory, power spectrum, sparse triangular mel filters,
-//                log -> logmel[frame][n_mels] and the per-utterance maximum (ordered-int atomicMax).
+// k_mfcc_logmel: persistent CTAs, one WARP per pair of frames: samples (+pre-emphasis, window) of the two real
+//                frames form the real / imaginary part of ONE complex FFT (three radix-2 stages per register pass
+//                over a padded shared-memory buffer, __syncwarp only), split spectra, power, sparse triangular mel
+//                filters, log -> logmel[frame][n_mels] and the per-utterance maximum (ordered-int atomicMax).
 // k_mfcc_dct:    clamp to max - top_db, DCT-II, write feats[frame][ld_out].
 #include "common.cuh"
 

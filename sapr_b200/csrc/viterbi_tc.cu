@@ -19,9 +19,9 @@
 // Precision: operands are fp16 hi/lo splits (x' = hi + lo to 22 bits, likewise W); the three products
 // hi*Whi + lo*Whi + hi*Wlo are one K = 3*Kh accumulation chain in fp32 TMEM (Kh = 80 for D = 39).
 //
-// CTA = 18 warps: warps 0-15 are workers (thread = (row r, group g): converts a quarter of row r's next frame
-// into the A operand, then runs the recursion for a quarter of the models), warp 16 issues the MMAs, warp 17
-// issues the bulk copies.  Pipeline per frame f (stage = f & 1): workers write A[f+1] -> mbarrier A_full ->
+// CTA = 20 warps: warps 0-15 are workers (thread = (row r, group g): converts a quarter of row r's next frame
+// into the A operand, then runs the recursion for a quarter of the models), warp 16 issues the MMAs, warps 17-19
+// issue the bulk copies.  Pipeline per frame f (stage = f & 1): workers write A[f+1] -> mbarrier A_full ->
 // MMA warp issues 3*nck/2 tcgen05.mma into accumulator (f+1)&1 -> tcgen05.commit -> mbarrier acc_full ->
 // workers tcgen05.ld, recursion, mbarrier acc_empty.  The MMAs of frame f+1 overlap the recursion of frame f.
 #include "tc_common.cuh"

@@ -60,7 +60,18 @@ class HMM:
         return st
 
     def __setstate__(self, st):
+        """Also accepts the state of a pickle written by the reference's own train.py (custom_hmm.py:10-33
+        attributes only: no ``semantics`` / ``precision`` / device handles) -- those get the constructor defaults."""
         self.__dict__.update(st)
+        if "semantics" not in st:
+            self.semantics = os.environ.get("SAPR_SEMANTICS", "sapr")
+        if "precision" not in st:
+            self.precision = "fp64" if os.environ.get("SAPR_FP64_VERIFY", "0") == "1" else "fp32"
+        if "total_states" not in st and "num_states" in st:
+            self.total_states = st["num_states"] + 2
+        if "pi" not in st and "num_states" in st:
+            self.pi = np.zeros(self.total_states)
+            self.pi[0] = 1.0
         self._dev = None
         self._dev_key = None
 

@@ -69,7 +69,8 @@ def train_hmm(implementation: Literal["custom", "hmmlearn"] = "hmmlearn", num_st
             log_likelihoods = hmm.baum_welch(features[word], n_iter)
             trained_model = hmm
         elif implementation == "hmmlearn":
-            hmm = HMMLearnModel(num_states=num_states, model_name=word, n_iter=n_iter, min_covar=min_covar)
+            hmm = HMMLearnModel(num_states=num_states, model_name=word, n_iter=n_iter, min_covar=min_covar,
+                                feature_set=feature_set)
             trained_model, _ = hmm.fit(features[word])
             log_likelihoods = hmm.model.monitor_.history
         else:

@@ -144,6 +144,34 @@ def test_pickle_roundtrip(HMM, rung0, tmp_path):
     assert h2.decode(feats[0]) == h.decode(feats[0])
 
 
+def test_reference_written_pickle_decodes(HMM, monkeypatch):
+    """tests/golden/ref_heed_custom_2.pkl was written by the REFERENCE's custom_hmm.HMM through pickle.dump as in
+    train.py:74-78 (tools/make_golden.py::ref_pickle); it resolves ``custom_hmm.HMM`` through the INTEGRATION.md shim,
+    has no semantics / precision attributes, and must decode like the reference did (decoder.py:26-27, :42-47)."""
+    import os
+    import sys
+    import types
+    from conftest import GOLDEN, load_golden
+    import sapr_b200.custom_hmm as shim_target
+    shim = types.ModuleType("custom_hmm")
+    shim.HMM = shim_target.HMM
+    monkeypatch.setitem(sys.modules, "custom_hmm", shim)
+    monkeypatch.delenv("SAPR_SEMANTICS", raising=False)
+    with open(os.path.join(GOLDEN, "ref_heed_custom_2.pkl"), "rb") as f:
+        h = pickle.load(f)
+    assert isinstance(h, HMM) and h.semantics == "sapr" and h.model_name == "heed"
+    g = load_golden("ref_pickle")
+    feats = split_features(g)
+    for u, x in enumerate(feats):
+        sc, path = h.decode(x)
+        assert path == g["dec_paths"][u].tolist()
+        assert_close(sc, g["dec_scores"][u], 1e-9, what="score")
+    hist = h.baum_welch(feats, 1)              # the unpickled object trains, too
+    assert np.isfinite(hist[0])
+    buf = pickle.dumps(h)                      # and re-pickles without device handles
+    assert pickle.loads(buf).decode(feats[0])[1] == g["dec_paths"][0].tolist()
+
+
 # ------------------------------------------------------------------------------------------------
 # the reference's own assertions (assignment2/tests/test_foward_backward.py, test_training.py,
 # test_initialization.py, test_decode.py) against the drop-in class

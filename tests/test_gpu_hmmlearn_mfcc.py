@@ -136,6 +136,29 @@ def test_ergodic_tensor_core_score_vs_float64(cuda, S, D, peaked):
     assert abs(model.score(X, lengths, precision="tc") - ref.sum()) <= 5e-6 * abs(ref.sum())
 
 
+@pytest.mark.parametrize("S,D", [(256, 39), (64, 13)])
+def test_ergodic_tensor_core_score_vs_oracle(cuda, S, D):
+    """sapr_ergodic_score (tensor-core forward, csrc/ergodic_tc.cu) checked DIRECTLY against the CPU oracle's
+    hmmlearn-style forward (orc.emission_diag + orc.hl_forward), not against another kernel of this repository.
+    Same tolerance as the kernel's contract in include/sapr_b200.h: |d logP| <= 5e-6 |logP| + 2e-4 T."""
+    from sapr_b200.hmmlearn_hmm import GaussianHMM
+    rng = np.random.default_rng(1000 + S)
+    means = 2.0 * rng.standard_normal((S, D)); var = rng.uniform(0.5, 1.5, (S, D)) ** 2
+    tm = rng.dirichlet(np.ones(S), size=S); sp = rng.dirichlet(np.ones(S))
+    lengths = [1, 2, 17, 40, 63, 5, 33, 90] + [int(x) for x in rng.integers(3, 50, size=140)]   # > one 128-row tile
+    states = rng.integers(0, S, size=sum(lengths))
+    X = (means[states] + np.sqrt(var[states]) * rng.standard_normal((sum(lengths), D))).astype(np.float32)
+    model = GaussianHMM(n_components=S, covariance_type="diag", n_iter=1, init_params="")
+    model.means_, model.covars_, model.transmat_, model.startprob_ = means, var, tm, sp
+    got = model.score_each(X, lengths, precision="tc").cpu().numpy()
+    offs = np.concatenate([[0], np.cumsum(lengths)])
+    ref = np.array([orc.hl_forward(orc.emission_diag(X[a:b].T, means, var, all_emit=True), sp, tm)[0]
+                    for a, b in zip(offs[:-1], offs[1:])])
+    err = np.abs(got - ref)
+    tol = 5e-6 * np.abs(ref) + 2e-4 * np.asarray(lengths)
+    assert np.isfinite(got).all() and (err <= tol).all(), (err.max(), (err / tol).max())
+
+
 def test_fit_vs_oracle(cuda, rung1_d13):
     model, X, lengths, (means, var, tm, sp) = _setup(rung1_d13, w=2)
     offs = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)

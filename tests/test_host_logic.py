@@ -47,6 +47,36 @@ def test_no_cpu_fallback():
     assert _lib.load().sapr_ctx_create(0, None, ctypes.byref(h)) != 0
 
 
+def test_reference_written_pickle_loads(monkeypatch):
+    """A pickle written by the reference's train.py (tests/golden/ref_heed_custom_2.pkl, made by
+    tools/make_golden.py::ref_pickle from the reference's own class) unpickles through the custom_hmm shim into a
+    usable drop-in object: attributes of custom_hmm.py:10-33 kept, mode attributes defaulted."""
+    import pickle
+    import types
+    import sapr_b200.custom_hmm as target
+    shim = types.ModuleType("custom_hmm")
+    shim.HMM = target.HMM
+    monkeypatch.setitem(sys.modules, "custom_hmm", shim)
+    monkeypatch.delenv("SAPR_SEMANTICS", raising=False)
+    monkeypatch.delenv("SAPR_FP64_VERIFY", raising=False)
+    with open(os.path.join(ROOT, "tests", "golden", "ref_heed_custom_2.pkl"), "rb") as f:
+        h = pickle.load(f)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_pickle.npz"))
+    assert isinstance(h, target.HMM)
+    assert (h.semantics, h.precision, h._dev, h._dev_key) == ("sapr", "fp32", None, None)
+    assert (h.num_states, h.num_obs, h.total_states, h.model_name) == (8, 13, 10, "heed")
+    assert np.array_equal(h.A, g["A"]) and np.array_equal(h.B["mean"], g["mean"])
+    assert h.B["covariance"].shape == (10, 13, 13) and h.pi[0] == 1.0
+    assert h._prec() == target.FP32
+    # a bare reference-shaped state dict (no pickle) takes the same route
+    st = {k: v for k, v in h.__dict__.items() if k not in ("semantics", "precision", "_dev", "_dev_key")}
+    h2 = target.HMM.__new__(target.HMM)
+    monkeypatch.setenv("SAPR_SEMANTICS", "standard")
+    h2.__setstate__(st)
+    assert h2.semantics == "standard" and h2._dev is None
+    assert set(pickle.loads(pickle.dumps(h2)).__dict__) >= set(st)
+
+
 def test_product_never_imports_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "sapr_b200")):
         for f in files:

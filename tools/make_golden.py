@@ -238,9 +238,36 @@ def edge_cases():
     print("edge_cases:", len(out), "arrays")
 
 
+def ref_pickle():
+    """A model pickle exactly as the reference's train.py:74-78 writes it (pickle.dump of the reference's own
+    ``custom_hmm.HMM`` object after baum_welch), plus what the reference's decode returns with that object."""
+    import pickle
+    N, D, B = 8, 13, 6
+    feats32, labels, mu, sd = synth.make_corpus(B, 1, N, D, 30, 40, seed=20241118 + 7)
+    feats = [f.astype(np.float64) for f in feats32]
+    hmm = RefHMM(N, D, feats, model_name="heed")
+    with np.errstate(all="ignore"):
+        quiet(hmm.baum_welch, feats, 2)
+    with open(os.path.join(OUT, "ref_heed_custom_2.pkl"), "wb") as f:
+        pickle.dump(hmm, f)
+    X, offs = pack(feats32)
+    scores = np.zeros(B); paths = np.zeros((B, D), dtype=np.int32)
+    with np.errstate(all="ignore"):
+        for u in range(B):
+            sc, p = hmm.decode(feats[u])
+            scores[u] = sc; paths[u] = p
+    np.savez_compressed(os.path.join(OUT, "ref_pickle.npz"), X=X, offsets=offs, dec_scores=scores, dec_paths=paths,
+                        A=hmm.A, mean=hmm.B["mean"], cov=hmm.B["covariance"])
+    print("ref_pickle: state keys", sorted(hmm.__dict__))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "ref_pickle":
+        ref_pickle()
+        sys.exit(0)
     rung0()
     rung1("rung1_d39", N=8, D=39, M=11, B=22, T_lo=40, T_hi=60, seed=20241118 + 2, a_self=0.9)
     rung1("rung1_d13", N=8, D=13, M=11, B=33, T_lo=24, T_hi=40, seed=20241118 + 3, a_self=0.85)
     edge_cases()
+    ref_pickle()
