@@ -2,6 +2,7 @@
 // mbarrier / bulk-copy / tcgen05 (alloc, mma, ld, st, commit, fences), packed fp32x2 arithmetic, fp16 hi/lo packing,
 // the no-swizzle K-major shared-memory matrix descriptor.
 #pragma once
+#include <cuda.h>          /* CUtensorMap type + enums only: the encoder is fetched through cudaGetDriverEntryPoint */
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -99,6 +100,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uin
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// TMA tensor-map tile load (3-D box) global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap *tmap, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst_smem), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 // bulk prefetch global -> L2: extends the bytes in flight beyond what the shared-memory ring can hold
 __device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
@@ -176,6 +186,15 @@ __device__ __forceinline__ uint32_t pack_h2(float2 a) {
     return r;
 }
 __device__ __forceinline__ float2 unpack_h2(uint32_t h) { return __half22float2(*reinterpret_cast<__half2 *>(&h)); }
+// a - (fp32)h, per element, as ONE mixed-precision FMA each (FHFMA: fp32 = half * half + fp32 with the constant -1):
+// the residual of an fp16 split without converting the hi part back to fp32 first
+__device__ __forceinline__ float2 residual_h2(float2 a, uint32_t h) {
+    float2 r;
+    asm("{\n\t.reg .b16 h0, h1, m1;\n\tmov.b32 {h0, h1}, %2;\n\tmov.b16 m1, 0xBC00;\n\t"
+        "fma.rn.f32.f16 %0, h0, m1, %3;\n\tfma.rn.f32.f16 %1, h1, m1, %4;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "r"(h), "f"(a.x), "f"(a.y));
+    return r;
+}
 
 // K-major, no-swizzle ("interleave") shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // core matrix = 8 rows x 16 bytes stored contiguously (128 B); LBO = byte distance between the two core
@@ -189,3 +208,28 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;                 // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (bits 61-63 = 0)
 }
 
+// ------------------------------------------------------------------------------------------------
+// host: 3-D fp32 tensor map (innermost dimension first).  The encoder lives in libcuda; it is looked up at run time so
+// the library links against cudart only.  Boxes may reach past the tensor: out-of-range elements arrive as zeros.
+typedef CUresult (*sapr_tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static inline int sapr_tmap_f32_3d(sapr_ctx *ctx, CUtensorMap *out, const void *base, const uint64_t (&dim)[3],
+                                   const uint64_t (&stride_bytes)[2], const uint32_t (&box)[3]) {
+    static sapr_tmap_encode_fn enc = nullptr;
+    if (!enc) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        SAPR_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        if (!fn || qr != cudaDriverEntryPointSuccess) SAPR_FAIL(ctx, SAPR_E_CUDA, "cuTensorMapEncodeTiled not available");
+        enc = (sapr_tmap_encode_fn)fn;
+    }
+    const cuuint64_t gd[3] = {dim[0], dim[1], dim[2]};
+    const cuuint64_t gs[2] = {stride_bytes[0], stride_bytes[1]};
+    const cuuint32_t bx[3] = {box[0], box[1], box[2]};
+    const cuuint32_t es[3] = {1, 1, 1};
+    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) SAPR_FAIL(ctx, SAPR_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return SAPR_OK;
+}

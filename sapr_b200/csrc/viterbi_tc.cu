@@ -601,6 +601,330 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_viterbi_tma: the same pipeline for EQUAL-LENGTH batches stored contiguously (total_frames == B * T, the shape of
+// BASELINE cfg 2): the raw-feature ring is filled by TMA tensor-map tile loads -- one cp.async.bulk.tensor.3d per frame of
+// a tile (box = [row width] x 1 frame x 128 utterances) issued by ONE thread -- instead of 128 per-row bulk copies per
+// stage from three polling copy warps (which were 12 % of the issued instructions of k_viterbi_tc).  The box is one
+// 16-byte chunk wider than the K extent of the A operand, so rows land at an odd multiple of 16 bytes (conflict-free
+// LDS.128 with one row per lane) and the columns past the feature row arrive as zeros; utterances past the end of the
+// batch arrive as zero rows, so the worker loops carry no per-row activity tests.  18 warps (16 workers, MMA, TMA) leave
+// 112 registers per thread: the standardisation constants of a thread's feature chunks and the transition constants of
+// its models stay in registers for the specialised splits.  The lo halves of the fp16 split come from one mixed-precision
+// FMA per element (FHFMA: x - (fp32)hi) instead of unpack + subtract.
+#define TM_THREADS (TC_WORKERS + 64)
+#ifndef TM_TR_IN_REGS
+#define TM_TR_IN_REGS 0
+#endif
+#ifndef TM_SB_IN_REGS
+#define TM_SB_IN_REGS 0
+#endif
+struct TmSmem { uint32_t w, raw, tr, sb, bar, total; };
+__host__ __device__ inline TmSmem tm_smem_layout(int M, int nck, int ncols, int nst, int F, uint32_t rw) {
+    TmSmem L;
+    L.w = 0;
+    L.raw = ((uint32_t)2 * (ncols / 8) * nck * 128 + 127u) & ~127u;
+    L.tr = L.raw + (uint32_t)nst * F * TC_ROWS * rw;
+    L.sb = L.tr + (uint32_t)M * TC_TRQ * 16;
+    L.bar = (L.sb + (uint32_t)8 * nck * 4 + 15u) & ~15u;
+    L.total = L.bar + (2 * TC_MAX_STAGES + 6) * 8 + 16;
+    return L;
+}
+
+template <int MG, int NKS>
+__global__ void __launch_bounds__(TM_THREADS, 1) k_viterbi_tma(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int nck = p.nck, ncols = p.ncols, M = p.M;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int F = 1 << p.Fshift, nst = 1 << p.nst_shift;
+    const uint32_t rw = p.rstride;                                   // bytes per row in the ring: (nck + 1) * 16
+    const uint32_t frame_bytes = TC_ROWS * rw, stage_bytes = (uint32_t)F * frame_bytes;
+    const TmSmem L = tm_smem_layout(M, nck, ncols, nst, F, rw);
+    const uint32_t w_plane = (uint32_t)(ncols / 8) * nck * 128;
+    unsigned char *sW = smem + L.w;
+    unsigned char *sRaw = smem + L.raw;
+    const float4 *sTr = reinterpret_cast<const float4 *>(smem + L.tr);
+    const float4 *sS = reinterpret_cast<const float4 *>(smem + L.sb);
+    uint64_t *sBar = reinterpret_cast<uint64_t *>(smem + L.bar);
+    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 2 * TC_MAX_STAGES + 6);
+    const uint32_t barRaw_full = smem_u32(sBar), barRaw_empty = barRaw_full + 8 * TC_MAX_STAGES;
+    const uint32_t barA_full = barRaw_empty + 8 * TC_MAX_STAGES, barAcc_full = barA_full + 24;
+
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.wimg);
+        uint4 *dst = reinterpret_cast<uint4 *>(sW);
+        for (uint32_t i = tid; i < 2 * w_plane / 16; i += TM_THREADS) dst[i] = src[i];
+        float4 *dtr = reinterpret_cast<float4 *>(smem + L.tr);
+        for (int i = tid; i < M * TC_TRQ; i += TM_THREADS) dtr[i] = p.trp[i];
+        float *dsb = reinterpret_cast<float *>(smem + L.sb);
+        for (int i = tid; i < 8 * nck; i += TM_THREADS) dsb[i] = p.sb[i];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < nst; s++) {
+            mbar_init(barRaw_full + 8 * s, 1);
+            mbar_init(barRaw_empty + 8 * s, TC_WORKER_WARPS);
+        }
+        for (int s = 0; s < 3; s++) mbar_init(barA_full + 8 * s, TC_WORKER_WARPS);
+        for (int s = 0; s < 2; s++) mbar_init(barAcc_full + 8 * s, 1);
+        fence_barrier_init();
+    }
+    const uint32_t a_cols = 8u * nck;
+    uint32_t tcols = 32;
+    while (tcols < 2u * ncols + 3u * a_cols) tcols <<= 1;
+    if (warp == TC_WORKER_WARPS) tmem_alloc(smem_u32(sTmem), tcols);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sTmem;
+    const uint32_t tmem_acc = tmem_base, tmem_a = tmem_base + 2u * ncols;
+
+    const int ntiles = (p.nu + TC_ROWS - 1) / TC_ROWS;
+    const int Tt = p.maxT;               // frames walked: the same for every utterance
+    uint32_t f = 0, sg = 0;
+
+    if (warp == TC_WORKER_WARPS + 1) {
+        // ===================== TMA producer: one thread =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap);
+            const int nsg = (Tt + F - 1) >> p.Fshift;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int urow = p.u0 + tile * TC_ROWS;
+                for (int k = 0; k < nsg; k++, sg++) {
+                    const uint32_t slot = sg & (uint32_t)(nst - 1), ph = (sg >> p.nst_shift) & 1u;
+                    const uint32_t bar = barRaw_full + 8 * slot;
+                    const int nf = min(F, Tt - k * F);
+                    mbar_wait(barRaw_empty + 8 * slot, ph ^ 1u);
+                    mbar_arrive_tx(bar, (uint32_t)nf * frame_bytes);
+                    const uint32_t dst = smem_u32(sRaw) + slot * stage_bytes;
+                    for (int fi = 0; fi < nf; fi++) tma_load_3d(dst + (uint32_t)fi * frame_bytes, &tmap, 0, k * F + fi, urow, bar);
+                }
+            }
+        }
+    } else if (warp == TC_WORKER_WARPS) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+        const uint32_t sW_hi = smem_u32(sW), sW_lo = sW_hi + w_plane;
+        const uint32_t sboW = (uint32_t)nck * 128u;
+        const uint64_t dW_hi = make_desc(sW_hi, 128, sboW), dW_lo = make_desc(sW_lo, 128, sboW);
+        const int nks = nck / 2;
+        uint32_t a3 = 0, aph = 0;
+        const int nfr = Tt * ((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);   // frames this CTA walks
+        for (int i = 0; i < nfr; i++, f++) {
+            const uint32_t s = f & 1;
+            mbar_wait(barA_full + 8 * a3, aph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d_tmem = tmem_acc + s * (uint32_t)ncols;
+                const uint32_t a_hi = tmem_a + a3 * a_cols, a_lo = a_hi + 8u;
+                if (NKS > 0) {
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_lo + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, ks > 0);
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_lo + (uint64_t)(16 * ks), idesc, 1);
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, 1);
+                } else {
+                    uint64_t dh = dW_hi, dl = dW_lo;
+                    uint32_t a = a_lo;
+                    for (int ks = 0; ks < nks; ks++, a += 16, dh += 16) umma_f16_ts(d_tmem, a, dh, idesc, ks > 0);
+                    a = a_hi;
+                    for (int ks = 0; ks < nks; ks++, a += 16, dl += 16) umma_f16_ts(d_tmem, a, dl, idesc, 1);
+                    a = a_hi; dh = dW_hi;
+                    for (int ks = 0; ks < nks; ks++, a += 16, dh += 16) umma_f16_ts(d_tmem, a, dh, idesc, 1);
+                }
+                umma_commit(barAcc_full + 8 * s);
+            }
+            __syncwarp();
+            if (++a3 == 3) { a3 = 0; aph ^= 1u; }
+        }
+    } else {
+        // ===================== workers =====================
+        const int q = warp & 3, g = warp >> 2, r = q * 32 + lane;
+        const int mbeg = p.mod0[g], mcnt = p.nmod[g];
+        const int pr0 = p.pair0[g], npr = p.npair[g];
+        const bool rec_first = g >= 2;
+        uint32_t c3 = 0;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const uint32_t ta0 = pin_reg(tmem_a + lane_sel + 16u * pr0);
+        const uint32_t acc0 = pin_reg(tmem_acc + lane_sel + (uint32_t)mbeg * 8u);
+        const uint32_t raw0 = pin_reg(smem_u32(sRaw) + (uint32_t)r * rw + 32u * pr0);
+        const uint32_t trS = smem_u32(sTr) + (uint32_t)mbeg * (TC_TRQ * 16u);
+        const uint32_t sbS = smem_u32(sS) + 32u * pr0;
+        const uint32_t sbB = sbS + 16u * nck;
+        // back-pointer scratch addressed with 32-bit element offsets (the scratch is bounded to 1 GB by the launcher)
+        const uint32_t bp_model = (uint32_t)p.maxT * (uint32_t)p.Bpad;
+        const uint32_t bp_frame = (uint32_t)p.Bpad;
+
+        auto lds4 = [](uint32_t a) -> float4 {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+            return v;
+        };
+        auto split4 = [&](const float4 x, const float4 sc, const float4 of, uint32_t *hi, uint32_t *lo) {
+            const float2 a01 = fma2(make_float2(x.x, x.y), make_float2(sc.x, sc.y), make_float2(of.x, of.y));
+            const float2 a23 = fma2(make_float2(x.z, x.w), make_float2(sc.z, sc.w), make_float2(of.z, of.w));
+            const float2 q01 = mul2(a01, a01), q23 = mul2(a23, a23);
+            hi[0] = pack_h2(a01); hi[1] = pack_h2(a23); hi[2] = pack_h2(q01); hi[3] = pack_h2(q23);
+            lo[0] = pack_h2(residual_h2(a01, hi[0])); lo[1] = pack_h2(residual_h2(a23, hi[1]));
+            lo[2] = pack_h2(residual_h2(q01, hi[2])); lo[3] = pack_h2(residual_h2(q23, hi[3]));
+        };
+
+        auto run = [&](auto NPc, auto MCc) {
+            constexpr int NPT = decltype(NPc)::value, MCT = decltype(MCc)::value;
+            constexpr bool SPEC = NPT > 0 && TM_TR_IN_REGS;      // specialised split: transition constants live in registers
+            constexpr int NPMAX = NPT > 0 ? NPT : 2, MCMAX = MCT > 0 ? MCT : MG;
+            const int np = NPT > 0 ? NPT : npr, mc = MCT > 0 ? MCT : mcnt;
+            const uint32_t recf = pin_reg(rec_first ? 1u : 0u);
+            uint32_t as = 0, aph = 0;
+            // register-resident constants (specialised splits only)
+            constexpr bool SBREG = SPEC && TM_SB_IN_REGS;     // standardisation constants in registers, too
+            float4 rsc[SBREG ? 2 * NPMAX : 1], rof[SBREG ? 2 * NPMAX : 1];
+            float4 rc03[SPEC ? MCMAX : 1];
+            if (SBREG) {
+#pragma unroll
+                for (int c = 0; c < 2 * NPMAX; c++) { rsc[c] = lds4(sbS + 16u * c); rof[c] = lds4(sbB + 16u * c); }
+            }
+            if (SPEC) {
+#pragma unroll
+                for (int k = 0; k < MCMAX; k++) {
+                    rc03[k] = lds4(trS + (TC_TRQ * 16u) * k);
+                }
+            }
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int ul = tile * TC_ROWS + r;
+                const bool live = ul < p.nu;
+                float2 U[MCMAX][4];
+                float Ux[MCMAX], base[MCMAX];
+                uint32_t bpo = (uint32_t)mbeg * bp_model + (uint32_t)ul;
+#pragma unroll
+                for (int k = 0; k < MCMAX; k++) {
+                    Ux[k] = -INFINITY; base[k] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) U[k][j] = make_float2(-INFINITY, -INFINITY);
+                }
+                int cfi = 0, ct = 0;
+                uint32_t cslot = sg & (uint32_t)(nst - 1), crph = (sg >> p.nst_shift) & 1u;
+                uint32_t crow = raw0 + cslot * stage_bytes;
+                auto convert = [&]() {
+                    if (cfi == 0) mbar_wait(barRaw_full + 8 * cslot, crph);
+                    const uint32_t ta = ta0 + c3 * a_cols;
+#pragma unroll
+                    for (int c = 0; c < NPMAX; c++) {
+                        if (c < np) {
+                            const float4 x0 = lds4(crow + 32u * c), x1 = lds4(crow + 32u * c + 16u);
+                            uint32_t v[16];
+                            if (SBREG) {
+                                split4(x0, rsc[2 * c], rof[2 * c], v, v + 8);
+                                split4(x1, rsc[2 * c + 1], rof[2 * c + 1], v + 4, v + 12);
+                            } else {
+                                split4(x0, lds4(sbS + 32u * c), lds4(sbB + 32u * c), v, v + 8);
+                                split4(x1, lds4(sbS + 32u * c + 16u), lds4(sbB + 32u * c + 16u), v + 4, v + 12);
+                            }
+                            tmem_st16(ta + 16u * c, v);
+                        }
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    const bool last = (cfi == F - 1) || (ct == Tt - 1);
+                    if (lane == 0) {
+                        mbar_arrive(barA_full + 8 * c3);
+                        if (last) mbar_arrive(barRaw_empty + 8 * cslot);
+                    }
+                    if (++c3 == 3) c3 = 0;
+                    ct++;
+                    if (last) {
+                        cfi = 0; sg++;
+                        if (++cslot == (uint32_t)nst) { cslot = 0; crph ^= 1u; }
+                        crow = raw0 + cslot * stage_bytes;
+                    } else {
+                        cfi++; crow += frame_bytes;
+                    }
+                };
+                auto acc_ready = [&]() -> uint32_t {
+                    mbar_wait(barAcc_full + 8 * as, aph);
+                    tc_fence_after();
+                    return acc0 + as * (uint32_t)ncols;
+                };
+                auto acc_next = [&]() { aph ^= as; as ^= 1u; };
+
+                if (Tt > 0) convert();
+                if (recf && Tt > 1) convert();
+                const int Tearly = min(Tt, 9);
+                int t = 0;
+                for (; t < Tearly; t++) {
+                    if (!recf && t + 1 < Tt) convert();
+                    const uint32_t tacc = acc_ready();
+                    acc_next();
+#pragma unroll
+                    for (int k = 0; k < MCMAX; k++) {
+                        if (k < mc) {
+                            uint32_t ev[8];
+                            tmem_ld8(tacc + 8u * k, ev);
+                            tmem_ld_wait();
+                            const float4 cm = lds4(trS + (TC_TRQ * 16u) * k + 32u);
+                            if (t == 0) {
+                                U[k][0].x = cm.y + __uint_as_float(ev[0]);
+                            } else {
+                                const float4 c03 = lds4(trS + (TC_TRQ * 16u) * k), c47 = lds4(trS + (TC_TRQ * 16u) * k + 16u);
+                                const uint32_t bits = vit_step<true>(U[k], Ux[k], c03, c47, cm.x, cm.y, ev, t);
+                                p.bp[bpo + (uint32_t)k * bp_model] = (uint16_t)bits;
+                                if ((t & 3) == 0) vit_renorm(U[k], Ux[k], base[k]);
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    bpo += bp_frame;
+                    if (recf && t + 2 < Tt) convert();
+                }
+                for (; t < Tt; t++) {
+                    if (!recf && t + 1 < Tt) convert();
+                    const uint32_t tacc = acc_ready();
+                    acc_next();
+                    const bool rn = (t & 7) == 0;
+#pragma unroll
+                    for (int k = 0; k < MCMAX; k++) {
+                        if (k < mc) {
+                            uint32_t ev[8];
+                            tmem_ld8(tacc + 8u * k, ev);
+                            tmem_ld_wait();
+                            uint32_t bits;
+                            if (SPEC) {
+                                float aex;
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(aex) : "r"(trS + (TC_TRQ * 16u) * k + 32u));
+                                bits = vit_step<false>(U[k], Ux[k], rc03[k], lds4(trS + (TC_TRQ * 16u) * k + 16u), aex, 0.f, ev, t);
+                            } else {
+                                const float4 c03 = lds4(trS + (TC_TRQ * 16u) * k), c47 = lds4(trS + (TC_TRQ * 16u) * k + 16u), cm = lds4(trS + (TC_TRQ * 16u) * k + 32u);
+                                bits = vit_step<false>(U[k], Ux[k], c03, c47, cm.x, cm.y, ev, t);
+                            }
+                            p.bp[bpo + (uint32_t)k * bp_model] = (uint16_t)bits;
+                            if (rn) vit_renorm(U[k], Ux[k], base[k]);
+                        }
+                    }
+                    tc_fence_before();
+                    bpo += bp_frame;
+                    if (recf && t + 2 < Tt) convert();
+                }
+                if (live) {
+#pragma unroll
+                    for (int k = 0; k < MCMAX; k++)
+                        if (k < mc) {
+                            const double sc = (Tt > 0 && Ux[k] > -INFINITY) ? (double)Ux[k] + (double)base[k] : -INFINITY;
+                            p.scores[(size_t)ul * M + mbeg + k] = sc;
+                        }
+                }
+            }
+        };
+        if (MG == 3 && npr == 2 && mcnt == 2) run(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{});
+        else if (MG == 3 && npr == 1 && mcnt == 3) run(std::integral_constant<int, 1>{}, std::integral_constant<int, 3>{});
+        else run(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_WORKER_WARPS) tmem_dealloc(tmem_base, tcols);
+}
+
+// ------------------------------------------------------------------------------------------------
 bool sapr_tc_eligible(const sapr_models *m) {
     return m->emission == SAPR_EMIT_DIAG && m->topology == SAPR_TOPO_ENTRY_EXIT && m->N == 8 && m->M <= 12 &&
            m->D + 1 <= 48;
@@ -683,6 +1007,34 @@ int sapr_viterbi_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
     L = tc_smem_layout(M, nck, ncols, nst, rstride);
     const size_t smem = L.total;
     const int MG = (M + TC_GROUPS - 1) / TC_GROUPS;
+    // equal-length contiguous batch (every utterance has max_T frames): TMA tensor-map loads, k_viterbi_tma
+    const char *tma_env = getenv("SAPR_TMA");
+    bool use_tma = !dbgE && Tm > 0 && total_frames == (int64_t)B * max_T && (!tma_env || tma_env[0] != '0') &&
+                   ((uintptr_t)X & 15u) == 0 && !getenv("SAPR_TC_TRACE");
+    const uint32_t tm_rw = (uint32_t)(nck + 1) * 16u;                 // ring row: K extent of the A operand + one chunk (odd multiple of 16 B)
+    int tm_Fshift = 3;
+    TmSmem TL = tm_smem_layout(M, nck, ncols, 2, 1 << tm_Fshift, tm_rw);
+    while (use_tma && TL.total > budget) {
+        if (tm_Fshift == 0) { use_tma = false; break; }
+        tm_Fshift--;
+        TL = tm_smem_layout(M, nck, ncols, 2, 1 << tm_Fshift, tm_rw);
+    }
+    CUtensorMap tmap;
+    if (use_tma) {
+        const uint64_t dim[3] = {(uint64_t)ldx, (uint64_t)max_T, (uint64_t)B};
+        const uint64_t str[2] = {(uint64_t)ldx * 4u, (uint64_t)max_T * ldx * 4u};
+        const uint32_t box[3] = {tm_rw / 4u, 1u, (uint32_t)TC_ROWS};
+        if ((rc = sapr_tmap_f32_3d(ctx, &tmap, X, dim, str, box))) return rc;
+    }
+    auto launch_tma = [&](auto kern, const TcParams &prm, int grid) -> int {
+        SAPR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL.total));
+        {
+            ProfScope ps(ctx, 0);
+            kern<<<grid, TM_THREADS, TL.total, ctx->stream>>>(prm, tmap);
+        }
+        SAPR_LAUNCH_CHECK(ctx);
+        return SAPR_OK;
+    };
     auto launch = [&](auto kern, const TcParams &prm, int grid) -> int {
         SAPR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
@@ -745,6 +1097,14 @@ int sapr_viterbi_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
         }
         const int ntiles = (nu + TC_ROWS - 1) / TC_ROWS;
         const int grid = std::min(ntiles, ctx->sm_count);
+        if (use_tma) {
+            prm.Fshift = tm_Fshift; prm.nst_shift = 1; prm.rstride = tm_rw;
+            if (MG <= 1) rc = launch_tma(k_viterbi_tma<1, 0>, prm, grid);
+            else if (MG <= 2) rc = launch_tma(k_viterbi_tma<2, 0>, prm, grid);
+            else if (nck == 10) rc = launch_tma(k_viterbi_tma<3, 5>, prm, grid);
+            else if (nck == 4) rc = launch_tma(k_viterbi_tma<3, 2>, prm, grid);
+            else rc = launch_tma(k_viterbi_tma<3, 0>, prm, grid);
+        } else
         if (dbgE) rc = launch(k_viterbi_tc<3, 0, true>, prm, grid);
         else if (MG <= 1) rc = launch(k_viterbi_tc<1, 0, false>, prm, grid);
         else if (MG <= 2) rc = launch(k_viterbi_tc<2, 0, false>, prm, grid);

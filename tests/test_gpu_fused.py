@@ -264,6 +264,41 @@ def test_moderate_batch_against_oracle(eng):
     assert_close(tot.cpu().numpy(), full.cpu().numpy(), 1e-12, atol=1e-9, what="sharded stats")
 
 
+@pytest.mark.parametrize("B,M,D,T,first", [(300, 11, 39, 37, 0), (129, 5, 13, 24, 0), (128, 11, 39, 9, 0), (77, 3, 20, 8, 0),
+                                           (260, 11, 13, 40, 13)])
+def test_viterbi_equal_length_batch_tma_vs_oracle(eng, B, M, D, T, first, monkeypatch):
+    """Equal-length batches (the BASELINE cfg-2 shape) take the TMA tensor-map kernel k_viterbi_tma: words, scores and
+    paths against the CPU oracle (custom_hmm.py:462-514 x all models + decoder.py:42-47); batch sizes that are not a
+    multiple of the 128-utterance tile (zero-filled rows), T down to N (exit never reachable: -inf), first_frames (D3);
+    and the per-row bulk-copy kernel (SAPR_TMA=0) must agree with it on words and to 1e-6 on scores."""
+    from sapr_b200 import synth
+    feats, labels, mu, sd = synth.make_corpus(B, M, 8, D, T, T, seed=1000 + B + T)
+    A, means, var = synth.truth_models(mu, sd, 0.9)
+    m = eng.WordModels(M, 8, D)
+    m.set(means, var, A)
+    batch = eng.PackedBatch.from_features(feats)
+    X, offs = orc.pack(feats)
+    bw, bs, sc, bp = orc.viterbi_batch(X, offs, A, means, var, first_frames=first)
+    l0 = m.ctx.launches()
+    out = m.viterbi(batch, None, eng.FP32, first, want_scores=True, want_path=True)
+    assert m.ctx.launches() > l0
+    got = out["scores"].cpu().numpy()
+    assert_close(got, sc, 1e-6, what="scores (tma)")
+    w = out["best_word"].cpu().numpy()
+    for u in np.nonzero(w != bw)[0]:
+        assert abs(sc[u, w[u]] - sc[u, bw[u]]) < 1e-5 * abs(sc[u, bw[u]]), u
+    assert np.sum(w != bw) <= 1
+    walked = first if first else T
+    pg = out["path"].cpu().numpy().astype(np.int32).reshape(B, T)[:, :walked]
+    pr = bp.reshape(B, T)[:, :walked] if bp.size == B * T else bp.reshape(B, -1)[:, :walked]
+    if np.isfinite(sc).all():
+        assert np.mean(pg == pr) > 0.999, np.mean(pg == pr)
+    monkeypatch.setenv("SAPR_TMA", "0")
+    out0 = m.viterbi(batch, None, eng.FP32, first, want_scores=True, want_path=True)
+    assert_close(out0["scores"].cpu().numpy(), got, 1e-6, what="scores (bulk-copy kernel vs tma kernel)")
+    assert np.mean(out0["best_word"].cpu().numpy() == w) > 0.995
+
+
 def test_estep_short_and_ragged_utterances_tc_vs_float64(eng):
     """The tensor-core E-step (fp32) against the float64 verification kernel on the shapes the reference's own
     recursions treat specially: T = 1, 2 (gamma rows NaN / one-hot, custom_hmm.py:252-255), T <= N (exit state
