@@ -36,6 +36,8 @@ struct sapr_ctx {
     struct ProfRec { cudaEvent_t a, b; int which; };
     std::vector<ProfRec> prof;       // used records
     std::vector<ProfRec> prof_pool;  // recycled event pairs
+    // sapr_estep_grouped: the tile table of the last call (re-uploaded only when the grouping changes)
+    std::vector<int32_t> eg_tab;
 };
 
 // RAII bracket: records an event pair around one kernel launch when profiling is on

@@ -299,6 +299,47 @@ def test_viterbi_equal_length_batch_tma_vs_oracle(eng, B, M, D, T, first, monkey
     assert np.mean(out0["best_word"].cpu().numpy() == w) > 0.995
 
 
+@pytest.mark.parametrize("B,M,D,T", [(700, 11, 39, 40), (150, 3, 13, 24), (1300, 11, 39, 16), (260, 5, 20, 33)])
+def test_estep_grouped_fused_vs_oracle(eng, B, M, D, T):
+    """Fused grouped E-step (csrc/estep_grouped.cu: forward sweep, backward sweep with Gamma^T.[x, x^2, 1] on the tensor
+    cores) against the CPU oracle (custom_hmm.py:417-439 + :372-386 restated): log-likelihoods, occupancies, xi sums and
+    the feature sums; model groups that do not fill a 128-utterance tile, several tiles per model, an empty model."""
+    import torch
+    from sapr_b200 import synth
+    feats, labels, mu, sd = synth.make_corpus(B, M, 8, D, T, T, seed=500 + B)
+    labels = np.asarray(labels).copy()
+    if M == 5:
+        labels[labels == 2] = 3                                   # model 2 gets no utterance at all
+    A, means, var = synth.truth_models(mu, sd, 0.9)
+    # evaluate away from the generating parameters, like an early Baum-Welch iteration
+    rng = np.random.default_rng(B)
+    means = means + 0.3 * np.sqrt(var) * rng.standard_normal(means.shape)
+    m = eng.WordModels(M, 8, D)
+    m.set(means, var, A)
+    batch = eng.PackedBatch.from_features(feats)
+    lab = torch.as_tensor(labels.astype(np.int32), device="cuda")
+    gb = eng.GroupedBatch(batch, lab, M)
+    stats, ll = m.estep_grouped(gb.X, gb.T, gb.model_start)
+    order = gb.order.cpu().numpy()
+    X, offs = orc.pack([feats[i] for i in order])
+    ost, oll = orc.estep_batch(X, offs, labels[order], A, means, var)
+    assert_close(ll.cpu().numpy(), oll, 1e-6, what="loglik")
+    st = stats.cpu().numpy()
+    S = 10
+    # G, Xi, occ: sums of posteriors over up to B*T/M frames
+    assert np.max(np.abs(st[:, :3 * S] - ost[:, :3 * S])) < 3e-5 * T * max(1, B // M), "occupancies"
+    occ = np.maximum(ost[:, 2 * S:3 * S], 1.0)                    # (M, S)
+    s1 = st[:, 3 * S:3 * S + S * D].reshape(M, S, D); o1 = ost[:, 3 * S:3 * S + S * D].reshape(M, S, D)
+    s2 = st[:, 3 * S + S * D:].reshape(M, S, D); o2 = ost[:, 3 * S + S * D:].reshape(M, S, D)
+    sig = np.sqrt(var)
+    # per-frame mean shift rel. to sigma <= 1e-4, second moment rel. to sigma^2 <= 1e-3 (the M-step tolerances)
+    assert np.max(np.abs(s1 - o1) / (occ[:, :, None] * sig)) < 1e-4, np.max(np.abs(s1 - o1) / (occ[:, :, None] * sig))
+    assert np.max(np.abs(s2 - o2) / (occ[:, :, None] * var)) < 1e-3, np.max(np.abs(s2 - o2) / (occ[:, :, None] * var))
+    # and against the general path of this library (k_estep_tc + k_stats_diag8) after the M-step both feed
+    stats_g, ll_g, _ = m.estep(batch, lab, None, eng.FP32)
+    assert_close(ll.cpu().numpy(), ll_g.cpu().numpy()[order], 1e-6, what="loglik vs general path")
+
+
 def test_estep_short_and_ragged_utterances_tc_vs_float64(eng):
     """The tensor-core E-step (fp32) against the float64 verification kernel on the shapes the reference's own
     recursions treat specially: T = 1, 2 (gamma rows NaN / one-hot, custom_hmm.py:252-255), T <= N (exit state
