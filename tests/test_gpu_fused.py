@@ -327,7 +327,9 @@ def test_estep_grouped_fused_vs_oracle(eng, B, M, D, T):
     st = stats.cpu().numpy()
     S = 10
     # G, Xi, occ: sums of posteriors over up to B*T/M frames
-    assert np.max(np.abs(st[:, :3 * S] - ost[:, :3 * S])) < 3e-5 * T * max(1, B // M), "occupancies"
+    d3 = np.abs(st[:, :3 * S] - ost[:, :3 * S])
+    assert np.max(d3) < 3e-5 * T * max(1, B // M), ("occupancies", [float(d3[:, k * S:(k + 1) * S].max()) for k in range(3)],
+                                                    np.unravel_index(np.argmax(d3), d3.shape), st[:, :3 * S][d3 > 0.5], ost[:, :3 * S][d3 > 0.5])
     occ = np.maximum(ost[:, 2 * S:3 * S], 1.0)                    # (M, S)
     s1 = st[:, 3 * S:3 * S + S * D].reshape(M, S, D); o1 = ost[:, 3 * S:3 * S + S * D].reshape(M, S, D)
     s2 = st[:, 3 * S + S * D:].reshape(M, S, D); o2 = ost[:, 3 * S + S * D:].reshape(M, S, D)
