@@ -48,6 +48,8 @@ struct EgParams {
     double *loglik;                                   // [B]
     float *tpart;                                     // [ntiles][128][8]: per-tile sums, row = feature row of the A image
     uint32_t rw;                                      // bytes per row of the raw ring
+    int pfd;                                          // L2 prefetch distance in pipeline frames
+    int flags;                                        // tuning experiments (SAPR_EG_EXP): 1 = statistics right behind the emission, 2 = recursions skip their arithmetic, 4 = converters skip theirs
     long long *trace;
 };
 
@@ -62,7 +64,7 @@ __host__ __device__ inline EgSmem eg_smem_layout(int M, int nck, int nraw, uint3
     L.tr = L.gam + 2u * 4096u;                        // two posterior operands [16 row groups][2][8 rows][8 halves]
     L.sb = L.tr + (uint32_t)M * TC_TRQ * 16;
     L.bar = (L.sb + (uint32_t)8 * nck * 4 + 15u) & ~15u;
-    L.total = L.bar + (2 * EG_MAX_RAW + 2 * EG_A_STAGES + 12) * 8 + 16;
+    L.total = L.bar + (2 * EG_MAX_RAW + 3 * EG_A_STAGES + 12) * 8 + 16;
     return L;
 }
 
@@ -112,10 +114,11 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
     const uint32_t sA = smem_u32(smem + L.a), sRaw = smem_u32(smem + L.raw), sW = smem_u32(smem + L.w), sG = smem_u32(smem + L.gam);
     const float4 *sTr = reinterpret_cast<const float4 *>(smem + L.tr);
     uint64_t *sBar = reinterpret_cast<uint64_t *>(smem + L.bar);
-    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 2 * EG_MAX_RAW + 2 * EG_A_STAGES + 12);
+    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 2 * EG_MAX_RAW + 3 * EG_A_STAGES + 12);
     const uint32_t bRawFull = smem_u32(sBar), bRawEmpty = bRawFull + 8 * EG_MAX_RAW;
     const uint32_t bAFull = bRawEmpty + 8 * EG_MAX_RAW, bAFree = bAFull + 8 * EG_A_STAGES;
-    const uint32_t bAccFull = bAFree + 8 * EG_A_STAGES, bAccEmpty = bAccFull + 16;
+    const uint32_t bImgFree = bAFree + 8 * EG_A_STAGES;          // shared-memory image stages (backward frames only)
+    const uint32_t bAccFull = bImgFree + 8 * EG_A_STAGES, bAccEmpty = bAccFull + 16;
     const uint32_t bGamFull = bAccEmpty + 16, bGamFree = bGamFull + 16;
     const uint32_t bStFull = bGamFree + 16, bStEmpty = bStFull + 16;
 
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
     }
     if (tid == 0) {
         for (int s = 0; s < nraw; s++) { mbar_init(bRawFull + 8 * s, 1); mbar_init(bRawEmpty + 8 * s, EG_CONV_WARPS); }
-        for (int s = 0; s < EG_A_STAGES; s++) { mbar_init(bAFull + 8 * s, EG_CONV_WARPS); mbar_init(bAFree + 8 * s, 1); }
+        for (int s = 0; s < EG_A_STAGES; s++) { mbar_init(bAFull + 8 * s, EG_CONV_WARPS); mbar_init(bAFree + 8 * s, 1); mbar_init(bImgFree + 8 * s, 1); }
         for (int s = 0; s < 2; s++) {
             mbar_init(bAccFull + 8 * s, 1); mbar_init(bAccEmpty + 8 * s, EG_REC_WARPS);
             mbar_init(bGamFull + 8 * s, EG_REC_WARPS); mbar_init(bGamFree + 8 * s, 1);
@@ -141,13 +144,17 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
         }
         fence_barrier_init();
     }
-    if (warp == EG_MMA_WARP) tmem_alloc(smem_u32(sTmem), 64);
+    const uint32_t a_cols = 8u * nck;                             // TMEM columns of one A-operand stage: per K step [hi 8 | lo 8]
+    uint32_t tcols = 128;
+    while (tcols < 64u + EG_A_STAGES * a_cols) tcols <<= 1;
+    if (warp == EG_MMA_WARP) tmem_alloc(smem_u32(sTmem), tcols);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *sTmem;
     const uint32_t tmem_acc = tmem_base, tmem_st = tmem_base + 32u;    // 2 x 16 emission columns, 2 x 16 statistics columns
+    const uint32_t tmem_a = tmem_base + 64u;                           // EG_A_STAGES A-operand stages of the emission product
     const int npf = 2 * T;                                            // pipeline frames per tile: forward, then backward
 
     if (warp == EG_TMA_WARP) {
@@ -155,11 +162,23 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
         if (lane == 0) {
             tma_prefetch_desc(&tmap);
             Ring rr = {0, 0};
+            // L2 prefetch cursor: runs p.pfd pipeline frames ahead of the loads (over tile boundaries), so the ring's loads
+            // find their boxes in L2 -- the ring alone (nraw x 22 KB per SM) does not cover the HBM latency at this rate
+            int ptile = blockIdx.x, pi = 0;
+            auto prefetch_next = [&]() {
+                if (ptile >= p.ntiles) return;
+                const int t = pi < T ? pi : npf - 1 - pi;
+                tma_prefetch_l2_3d(&tmap, 0, t, p.tile_u0[ptile]);
+                if (++pi == npf) { pi = 0; ptile += gridDim.x; }
+            };
+            for (int k = 0; k < p.pfd; k++) prefetch_next();
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 const int u0 = p.tile_u0[tile];
                 for (int i = 0; i < npf; i++) {
                     const int t = i < T ? i : npf - 1 - i;
+                    if (p.pfd > 0) prefetch_next();
                     mbar_wait(bRawEmpty + 8 * rr.s, rr.ph ^ 1u);
+                    if (p.flags & 16) { mbar_arrive(bRawFull + 8 * rr.s); rr.next((uint32_t)nraw); continue; }   // tuning experiment: no loads
                     mbar_arrive_tx(bRawFull + 8 * rr.s, frame_bytes);
                     tma_load_3d(sRaw + rr.s * frame_bytes, &tmap, 0, t, u0, bRawFull + 8 * rr.s);
                     rr.next((uint32_t)nraw);
@@ -171,8 +190,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
         const uint32_t idesc_k = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);   // M = 128, N = 16, K-major
         const uint32_t idesc_mn = idesc_k | (1u << 15) | (1u << 16);                                            // both operands MN-major
         const int nks = nck / 2;
-        Ring ar = {0, 0}, cr = {0, 0}, gr = {0, 0}, sr = {0, 0};     // A stages, accumulator stages, posterior operands, statistics buffers
-        uint32_t a_prev = 0;                                          // A stage of the frame whose statistics are pending
+        Ring ar = {0, 0}, ir = {0, 0}, cr = {0, 0}, gr = {0, 0}, sr = {0, 0};   // TMEM A stages, image stages, accumulator stages, posterior operands, statistics buffers
         int kt = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, kt++) {
             const int m = p.tile_model[tile];
@@ -186,57 +204,72 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
                 fence_proxy_async();
                 __syncwarp();
             }
+            // Two product streams, issued greedily by this one warp: the emission of pipeline frame ei (needs its A image and
+            // a free accumulator stage) runs ahead; the statistics of backward frame si (needs the posteriors the recursion
+            // warps write, releases the A image) follow as soon as they can.  A fixed order would chain the two through the
+            // converters (statistics -> free A stage -> conversion -> emission).
             int sf = 0;                                               // statistics frames issued in this tile
-            auto stats_mma = [&](uint32_t astage) {
-                // Gamma^T . X of one frame: 8 K steps of 16 utterance rows, hi plane then lo plane
-                if (sf % EG_GROUP == 0) mbar_wait(bStEmpty + 8 * sr.s, sr.ph ^ 1u);
-                mbar_wait(bGamFull + 8 * gr.s, gr.ph);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t d = tmem_st + sr.s * 16u;
-                    const uint32_t ab = sA + astage * a_stage, gb = sG + gr.s * 4096u;
+            int ei = 0, si = T + 1;                                   // next emission frame, next statistics frame (pipeline indices)
+            uint32_t a_hist[4] = {0, 0, 0, 0};                        // A stage of pipeline frame k at [k & 3]
+            while (si < npf) {
+                bool did = false;
+                if (ei < npf && mbar_test(bAFull + 8 * ar.s, ar.ph) && mbar_test(bAccEmpty + 8 * cr.s, cr.ph ^ 1u)) {
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t d = tmem_acc + cr.s * 16u;
+                        const uint32_t a_hi = tmem_a + ar.s * a_cols, a_lo = a_hi + 8u;      // K step ks: hi at +16 ks, lo at +16 ks + 8
+                        if (NCH > 0) {
 #pragma unroll
-                    for (int ks = 0; ks < 8; ks++)
-                        umma_f16_ss(d, make_desc(ab + 2u * ks * rg_stride, rg_stride, 128), make_desc(gb + 2u * ks * 256u, 256, 128), idesc_mn,
-                                    (sf % EG_GROUP != 0 || ks > 0) ? 1u : 0u);
+                            for (int ks = 0; ks < NCH; ks++) umma_f16_ts(d, a_lo + 16u * ks, make_desc(wb + 256u * ks, 128, rg_stride), idesc_k, ks > 0);
 #pragma unroll
-                    for (int ks = 0; ks < 8; ks++)
-                        umma_f16_ss(d, make_desc(ab + a_plane + 2u * ks * rg_stride, rg_stride, 128), make_desc(gb + 2u * ks * 256u, 256, 128), idesc_mn, 1u);
-                    umma_commit(bAFree + 8 * astage);
-                    umma_commit(bGamFree + 8 * gr.s);
-                    if (sf % EG_GROUP == EG_GROUP - 1 || sf == T - 2) umma_commit(bStFull + 8 * sr.s);
-                }
-                __syncwarp();
-                if (sf % EG_GROUP == EG_GROUP - 1 || sf == T - 2) sr.next(2);
-                gr.next(2);
-                sf++;
-            };
-            for (int i = 0; i < npf; i++) {
-                mbar_wait(bAFull + 8 * ar.s, ar.ph);
-                mbar_wait(bAccEmpty + 8 * cr.s, cr.ph ^ 1u);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t d = tmem_acc + cr.s * 16u;
-                    const uint32_t ab = sA + ar.s * a_stage;
-                    if (NCH > 0) {
-#pragma unroll
-                        for (int ks = 0; ks < NCH; ks++) umma_f16_ss(d, make_desc(ab + a_plane + 256u * ks, 128, rg_stride), make_desc(wb + 256u * ks, 128, rg_stride), idesc_k, ks > 0);
-#pragma unroll
-                        for (int ks = 0; ks < NCH; ks++) umma_f16_ss(d, make_desc(ab + 256u * ks, 128, rg_stride), make_desc(wb + 256u * ks, 128, rg_stride), idesc_k, 1u);
-                    } else {
-                        for (int ks = 0; ks < nks; ks++) umma_f16_ss(d, make_desc(ab + a_plane + 256u * ks, 128, rg_stride), make_desc(wb + 256u * ks, 128, rg_stride), idesc_k, ks > 0);
-                        for (int ks = 0; ks < nks; ks++) umma_f16_ss(d, make_desc(ab + 256u * ks, 128, rg_stride), make_desc(wb + 256u * ks, 128, rg_stride), idesc_k, 1u);
+                            for (int ks = 0; ks < NCH; ks++) umma_f16_ts(d, a_hi + 16u * ks, make_desc(wb + 256u * ks, 128, rg_stride), idesc_k, 1u);
+                        } else {
+                            for (int ks = 0; ks < nks; ks++) umma_f16_ts(d, a_lo + 16u * ks, make_desc(wb + 256u * ks, 128, rg_stride), idesc_k, ks > 0);
+                            for (int ks = 0; ks < nks; ks++) umma_f16_ts(d, a_hi + 16u * ks, make_desc(wb + 256u * ks, 128, rg_stride), idesc_k, 1u);
+                        }
+                        umma_commit(bAccFull + 8 * cr.s);
+                        umma_commit(bAFree + 8 * ar.s);               // the TMEM operand is free once the emission product has read it
                     }
-                    umma_commit(bAccFull + 8 * cr.s);
-                    if (i <= T) umma_commit(bAFree + 8 * ar.s);       // forward frames and frame T-1 of the backward sweep carry no statistics
+                    __syncwarp();
+                    if (ei > T) { a_hist[ei & 3] = ir.s; ir.next(EG_A_STAGES); }   // backward frames with statistics also have a shared-memory image
+                    ar.next(EG_A_STAGES);
+                    cr.next(2);
+                    ei++;
+                    did = true;
                 }
-                __syncwarp();
-                if (i > T + 1) stats_mma(a_prev);                     // statistics of the previous backward frame (its posteriors exist by now)
-                a_prev = ar.s;
-                ar.next(EG_A_STAGES);
-                cr.next(2);
+                if (si < ei && mbar_test(bGamFull + 8 * gr.s, gr.ph) &&
+                    (sf % EG_GROUP != 0 || mbar_test(bStEmpty + 8 * sr.s, sr.ph ^ 1u))) {
+                    // Gamma^T . X of one frame: 8 K steps of 16 utterance rows, hi plane then lo plane
+                    tc_fence_after();
+                    const uint32_t astage = a_hist[si & 3];
+                    const bool last = sf % EG_GROUP == EG_GROUP - 1 || sf == T - 2;
+                    if (elect_one()) {
+                        const uint32_t d = tmem_st + sr.s * 16u;
+                        const uint32_t ab = sA + astage * a_stage, gb = sG + gr.s * 4096u;
+                        if (!(p.flags & 8)) {
+#pragma unroll
+                        for (int ks = 0; ks < 8; ks++)
+                            umma_f16_ss(d, make_desc(ab + 2u * ks * rg_stride, rg_stride, 128), make_desc(gb + 2u * ks * 256u, 256, 128), idesc_mn,
+                                        (sf % EG_GROUP != 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+                        for (int ks = 0; ks < 8; ks++)
+                            umma_f16_ss(d, make_desc(ab + a_plane + 2u * ks * rg_stride, rg_stride, 128), make_desc(gb + 2u * ks * 256u, 256, 128), idesc_mn, 1u);
+                        }
+                        umma_commit(bImgFree + 8 * astage);
+                        umma_commit(bGamFree + 8 * gr.s);
+                        if (last) umma_commit(bStFull + 8 * sr.s);
+                    }
+                    __syncwarp();
+                    if (last) sr.next(2);
+                    gr.next(2);
+                    sf++; si++;
+                    did = true;
+                }
+                if (!did) {      // nothing ready: park on the barrier the next product of the leading stream waits for
+                    if (ei < npf) mbar_try(bAFull + 8 * ar.s, ar.ph);
+                    else mbar_try(bGamFull + 8 * gr.s, gr.ph);
+                }
             }
-            stats_mma(a_prev);                                        // frame 0
         }
     } else if (warp >= EG_REC_WARPS) {
         // ===================== converters: raw features -> fp16 hi/lo A image =====================
@@ -258,31 +291,51 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
             if (c < nch) { rsc[c] = lds4(sbS + 16u * c); rof[c] = lds4(sbB + 16u * c); }
         const uint32_t raw_row = sRaw + (uint32_t)r * rw + 16u * c0;
         const uint32_t a_row = sA + (uint32_t)(r >> 3) * rg_stride + (uint32_t)c0 * 128u + (uint32_t)(r & 7) * 16u;
-        Ring rr = {0, 0}, ar = {0, 0};
+        const uint32_t ta_row = tmem_a + ((uint32_t)(q * 32) << 16);
+        Ring rr = {0, 0}, ar = {0, 0}, ir = {0, 0};
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             for (int i = 0; i < npf; i++) {
+                const bool img = i > T;                               // backward frame whose statistics will be accumulated
                 mbar_wait(bRawFull + 8 * rr.s, rr.ph);
                 mbar_wait(bAFree + 8 * ar.s, ar.ph ^ 1u);
+                if (img) mbar_wait(bImgFree + 8 * ir.s, ir.ph ^ 1u);
                 tc_fence_after();
-                const uint32_t src = raw_row + rr.s * frame_bytes, dst = a_row + ar.s * a_stage;
+                const uint32_t src = raw_row + rr.s * frame_bytes, dst = a_row + ir.s * a_stage, ta = ta_row + ar.s * a_cols;
+                float4 xr[NCMAX];                                     // all loads first: the (ordered) shared-memory loads overlap
 #pragma unroll
-                for (int c = 0; c < NCMAX; c++) {
-                    if (c < nch) {
-                        const float4 x = lds4(src + 16u * c);
-                        const float2 a01 = fma2(make_float2(x.x, x.y), make_float2(rsc[c].x, rsc[c].y), make_float2(rof[c].x, rof[c].y));
-                        const float2 a23 = fma2(make_float2(x.z, x.w), make_float2(rsc[c].z, rsc[c].w), make_float2(rof[c].z, rof[c].w));
-                        const float2 q01 = mul2(a01, a01), q23 = mul2(a23, a23);
-                        const uint32_t h0 = pack_h2(a01), h1 = pack_h2(a23), h2 = pack_h2(q01), h3 = pack_h2(q23);
-                        sts128(dst + 128u * c, h0, h1, h2, h3);
-                        sts128(dst + a_plane + 128u * c, pack_h2(residual_h2(a01, h0)), pack_h2(residual_h2(a23, h1)),
-                               pack_h2(residual_h2(q01, h2)), pack_h2(residual_h2(q23, h3)));
+                for (int c = 0; c < NCMAX; c++)
+                    if (c < nch) xr[c] = lds4(src + 16u * c);
+                if (!(p.flags & 4)) {
+#pragma unroll
+                    for (int c = 0; c < NCMAX; c++) {
+                        if (c < nch) {
+                            const float4 x = xr[c];
+                            const float2 a01 = fma2(make_float2(x.x, x.y), make_float2(rsc[c].x, rsc[c].y), make_float2(rof[c].x, rof[c].y));
+                            const float2 a23 = fma2(make_float2(x.z, x.w), make_float2(rsc[c].z, rsc[c].w), make_float2(rof[c].z, rof[c].w));
+                            const float2 q01 = mul2(a01, a01), q23 = mul2(a23, a23);
+                            const uint32_t h0 = pack_h2(a01), h1 = pack_h2(a23), h2 = pack_h2(q01), h3 = pack_h2(q23);
+                            const uint32_t l0 = pack_h2(residual_h2(a01, h0)), l1 = pack_h2(residual_h2(a23, h1));
+                            const uint32_t l2 = pack_h2(residual_h2(q01, h2)), l3 = pack_h2(residual_h2(q23, h3));
+                            // emission operand in TMEM: chunk cg of row r = 4 columns, K step cg / 2: [hi c even | hi c odd | lo c even | lo c odd]
+                            const uint32_t cg = (uint32_t)(c0 + c);
+                            const uint32_t tc = ta + 16u * (cg >> 1) + 4u * (cg & 1u);
+                            tmem_st4(tc, h0, h1, h2, h3);
+                            tmem_st4(tc + 8u, l0, l1, l2, l3);
+                            if (img) {                                // the same halves as the shared-memory image of the statistics product
+                                sts128(dst + 128u * c, h0, h1, h2, h3);
+                                sts128(dst + a_plane + 128u * c, l0, l1, l2, l3);
+                            }
+                        }
                     }
                 }
-                fence_proxy_async();                                  // generic-proxy stores -> visible to the tensor core's reads
+                tmem_st_wait();
+                tc_fence_before();
+                if (img) fence_proxy_async();                         // generic-proxy stores -> visible to the tensor core's reads
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(bAFull + 8 * ar.s); mbar_arrive(bRawEmpty + 8 * rr.s); }
                 rr.next((uint32_t)nraw);
                 ar.next(EG_A_STAGES);
+                if (img) ir.next(EG_A_STAGES);
             }
         }
     } else {
@@ -347,6 +400,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
             for (int t = 0; t < T; t++) {
                 float e[8];
                 fetch(e);
+                if (p.flags & 2) continue;                            // tuning experiment: pipeline without the recursion arithmetic
                 float *sp = scr + (size_t)t * 8 * TC_ROWS;
                 if (t == 0) {
                     U[0] = lb0 + e[0];
@@ -408,6 +462,16 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
                 fetch(e);
                 if (t == T - 1) {
                     glast = exit_ok ? 0.f : NAN;
+                } else if (p.flags & 2) {                           // tuning experiment: zero posteriors, barrier protocol only
+                    mbar_wait(bGamFree + 8 * gr.s, gr.ph ^ 1u);
+                    const uint32_t gb = sG + gr.s * 4096u + g_row;
+                    sts128(gb, 0, 0, 0, 0); sts128(gb + 128u, 0, 0, 0, 0);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bGamFull + 8 * gr.s);
+                    gr.next(2);
+                    sf++;
+                    if (sf >= (drained + 1) * EG_GROUP + 2) { drain(); drained++; }
                 } else {
                     float at[8], self[8], nb[8];
 #pragma unroll
@@ -498,7 +562,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == EG_MMA_WARP) tmem_dealloc(tmem_base, 64);
+    if (warp == EG_MMA_WARP) tmem_dealloc(tmem_base, tcols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -615,6 +679,8 @@ extern "C" int sapr_estep_grouped(sapr_ctx *ctx, sapr_models *m, const float *X,
     prm.trp = (const float4 *)((const char *)m->tc_image + w + g);
     prm.scratch = (float *)ctx->ws[7]; prm.ustats = (float *)ctx->ws[1]; prm.loglik = loglik; prm.tpart = (float *)ctx->ws[4];
     prm.rw = rw; prm.trace = nullptr;
+    prm.flags = getenv("SAPR_EG_EXP") ? atoi(getenv("SAPR_EG_EXP")) : 0;
+    prm.pfd = getenv("SAPR_EG_PFD") ? atoi(getenv("SAPR_EG_PFD")) : 0;
     auto kern = (nck == 10) ? k_estep_grouped<5> : (nck == 4) ? k_estep_grouped<2> : k_estep_grouped<0>;
     SAPR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     {

@@ -79,6 +79,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         ::"r"(bar), "r"(parity) : "memory");
 #endif
 }
+// non-blocking phase test, and one suspending try (returns after the hardware's time limit at the latest)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t e;
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(e));
@@ -104,6 +117,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uin
 __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap *tmap, int c0, int c1, int c2, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(dst_smem), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+// TMA tile prefetch into L2 only: extends the bytes in flight beyond what the shared-memory ring holds
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap *tmap, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");

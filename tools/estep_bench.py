@@ -14,7 +14,8 @@ A, means, var = synth.truth_models(mu, sd, 0.9)
 ctx = _lib.default_context()
 batch = engine.PackedBatch(X, offsets, 39, offsets.cpu().numpy(), labels)
 res = {}
-for mode in ("general", "grouped"):
+modes = sys.argv[3].split(",") if len(sys.argv) > 3 else ("general", "grouped")
+for mode in modes:
     m = engine.WordModels(11, 8, 39); m.set(means, var, A)
     if mode == "grouped":
         gb = engine.GroupedBatch(batch, labels, 11)
@@ -37,4 +38,4 @@ for mode in ("general", "grouped"):
     res[mode] = {"iter_ms": ms, "estep_kernel_ms": k_ms / max(k_n, 1), "stats_kernel_ms": s_ms / max(s_n, 1),
                  "frac": 31208 * B / (ms / 1e3) / 1e9 / 6552.3, "ll_sum": float(ll.sum().item()),
                  "mean0": m.get()[0][0, 1, :3].tolist()}
-print(json.dumps({"utts": B, **res}))
+print(json.dumps({"utts": B, "exp": os.environ.get("SAPR_EG_EXP", "0"), **res}))

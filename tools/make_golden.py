@@ -143,10 +143,21 @@ def rung0():
     print("rung0_d13:", len(out), "arrays")
 
 
-def rung1(name, N, D, M, B, T_lo, T_hi, seed, a_self):
+def rung1(name, N, D, M, B, T_lo, T_hi, seed, a_self, perturb=0.0, take=None):
+    """perturb > 0: the models are moved off the generating parameters (means + perturb * sigma * N(0,1)), the situation of
+    an early Baum-Welch iteration.  With D = 39 this makes exit-constrained paths so unlikely for some utterances that the
+    reference's un-normalised xi (custom_hmm.py:270-316: exp(alpha + ... + beta - logsumexp(alpha[-1]))) underflows to 0 in
+    float64 for EVERY arc, the `if np.sum(xi[t]) > 0` guard (:319) skips the normalisation and the utterance contributes
+    nothing to the transition statistics -- recorded here as reference behaviour (quirk D10)."""
     feats32, labels, mu, sd = synth.make_corpus(B, M, N, D, T_lo, T_hi, seed=seed)
+    if take is not None:                                    # a slice of a larger corpus (keeps the files small)
+        feats32, labels, B = feats32[:take], labels[:take], take
     feats = [f.astype(np.float64) for f in feats32]
     A, means, var = synth.truth_models(mu, sd, a_self)
+    if perturb > 0:
+        prng = np.random.default_rng(seed + 17)
+        means = means + perturb * np.sqrt(var) * prng.standard_normal(means.shape)
+        means[:, 0] = 0.0; means[:, -1] = 0.0
     S = N + 2
     out = {}
     X, offs = pack(feats32)
@@ -181,6 +192,8 @@ def rung1(name, N, D, M, B, T_lo, T_hi, seed, a_self):
         ll[u] = np.logaddexp.reduce(al[-1])
         G[u] = g[:-1].sum(axis=0); occ[u] = g.sum(axis=0)
         Xs[u] = np.einsum("tii->i", x)
+        if perturb > 0:
+            out.setdefault("es_xi_rows_zero", np.zeros(B, dtype=np.int32))[u] = int(np.sum(x.sum(axis=(1, 2)) == 0.0))
         gam[offs[u]:offs[u + 1]] = g
     out.update(es_loglik=ll, es_G=G, es_xi_self=Xs, es_occ=occ, es_gamma=gam)
     # one Baum-Welch iteration per word (E-step + M-step) through the reference loop
@@ -266,8 +279,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ref_pickle":
         ref_pickle()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "mismatch":
+        rung1("rung1_mismatch_d39", N=8, D=39, M=11, B=700, T_lo=40, T_hi=40, seed=1200, a_self=0.9, perturb=0.3, take=22)
+        sys.exit(0)
     rung0()
     rung1("rung1_d39", N=8, D=39, M=11, B=22, T_lo=40, T_hi=60, seed=20241118 + 2, a_self=0.9)
     rung1("rung1_d13", N=8, D=13, M=11, B=33, T_lo=24, T_hi=40, seed=20241118 + 3, a_self=0.85)
+    rung1("rung1_mismatch_d39", N=8, D=39, M=11, B=700, T_lo=40, T_hi=40, seed=1200, a_self=0.9, perturb=0.3, take=22)
     edge_cases()
     ref_pickle()
