@@ -35,7 +35,7 @@
 //   sb[2][4*nck] float (scale s, offset b: x' = x*s + b);  trp[M][TC_TRQ = 8] float4 transition block:
 //     [0] = (c1, c2, c3, c4)  [1] = (c5, c6, c7, cx)   c_j = ln A[j-1,j] - ln A[j-1,j-1] (advance minus stay),
 //                                                      cx = ln A[N,exit] - ln A[N,N]
-//     [2] = (ln A[exit,exit], ln A[0,1], 0, 0)   [3], [4] = stay_1 .. stay_8 = ln A[j,j] (folded into W's constant)
+//     [2] = (ln A[exit,exit], ln A[0,1], kx_hi, kx_lo)   [3], [4] = stay_1 .. stay_8 = ln A[j,j] (folded into W's constant)
 //     [5], [6] = (badv_1 .. badv_7, ln A[N,exit])   [7] = (ln A[0,1] - ln A[1,1], 0, 0, 0)   (E-step backward sweep)
 __global__ void k_prepare_tc(int M, int S, int D, int nck, int ncols, const double *__restrict__ mean,
                              const double *__restrict__ var, const double *__restrict__ la, const double *__restrict__ lb,
@@ -112,7 +112,15 @@ __global__ void k_prepare_tc(int M, int S, int D, int nck, int ncols, const doub
         float v[20];
         for (int j = 1; j <= 7; j++) v[j - 1] = (j + 1 <= N) ? (float)(b[j] - a[j]) : -INFINITY;   // c_{j+1}: into state j+1
         v[7] = (float)(b[N] - a[N]);                                                              // cx (N == 8)
-        v[8] = (float)a[S - 1]; v[9] = (float)b[0]; v[10] = 0.f; v[11] = 0.f;
+        v[8] = (float)a[S - 1]; v[9] = (float)b[0];
+        {   // kx = sum of the advance-minus-stay constants along the chain incl. the exit arc (k_viterbi_v3 adds it to the final
+            // score only), as a float pair; -inf when a forward arc has probability zero
+            double kx = 0.0;
+            for (int j = 1; j <= N; j++) kx += b[j] - a[j];
+            v[10] = (float)kx;
+            const double rest = kx - (double)v[10];
+            v[11] = (rest == rest && rest - rest == 0.0) ? (float)rest : 0.f;
+        }
         for (int j = 1; j <= 8; j++) v[11 + j] = (j <= N) ? (float)a[j] : 0.f;
         // E-step extras: badv_j = ln A[j,j+1] - ln A[j+1,j+1] (advance arc of state j on top of self[j+1]), ln A[N,exit],
         // ln A[0,1] - ln A[1,1]
@@ -996,6 +1004,10 @@ int sapr_viterbi_finish_u16(sapr_ctx *ctx, const int64_t *offsets, int u0, int n
                             double *best_score, double *scores_out, int M, uint8_t *best_path, uint8_t *all_paths,
                             int64_t total_frames);
 
+int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int B, int max_T,
+                           int first_frames, int32_t *best_word, double *best_score, double *scores, uint8_t *best_path,
+                           bool *taken);
+
 int sapr_viterbi_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int B,
                            int64_t total_frames, int max_T, int first_frames, int32_t *best_word, double *best_score,
                            double *scores, uint8_t *best_path, uint8_t *all_paths, float *dbgE) {
@@ -1033,6 +1045,16 @@ int sapr_viterbi_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
     L = tc_smem_layout(M, nck, ncols, nst, rstride);
     const size_t smem = L.total;
     const int MG = (M + TC_GROUPS - 1) / TC_GROUPS;
+    // equal-length contiguous batch, best path only: the re-cut kernel (viterbi_v3.cu) when the shape fits it
+    {
+        const char *v3_env = getenv("SAPR_V3");
+        if (!dbgE && !all_paths && Tm > 0 && total_frames == (int64_t)B * max_T && (!v3_env || v3_env[0] != '0') && !getenv("SAPR_TC_TRACE")) {
+            bool taken = false;
+            if ((rc = sapr_viterbi_v3_launch(ctx, m, X, ldx, offsets, B, max_T, first_frames, best_word, best_score, scores, best_path, &taken)))
+                return rc;
+            if (taken) return SAPR_OK;
+        }
+    }
     // equal-length contiguous batch (every utterance has max_T frames): TMA tensor-map loads, k_viterbi_tma
     const char *tma_env = getenv("SAPR_TMA");
     bool use_tma = !dbgE && Tm > 0 && total_frames == (int64_t)B * max_T && (!tma_env || tma_env[0] != '0') &&

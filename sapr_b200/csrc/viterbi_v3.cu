@@ -1,0 +1,490 @@
+// viterbi_v3.cu -- the cfg-2 headline kernel: batched Viterbi of EQUAL-LENGTH utterances against M <= 12 eight-state word models,
+// emission on tcgen05 (same operand images as viterbi_tc.cu), re-cut for instruction count.
+//
+// Contract: custom_hmm.py:462-514 for every (utterance, model) + decoder.py:42-47, as k_viterbi_tc.  What changed against
+// k_viterbi_tc / k_viterbi_tma (which stay for ragged batches, the debug emission dump and all_paths):
+//   * Transition constants are gone from the recursion.  With U_j = V_j + ln A[j,j] the step is
+//         U'_j = max(U_{j-1} + c_j, U_j) + e_j,      c_j = ln A[j-1,j] - ln A[j-1,j-1],  e_j = E_j + ln A[j,j] (tensor core)
+//     and the substitution W_j = U_j - (c_2 + .. + c_j) turns it into  W'_j = max(W_{j-1}, W_j) + e_j : no per-state adds, no
+//     constants to hold or load.  The sum of the c's (and the exit arc) is added to the final score only (kx, float64).
+//     A model with a zero-probability forward arc has kx = -inf: its score is -inf, as in the reference (no path reaches the
+//     exit), and its recursion values are never used.
+//   * One 32-bit back-pointer word per (thread, frame) for all of the thread's models (8 "stayed" sign bits per model: exit,
+//     states 8..2; state 1 has a predecessor at t == 1 only and borrows the exit slot there), gathered by ONE chained
+//     funnel shift per state -- no masks, no inversion, one store per frame instead of one per model.
+//   * Four A-operand stages + two accumulator stages = all 512 TMEM columns, frames are processed in blocks of four with
+//     every stage index, barrier address and phase a compile-time constant; the raw-feature ring is two stages of four
+//     frames filled by TMA tensor-map loads from one thread.  Tiles are padded to a multiple of four frames (zero-filled by
+//     the tensor map), so each tile starts at stage 0.
+//   * 18 warps (16 workers, MMA issuer, TMA producer): 112 registers per thread, the standardisation constants of a
+//     thread's feature chunks live in registers.
+#include "tc_common.cuh"
+
+#define V3_THREADS (TC_WORKERS + 64)
+#define V3_FB 4                       /* frames per block = frames per raw-ring stage = A-operand stages */
+
+struct V3Params {
+    int u0, nu, M, nck, ncols, Tt, Tpad, ntiles;
+    const __half *wimg; const float *sb; const float4 *trp;
+    uint32_t *bp; uint32_t Bpad;        // back-pointer words [group][Tpad][Bpad]
+    double *scores;                     // [nu][M]
+    int mod0[TC_GROUPS], nmod[TC_GROUPS], pair0[TC_GROUPS], npair[TC_GROUPS];
+    uint32_t rw;                        // bytes per row of the raw ring: (nck + 1) * 16
+};
+
+struct V3Smem { uint32_t w, raw, tr, sb, bar, total; };
+__host__ __device__ inline V3Smem v3_smem_layout(int M, int nck, int ncols, uint32_t rw) {
+    V3Smem L;
+    L.w = 0;
+    L.raw = ((uint32_t)2 * (ncols / 8) * nck * 128 + 127u) & ~127u;
+    L.tr = L.raw + 2u * V3_FB * TC_ROWS * rw;
+    L.sb = L.tr + (uint32_t)M * TC_TRQ * 16;
+    L.bar = (L.sb + (uint32_t)8 * nck * 4 + 15u) & ~15u;
+    L.total = L.bar + 12 * 8 + 16;      // raw_full[2], raw_empty[2], A_full[4], acc_full[2]
+    return L;
+}
+
+__device__ __forceinline__ float4 v3_lds4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+// 4 feature dims: standardise, square, fp16 hi / lo split.  hi = (x'01, x'23, x'^2 01, x'^2 23), lo likewise
+__device__ __forceinline__ void v3_split4(const float4 x, const float4 sc, const float4 of, uint32_t *hi, uint32_t *lo) {
+    const float2 a01 = fma2(make_float2(x.x, x.y), make_float2(sc.x, sc.y), make_float2(of.x, of.y));
+    const float2 a23 = fma2(make_float2(x.z, x.w), make_float2(sc.z, sc.w), make_float2(of.z, of.w));
+    const float2 q01 = mul2(a01, a01), q23 = mul2(a23, a23);
+    hi[0] = pack_h2(a01); hi[1] = pack_h2(a23); hi[2] = pack_h2(q01); hi[3] = pack_h2(q23);
+    lo[0] = pack_h2(residual_h2(a01, hi[0])); lo[1] = pack_h2(residual_h2(a23, hi[1]));
+    lo[2] = pack_h2(residual_h2(q01, hi[2])); lo[3] = pack_h2(residual_h2(q23, hi[3]));
+}
+
+// one frame of one model in W space; appends 8 "stayed" sign bits to sb: exit first, then states 8 .. 2 (state 2 ends up lowest).
+// The predecessor wins ties (sign(+0) = 0 = advanced; custom_hmm.py:488-497 tries j-1 first and replaces on strict > only).
+__device__ __forceinline__ void v3_step(float (&W)[8], float &Wx, const float aex, const uint32_t (&ev)[8], uint32_t &sb) {
+    const float xs = Wx + aex;                                   // exit self-loop (custom_hmm.py:481-485; D9)
+    sb = __funnelshift_l(__float_as_uint(W[7] - xs), sb, 1);
+    Wx = fmaxf(W[7], xs);
+#pragma unroll
+    for (int j = 7; j >= 1; j--) {
+        sb = __funnelshift_l(__float_as_uint(W[j - 1] - W[j]), sb, 1);
+        W[j] = fmaxf(W[j - 1], W[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        const float2 s = add2(make_float2(W[j], W[j + 1]), make_float2(__uint_as_float(ev[j]), __uint_as_float(ev[j + 1])));
+        W[j] = s.x; W[j + 1] = s.y;
+    }
+}
+// frame 1: the entry state is still alive (custom_hmm.py:477-480: prev_states = [1, 0], the self-loop wins ties); the exit is
+// closed, its slot carries "entry taken"
+__device__ __forceinline__ void v3_step_entry(float (&W)[8], float &Wx, const float b0, const uint32_t (&ev)[8], uint32_t &sb) {
+    sb = __funnelshift_l(__float_as_uint(W[0] - b0), sb, 1);     // 1 = the entry arc is strictly better
+    Wx = -INFINITY;
+#pragma unroll
+    for (int j = 7; j >= 1; j--) {
+        sb = __funnelshift_l(__float_as_uint(W[j - 1] - W[j]), sb, 1);
+        W[j] = fmaxf(W[j - 1], W[j]);
+    }
+    W[0] = fmaxf(W[0], b0);
+#pragma unroll
+    for (int j = 0; j < 8; j++) W[j] += __uint_as_float(ev[j]);
+}
+// renormalise by an integer-valued shift (accumulates exactly in fp32 for |offset| < 2^24)
+__device__ __forceinline__ void v3_renorm(float (&W)[8], float &Wx, float &base) {
+    float mx = fmaxf(fmaxf(W[0], W[1]), Wx);
+    mx = fmaxf(fmaxf(W[2], W[3]), mx);
+    mx = fmaxf(fmaxf(W[4], W[5]), mx);
+    mx = fmaxf(fmaxf(W[6], W[7]), mx);
+    mx = rintf(fminf(fmaxf(mx, -4194304.f), 4194304.f));
+    const float2 m2 = make_float2(mx, mx);
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        const float2 s = sub2(make_float2(W[j], W[j + 1]), m2);
+        W[j] = s.x; W[j + 1] = s.y;
+    }
+    Wx -= mx;
+    base += mx;
+}
+
+template <int NKS>
+__global__ void __launch_bounds__(V3_THREADS, 1) k_viterbi_v3(const V3Params p, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int nck = p.nck, ncols = p.ncols, M = p.M;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rw = p.rw, frame_bytes = TC_ROWS * rw, stage_bytes = V3_FB * frame_bytes;
+    const V3Smem L = v3_smem_layout(M, nck, ncols, rw);
+    const uint32_t w_plane = (uint32_t)(ncols / 8) * nck * 128;
+    unsigned char *sW = smem + L.w;
+    const uint32_t sRaw = smem_u32(smem + L.raw);
+    const float4 *sTr = reinterpret_cast<const float4 *>(smem + L.tr);
+    uint64_t *sBar = reinterpret_cast<uint64_t *>(smem + L.bar);
+    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 12);
+    const uint32_t barRawFull = smem_u32(sBar), barRawEmpty = barRawFull + 16, barAFull = barRawFull + 32, barAccFull = barRawFull + 64;
+
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.wimg);
+        uint4 *dst = reinterpret_cast<uint4 *>(sW);
+        for (uint32_t i = tid; i < 2 * w_plane / 16; i += V3_THREADS) dst[i] = src[i];
+        float4 *dtr = reinterpret_cast<float4 *>(smem + L.tr);
+        for (int i = tid; i < M * TC_TRQ; i += V3_THREADS) dtr[i] = p.trp[i];
+        float *dsb = reinterpret_cast<float *>(smem + L.sb);
+        for (int i = tid; i < 8 * nck; i += V3_THREADS) dsb[i] = p.sb[i];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < 2; s++) { mbar_init(barRawFull + 8 * s, 1); mbar_init(barRawEmpty + 8 * s, TC_WORKER_WARPS); }
+        for (int s = 0; s < 4; s++) mbar_init(barAFull + 8 * s, TC_WORKER_WARPS);
+        for (int s = 0; s < 2; s++) mbar_init(barAccFull + 8 * s, 1);
+        fence_barrier_init();
+    }
+    const uint32_t a_cols = 8u * nck;                       // TMEM columns of one A stage: per K step [hi 8 | lo 8]
+    if (warp == TC_WORKER_WARPS) tmem_alloc(smem_u32(sTmem), 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sTmem;
+    const uint32_t tmem_acc = tmem_base, tmem_a = tmem_base + 2u * ncols;
+    const int Tt = p.Tt, Tpad = p.Tpad;
+    const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles this CTA walks
+
+    if (warp == TC_WORKER_WARPS + 1) {
+        // ===================== TMA producer: one thread, one stage = four frames of a tile =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap);
+            uint32_t G = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                const int urow = p.u0 + tile * TC_ROWS;
+                for (int t0 = 0; t0 < Tpad; t0 += V3_FB, G++) {
+                    const uint32_t s = G & 1u, ph = (G >> 1) & 1u;
+                    const uint32_t bar = barRawFull + 8 * s;
+                    mbar_wait(barRawEmpty + 8 * s, ph ^ 1u);
+                    mbar_arrive_tx(bar, stage_bytes);
+                    const uint32_t dst = sRaw + s * stage_bytes;
+#pragma unroll
+                    for (int fi = 0; fi < V3_FB; fi++) tma_load_3d(dst + (uint32_t)fi * frame_bytes, &tmap, 0, t0 + fi, urow, bar);
+                }
+            }
+        }
+    } else if (warp == TC_WORKER_WARPS) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+        const uint32_t sW_hi = smem_u32(sW), sW_lo = sW_hi + w_plane;
+        const uint32_t sboW = (uint32_t)nck * 128u;
+        const uint64_t dW_hi = make_desc(sW_hi, 128, sboW), dW_lo = make_desc(sW_lo, 128, sboW);
+        const int nks = nck / 2;
+        const int nblk = my_tiles * (Tpad / V3_FB);
+        uint32_t aph = 0;
+        for (int b = 0; b < nblk; b++, aph ^= 1u) {
+#pragma unroll
+            for (int i = 0; i < V3_FB; i++) {
+                mbar_wait(barAFull + 8 * i, aph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t d_tmem = tmem_acc + (uint32_t)(i & 1) * (uint32_t)ncols;
+                    const uint32_t a_hi = tmem_a + (uint32_t)i * a_cols, a_lo = a_hi + 8u;
+                    // the two correction products first: the large hi * W_hi partial sums see the fewest truncating steps
+                    if (NKS > 0) {
+#pragma unroll
+                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_lo + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, ks > 0);
+#pragma unroll
+                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_lo + (uint64_t)(16 * ks), idesc, 1);
+#pragma unroll
+                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, 1);
+                    } else {
+                        for (int ks = 0; ks < nks; ks++) umma_f16_ts(d_tmem, a_lo + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, ks > 0);
+                        for (int ks = 0; ks < nks; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_lo + (uint64_t)(16 * ks), idesc, 1);
+                        for (int ks = 0; ks < nks; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, 1);
+                    }
+                    umma_commit(barAccFull + 8 * (i & 1));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== workers: thread = (row, group) =====================
+        const int q = warp & 3, g = warp >> 2, r = q * 32 + lane;
+        const int mbeg = p.mod0[g], pr0 = p.pair0[g];
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const uint32_t ta0 = tmem_a + lane_sel + 16u * pr0;
+        const uint32_t acc0 = tmem_acc + lane_sel + (uint32_t)mbeg * 8u;
+        const uint32_t raw0 = sRaw + (uint32_t)r * rw + 32u * pr0;
+        const uint32_t sbS = smem_u32(smem + L.sb) + 32u * pr0, sbB = sbS + 16u * nck;
+
+        auto run = [&](auto NPc, auto MCc) {
+            constexpr int NP = decltype(NPc)::value, MC = decltype(MCc)::value;
+            float aex[MC];
+#pragma unroll
+            for (int k = 0; k < MC; k++) aex[k] = sTr[(mbeg + k) * TC_TRQ + 2].x;
+            uint32_t cG = 0;                                 // raw-ring stage counter of the conversions (stage = cG & 1, phase = cG >> 1)
+            // frame (4 G + FI) of the ring -> A stage FI (compile time); waits for / releases the ring stage at its ends
+            auto convert = [&](auto FIc) {
+                constexpr int FI = decltype(FIc)::value;
+                const uint32_t s = cG & 1u;
+                if (FI == 0) mbar_wait(barRawFull + 8 * s, (cG >> 1) & 1u);
+                const uint32_t src = raw0 + s * stage_bytes + (uint32_t)FI * frame_bytes;
+                const uint32_t ta = ta0 + (uint32_t)FI * a_cols;
+#pragma unroll
+                for (int c = 0; c < 2 * NP; c++) {          // chunk c of this thread: 4 TMEM columns of the hi half, 4 of the lo half of its K step
+                    uint32_t hi[4], lo[4];
+                    v3_split4(v3_lds4(src + 16u * c), v3_lds4(sbS + 16u * c), v3_lds4(sbB + 16u * c), hi, lo);
+                    const uint32_t tc = ta + 16u * (c >> 1) + 4u * (c & 1);
+                    tmem_st4(tc, hi[0], hi[1], hi[2], hi[3]);
+                    tmem_st4(tc + 8u, lo[0], lo[1], lo[2], lo[3]);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(barAFull + 8 * FI);
+                    if (FI == V3_FB - 1) mbar_arrive(barRawEmpty + 8 * s);
+                }
+                if (FI == V3_FB - 1) cG++;
+            };
+            constexpr std::integral_constant<int, 0> F0{};
+            constexpr std::integral_constant<int, 1> F1{};
+            constexpr std::integral_constant<int, 2> F2{};
+            constexpr std::integral_constant<int, 3> F3{};
+
+            if (my_tiles > 0) { convert(F0); convert(F1); }
+            int tiles_left = my_tiles;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                tiles_left--;
+                const int ul = tile * TC_ROWS + r;
+                float W[MC][8], Wx[MC], base[MC];
+#pragma unroll
+                for (int k = 0; k < MC; k++) {
+                    Wx[k] = -INFINITY; base[k] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) W[k][j] = -INFINITY;
+                }
+                uint32_t bpo = (uint32_t)g * (uint32_t)Tpad * p.Bpad + (uint32_t)ul;
+                uint32_t sb = 0;
+                // recursion of frame t0 + I from accumulator stage I & 1 (phase (I >> 1) & 1: tiles start at a multiple of four
+                // frames); GEN = first / last block of a tile (run-time frame tests), else straight-line
+                auto recurse = [&](auto Ic, auto GENc, int t0) {
+                    constexpr int I = decltype(Ic)::value;
+                    constexpr bool GEN = decltype(GENc)::value;
+                    mbar_wait(barAccFull + 8 * (I & 1), (I >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t tacc = acc0 + (uint32_t)(I & 1) * (uint32_t)ncols;
+                    const int t = t0 + I;
+                    if (!GEN) {
+                        // accumulator columns of model k - 1 are in flight while model k is stepped
+                        uint32_t ev[2][8];
+                        tmem_ld8(tacc + 8u * (MC - 1), ev[(MC - 1) & 1]);
+#pragma unroll
+                        for (int k = MC - 1; k >= 0; k--) {
+                            tmem_ld_wait();
+                            if (k > 0) tmem_ld8(tacc + 8u * (k - 1), ev[(k - 1) & 1]);
+                            v3_step(W[k], Wx[k], aex[k], ev[k & 1], sb);
+                        }
+                        tc_fence_before();
+                        p.bp[bpo] = sb;
+                        bpo += p.Bpad;
+                        return;
+                    }
+                    uint32_t ev[MC][8];
+#pragma unroll
+                    for (int k = 0; k < MC; k++) tmem_ld8(tacc + 8u * k, ev[k]);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    if (t < Tt) {
+                        if (t == 0) {
+#pragma unroll
+                            for (int k = 0; k < MC; k++) W[k][0] = sTr[(mbeg + k) * TC_TRQ + 2].y + __uint_as_float(ev[k][0]);   // ln A[0,1] + E[0,1] + ln A[1,1]
+                        } else if (t == 1) {
+#pragma unroll
+                            for (int k = MC - 1; k >= 0; k--) v3_step_entry(W[k], Wx[k], sTr[(mbeg + k) * TC_TRQ + 2].y, ev[k], sb);
+                        } else {
+#pragma unroll
+                            for (int k = MC - 1; k >= 0; k--) v3_step(W[k], Wx[k], aex[k], ev[k], sb);
+                        }
+                        p.bp[bpo] = sb;
+                    }
+                    bpo += p.Bpad;
+                };
+                constexpr std::integral_constant<bool, false> LEAN{};
+                constexpr std::integral_constant<bool, true> GENERIC{};
+                for (int t0 = 0; t0 < Tpad; t0 += V3_FB) {
+                    const bool first = t0 == 0, last = t0 + V3_FB >= Tpad;
+                    if (!first && !last) {
+                        recurse(F0, LEAN, t0); convert(F2);
+                        recurse(F1, LEAN, t0); convert(F3);
+                        recurse(F2, LEAN, t0); convert(F0);
+                        recurse(F3, LEAN, t0); convert(F1);
+                    } else {
+                        const bool more = !last || tiles_left > 0;     // frames t0 + 4, t0 + 5 exist (this tile or the CTA's next one)
+                        recurse(F0, GENERIC, t0); convert(F2);
+                        recurse(F1, GENERIC, t0); convert(F3);
+                        recurse(F2, GENERIC, t0); if (more) convert(F0);
+                        recurse(F3, GENERIC, t0); if (more) convert(F1);
+                    }
+                    if ((t0 & 4) != 0) {
+#pragma unroll
+                        for (int k = 0; k < MC; k++) v3_renorm(W[k], Wx[k], base[k]);
+                    }
+                }
+                if (ul < p.nu) {
+#pragma unroll
+                    for (int k = 0; k < MC; k++) {
+                        const float4 cm = sTr[(mbeg + k) * TC_TRQ + 2];
+                        const double sc = (Wx[k] > -INFINITY) ? ((double)Wx[k] + (double)base[k]) + ((double)cm.z + (double)cm.w) : -INFINITY;
+                        p.scores[(size_t)ul * M + mbeg + k] = sc;
+                    }
+                }
+            }
+        };
+        const int npr = p.npair[g], mcnt = p.nmod[g];
+        if (npr == 2 && mcnt == 2) run(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{});
+        else if (npr == 1 && mcnt == 3) run(std::integral_constant<int, 1>{}, std::integral_constant<int, 3>{});
+        else if (npr == 2 && mcnt == 3) run(std::integral_constant<int, 2>{}, std::integral_constant<int, 3>{});
+        else if (npr == 1 && mcnt == 2) run(std::integral_constant<int, 1>{}, std::integral_constant<int, 2>{});
+        else __trap();      // the launcher only picks this kernel for the splits above
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_WORKER_WARPS) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// arg-max over models (strict >, first model wins: decoder.py:42-47) + back-trace of the winner from the packed words
+struct V3Map { int grp[16], shift[16]; };
+__global__ void __launch_bounds__(128)
+k_viterbi_finish_v3(const int64_t *__restrict__ offsets, int u0, int nu, int M, int Tt, int Tpad, const uint32_t *__restrict__ bp,
+                    uint32_t Bpad, const V3Map map, const double *__restrict__ scores, int32_t *__restrict__ best_word,
+                    double *__restrict__ best_score, double *__restrict__ scores_out, uint8_t *__restrict__ best_path) {
+    constexpr int CH = 32;
+    __shared__ uint8_t sp[4][32][CH + 4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int ul = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = ul < nu;
+    const int u = u0 + ul;
+    double bs = -INFINITY;
+    int bslot = -1;
+    int64_t off = 0;
+    if (live) {
+        off = offsets[u];
+        for (int s = 0; s < M; s++) {
+            const double sc = scores[(size_t)ul * M + s];
+            if (scores_out) scores_out[(size_t)u * M + s] = sc;
+            if (sc > bs) { bs = sc; bslot = s; }
+        }
+        if (best_word) best_word[u] = bslot;
+        if (best_score) best_score[u] = bs;
+    }
+    if (!best_path) return;
+    const int wslot = bslot < 0 ? 0 : bslot;
+    const bool reachable = live && bslot >= 0;
+    const uint32_t *bpp = bp + (size_t)map.grp[wslot] * Tpad * Bpad + ul;
+    const int sh = map.shift[wslot];
+    const int Te = live ? Tt : 0;
+    int cur = 9;
+    for (int t0 = (Tt - 1) / CH * CH; t0 >= 0; t0 -= CH) {
+        uint32_t bits[CH];
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            const int t = t0 + j;
+            bits[j] = (reachable && t >= 1 && t < Te) ? (bpp[(size_t)t * Bpad] >> sh) & 0xFFu : 0xFFu;
+        }
+#pragma unroll
+        for (int j = CH - 1; j >= 0; j--) {
+            const int t = t0 + j;
+            if (t < Te) {
+                sp[w][lane][j] = (uint8_t)cur;
+                if (!reachable) cur = 0;                                          // unreachable cell: back-pointer stays 0 (:470)
+                else if (cur >= 2) cur -= (int)(((bits[j] >> (cur - 2)) & 1u) ^ 1u);   // a set bit = stayed (frame 0 reads as all set)
+                else if (cur == 1 && t == 1) cur -= (int)(bits[j] >> 7);         // entry arc (exit slot at t == 1)
+            }
+        }
+        __syncwarp();
+        for (int row = 0; row < 32; row++) {
+            const int Te_r = __shfl_sync(0xffffffffu, Te, row);
+            const int64_t off_r = __shfl_sync(0xffffffffu, off, row);
+            if (t0 + lane < Te_r) best_path[off_r + t0 + lane] = sp[w][row][lane];
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// returns SAPR_OK and sets *taken when the batch / model set has the shape this kernel is cut for
+int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int B, int max_T,
+                           int first_frames, int32_t *best_word, double *best_score, double *scores, uint8_t *best_path,
+                           bool *taken) {
+    *taken = false;
+    int nck, ncols;
+    sapr_tc_image_bytes(m, &nck, &ncols);
+    const int M = m->M;
+    const int Tt = (first_frames > 0 && first_frames < max_T) ? first_frames : max_T;
+    if (Tt < 2 || ((uintptr_t)X & 15u) || nck % 2) return SAPR_OK;
+    // work split over the four worker groups: chunk pairs to the low groups, models to the high groups
+    V3Params prm;
+    const int npairs = nck / 2;
+    if (npairs > 2 * TC_GROUPS || npairs < TC_GROUPS) return SAPR_OK;
+    {
+        int pc[TC_GROUPS], mcn[TC_GROUPS];
+        const int MG = (M + TC_GROUPS - 1) / TC_GROUPS;
+        for (int g = 0; g < TC_GROUPS; g++) { pc[g] = npairs / TC_GROUPS + (g < npairs % TC_GROUPS ? 1 : 0); mcn[g] = 0; }
+        for (int mi = 0; mi < M; mi++) {
+            int best = TC_GROUPS - 1;
+            for (int g = TC_GROUPS - 1; g >= 0; g--)
+                if (mcn[g] < MG && (mcn[best] >= MG || pc[g] + mcn[g] < pc[best] + mcn[best])) best = g;
+            mcn[best]++;
+        }
+        int pa = 0, ma = 0;
+        for (int g = 0; g < TC_GROUPS; g++) {
+            prm.pair0[g] = pa; prm.npair[g] = pc[g]; pa += pc[g];
+            prm.mod0[g] = ma; prm.nmod[g] = mcn[g]; ma += mcn[g];
+            const bool ok = (pc[g] == 2 && mcn[g] == 2) || (pc[g] == 1 && mcn[g] == 3) || (pc[g] == 2 && mcn[g] == 3) || (pc[g] == 1 && mcn[g] == 2);
+            if (!ok) return SAPR_OK;
+        }
+    }
+    const uint32_t rw = (uint32_t)(nck + 1) * 16u;
+    const V3Smem L = v3_smem_layout(M, nck, ncols, rw);
+    if (L.total > 227 * 1024 || 2 * ncols + 4 * 8 * nck > 512) return SAPR_OK;
+    const int Tpad = (Tt + V3_FB - 1) / V3_FB * V3_FB;
+    const int64_t per_utt = (int64_t)TC_GROUPS * Tpad * sizeof(uint32_t);
+    int chunk = (int)std::min<int64_t>(B, std::max<int64_t>(TC_ROWS, ((int64_t)1024 << 20) / per_utt));
+    chunk = (chunk + TC_ROWS - 1) / TC_ROWS * TC_ROWS;
+    int rc;
+    if ((rc = sapr_ws_reserve(ctx, 0, (size_t)per_utt * chunk))) return rc;
+    if ((rc = sapr_ws_reserve(ctx, 1, (size_t)chunk * M * sizeof(double)))) return rc;
+    CUtensorMap tmap;
+    {
+        const uint64_t dim[3] = {(uint64_t)ldx, (uint64_t)max_T, (uint64_t)B};
+        const uint64_t str[2] = {(uint64_t)ldx * 4u, (uint64_t)max_T * ldx * 4u};
+        const uint32_t box[3] = {rw / 4u, 1u, (uint32_t)TC_ROWS};
+        if ((rc = sapr_tmap_f32_3d(ctx, &tmap, X, dim, str, box))) return rc;
+    }
+    auto al256 = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t w = al256((size_t)2 * (ncols / 8) * nck * 64 * sizeof(__half));
+    const size_t gsz = al256((size_t)8 * nck * sizeof(float));
+    V3Map map;
+    for (int g = 0; g < TC_GROUPS; g++)
+        for (int k = 0; k < prm.nmod[g]; k++) { map.grp[prm.mod0[g] + k] = g; map.shift[prm.mod0[g] + k] = 8 * k; }
+    auto kern = (nck == 10) ? k_viterbi_v3<5> : (nck == 4) ? k_viterbi_v3<2> : k_viterbi_v3<0>;
+    SAPR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    for (int u0 = 0; u0 < B; u0 += chunk) {
+        const int nu = std::min(chunk, B - u0);
+        prm.u0 = u0; prm.nu = nu; prm.M = M; prm.nck = nck; prm.ncols = ncols; prm.Tt = Tt; prm.Tpad = Tpad;
+        prm.ntiles = (nu + TC_ROWS - 1) / TC_ROWS;
+        prm.wimg = (const __half *)m->tc_image;
+        prm.sb = (const float *)((const char *)m->tc_image + w);
+        prm.trp = (const float4 *)((const char *)m->tc_image + w + gsz);
+        prm.bp = (uint32_t *)ctx->ws[0]; prm.Bpad = (uint32_t)chunk; prm.scores = (double *)ctx->ws[1]; prm.rw = rw;
+        {
+            ProfScope ps(ctx, 0);
+            kern<<<std::min(prm.ntiles, ctx->sm_count), V3_THREADS, L.total, ctx->stream>>>(prm, tmap);
+        }
+        SAPR_LAUNCH_CHECK(ctx);
+        {
+            ProfScope ps(ctx, 1);
+            k_viterbi_finish_v3<<<(nu + 127) / 128, 128, 0, ctx->stream>>>(offsets, u0, nu, M, Tt, Tpad, prm.bp, prm.Bpad, map, prm.scores,
+                                                                          best_word, best_score, scores, best_path);
+        }
+        SAPR_LAUNCH_CHECK(ctx);
+    }
+    *taken = true;
+    return SAPR_OK;
+}
