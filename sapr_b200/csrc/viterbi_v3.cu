@@ -30,6 +30,8 @@ struct V3Params {
     double *scores;                     // [nu][M]
     int mod0[TC_GROUPS], nmod[TC_GROUPS], pair0[TC_GROUPS], npair[TC_GROUPS];
     uint32_t rw;                        // bytes per row of the raw ring: (nck + 1) * 16
+    long long *trace;                   // [V4_TRACE_ROLES][V4_TRACE_FRAMES][4] clock64 stamps of CTA 0 or null (SAPR_V_TRACE=file)
+    int flags;                          // tuning what-ifs (SAPR_V_EXP, k_viterbi_v4<.., EXP = true>): 1 = no MMAs, 2 = no recursion arithmetic, 4 = no conversion arithmetic, 8 = no back-pointer stores
 };
 
 struct V3Smem { uint32_t w, raw, tr, sb, bar, total; };
@@ -348,6 +350,353 @@ __global__ void __launch_bounds__(V3_THREADS, 1) k_viterbi_v3(const V3Params p, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_viterbi_v4: the same arithmetic with the two halves of a worker's frame -- feature conversion and recursion -- on SEPARATE
+// warps, so that neither waits for the other's barriers and an SM sub-partition has 6 resident instruction streams instead of 4:
+//   warps  0-7   conversion: thread = (row, half of the feature chunks); raw ring -> standardise / square / fp16 hi-lo ->
+//                A-operand stage in TMEM (A_full); stages are handed back by tcgen05.commit (A_empty)
+//   warps  8-23  recursion: thread = (row, model group); steps its models on the columns already in registers while the next
+//                frame's columns are fetched behind each model (rolling fetch), then hands that stage back (acc_empty)
+//   warp  24     MMA issuer: A_full + acc_empty -> 15 x tcgen05.mma -> commit to acc_full and A_empty
+//   warp  25     TMA producer
+// (the scheduler favours high warp ids: the conversions, which run stages ahead anyway, get the low ones.)
+// Four A stages + two accumulator stages (512 TMEM columns) as in k_viterbi_v3, frames in blocks of four with static stage
+// indices.  setmaxnreg moves registers from the conversion warps (56) to the recursion warps (80).
+#define V4_REC_WARPS 16
+#define V4_CONV_WARPS 8
+#define V4_REC_WARP0 V4_CONV_WARPS
+#define V4_MMA_WARP (V4_REC_WARPS + V4_CONV_WARPS)
+#define V4_TMA_WARP (V4_MMA_WARP + 1)
+#define V4_THREADS (32 * (V4_TMA_WARP + 1))
+#define V4_TRACE_ROLES 5
+#define V4_TRACE_FRAMES 256
+
+struct V4Smem { uint32_t w, raw, tr, sb, bar, total; };
+__host__ __device__ inline V4Smem v4_smem_layout(int M, int nck, int ncols, uint32_t rw) {
+    V4Smem L;
+    L.w = 0;
+    L.raw = ((uint32_t)2 * (ncols / 8) * nck * 128 + 127u) & ~127u;
+    L.tr = L.raw + 2u * V3_FB * TC_ROWS * rw;
+    L.sb = L.tr + (uint32_t)M * TC_TRQ * 16;
+    L.bar = (L.sb + (uint32_t)8 * nck * 4 + 15u) & ~15u;
+    L.total = L.bar + 16 * 8 + 16;      // raw_full[2], raw_empty[2], A_full[4], A_empty[4], acc_full[2], acc_empty[2]
+    return L;
+}
+
+// waits for two barriers with one poll loop (a check of a completed barrier costs ~150 cycles: the two overlap)
+__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%2], %3;\n\t"
+        "and.pred p, p, q;\n\t"
+        "@p bra DONE;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.gt.u32 q, n, 64000000;\n\t"
+        "@q trap;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t}"
+        ::"r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b) : "memory");
+}
+
+template <int NKS, bool TRACE = false, bool EXP = false>      // nck = 2 * NKS feature chunks; EXP: the what-if flags are honoured
+__global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int nck = 2 * NKS;
+    const int ncols = p.ncols, M = p.M;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rw = p.rw, frame_bytes = TC_ROWS * rw, stage_bytes = V3_FB * frame_bytes;
+    const V4Smem L = v4_smem_layout(M, nck, ncols, rw);
+    const uint32_t w_plane = (uint32_t)(ncols / 8) * nck * 128;
+    unsigned char *sW = smem + L.w;
+    const uint32_t sRaw = smem_u32(smem + L.raw);
+    const float4 *sTr = reinterpret_cast<const float4 *>(smem + L.tr);
+    uint64_t *sBar = reinterpret_cast<uint64_t *>(smem + L.bar);
+    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 16);
+    const uint32_t barRawFull = smem_u32(sBar), barRawEmpty = barRawFull + 16, barAFull = barRawFull + 32, barAEmpty = barRawFull + 64;
+    const uint32_t barAccFull = barRawFull + 96, barAccEmpty = barRawFull + 112;
+
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.wimg);
+        uint4 *dst = reinterpret_cast<uint4 *>(sW);
+        for (uint32_t i = tid; i < 2 * w_plane / 16; i += V4_THREADS) dst[i] = src[i];
+        float4 *dtr = reinterpret_cast<float4 *>(smem + L.tr);
+        for (int i = tid; i < M * TC_TRQ; i += V4_THREADS) dtr[i] = p.trp[i];
+        float *dsb = reinterpret_cast<float *>(smem + L.sb);
+        for (int i = tid; i < 8 * nck; i += V4_THREADS) dsb[i] = p.sb[i];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < 2; s++) { mbar_init(barRawFull + 8 * s, 1); mbar_init(barRawEmpty + 8 * s, V4_CONV_WARPS); }
+        for (int s = 0; s < 4; s++) { mbar_init(barAFull + 8 * s, V4_CONV_WARPS); mbar_init(barAEmpty + 8 * s, 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(barAccFull + 8 * s, 1); mbar_init(barAccEmpty + 8 * s, V4_REC_WARPS); }
+        fence_barrier_init();
+    }
+    constexpr uint32_t a_cols = 8u * nck;
+    if (warp == V4_MMA_WARP) tmem_alloc(smem_u32(sTmem), 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sTmem;
+    const uint32_t tmem_acc = tmem_base, tmem_a = tmem_base + 2u * ncols;
+    const int Tt = p.Tt, Tpad = p.Tpad;
+    const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int nblk = my_tiles * (Tpad / V3_FB);          // four-frame blocks this CTA walks
+    auto trace = [&](int role, int frame, int ev) {
+        if (TRACE && blockIdx.x == 0 && lane == 0 && frame < V4_TRACE_FRAMES) p.trace[((size_t)role * V4_TRACE_FRAMES + frame) * 4 + ev] = clock64();
+    };
+
+    if (warp == V4_TMA_WARP) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap);
+            uint32_t G = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                const int urow = p.u0 + tile * TC_ROWS;
+                for (int t0 = 0; t0 < Tpad; t0 += V3_FB, G++) {
+                    const uint32_t s = G & 1u, ph = (G >> 1) & 1u;
+                    const uint32_t bar = barRawFull + 8 * s;
+                    mbar_wait(barRawEmpty + 8 * s, ph ^ 1u);
+                    trace(1, (int)G, 0);
+                    mbar_arrive_tx(bar, stage_bytes);
+                    const uint32_t dst = sRaw + s * stage_bytes;
+#pragma unroll
+                    for (int fi = 0; fi < V3_FB; fi++) tma_load_3d(dst + (uint32_t)fi * frame_bytes, &tmap, 0, t0 + fi, urow, bar);
+                    trace(1, (int)G, 1);
+                    if (TRACE && blockIdx.x == 0) { mbar_wait(bar, ph); trace(1, (int)G, 2); }
+                }
+            }
+        }
+    } else if (warp == V4_MMA_WARP) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+        const uint32_t sW_hi = smem_u32(sW), sW_lo = sW_hi + w_plane;
+        const uint32_t sboW = (uint32_t)nck * 128u;
+        const uint64_t dW_hi = make_desc(sW_hi, 128, sboW), dW_lo = make_desc(sW_lo, 128, sboW);
+        uint32_t aph = 0;
+        for (int b = 0; b < nblk; b++, aph ^= 1u) {
+#pragma unroll
+            for (int i = 0; i < V3_FB; i++) {
+                trace(0, 4 * b + i, 0);
+                mbar_wait2(barAFull + 8 * i, aph, barAccEmpty + 8 * (i & 1), ((i >> 1) & 1) ^ 1);
+                trace(0, 4 * b + i, 2);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t d_tmem = tmem_acc + (uint32_t)(i & 1) * (uint32_t)ncols;
+                    const uint32_t a_hi = tmem_a + (uint32_t)i * a_cols, a_lo = a_hi + 8u;
+                    // the two correction products first: the large hi * W_hi partial sums see the fewest truncating steps
+                    if (!EXP || !(p.flags & 1)) {
+#pragma unroll
+                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_lo + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, ks > 0);
+#pragma unroll
+                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_lo + (uint64_t)(16 * ks), idesc, 1);
+#pragma unroll
+                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, 1);
+                    }
+                    umma_commit(barAccFull + 8 * (i & 1));
+                    umma_commit(barAEmpty + 8 * i);
+                }
+                __syncwarp();
+                trace(0, 4 * b + i, 3);
+            }
+        }
+    } else if (warp < V4_REC_WARP0) {
+        // ===================== conversion: thread = (row, chunk half) =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");          // registers move from the conversion to the recursion warps
+        const int cw = warp, q = cw & 3, h = cw >> 2, r = q * 32 + lane;
+        const uint32_t c0 = (uint32_t)(h * NKS);                       // first chunk of this half
+        // per-thread addresses pinned in registers: left alone, the compiler re-derives them from %tid and the parameter block
+        // in every frame (special-register and indexed constant loads in front of the dependent TMEM / shared accesses)
+        const uint32_t raw0 = pin_reg(sRaw + (uint32_t)r * rw + 16u * c0);
+        const uint32_t ta0 = pin_reg(tmem_a + ((uint32_t)(q * 32) << 16));
+        const uint32_t sbS = pin_reg(smem_u32(smem + L.sb) + 16u * c0), sbB = sbS + 16u * nck;
+        const uint32_t lane0 = pin_reg(lane == 0 ? 1u : 0u);
+        const uint32_t sbytes = pin_reg(stage_bytes), fbytes = pin_reg(frame_bytes);
+        uint32_t G = 0, eph = 1;                                       // ring stage counter; A_empty phase to wait for
+        for (int b = 0; b < nblk; b++, G++, eph ^= 1u) {
+            const uint32_t s = G & 1u;
+            if (cw == 0) trace(2, 4 * b, 0);
+            mbar_wait(barRawFull + 8 * s, (G >> 1) & 1u);
+#pragma unroll
+            for (int fi = 0; fi < V3_FB; fi++) {
+                if (cw == 0) trace(2, 4 * b + fi, fi == 0 ? 1 : 0);
+                const uint32_t src = raw0 + s * sbytes + (uint32_t)fi * fbytes;
+                float4 x[NKS];
+#pragma unroll
+                for (int c = 0; c < NKS; c++) x[c] = v3_lds4(src + 16u * c);
+                mbar_wait(barAEmpty + 8 * fi, eph);
+                if (cw == 0) trace(2, 4 * b + fi, 2);
+                tc_fence_after();
+                const uint32_t ta = ta0 + (uint32_t)fi * a_cols;
+#pragma unroll
+                for (int c = 0; c < NKS; c++) {
+                    uint32_t hi[4], lo[4];
+                    if (EXP && (p.flags & 4)) {
+                        hi[0] = __float_as_uint(x[c].x); hi[1] = __float_as_uint(x[c].y); hi[2] = __float_as_uint(x[c].z); hi[3] = __float_as_uint(x[c].w);
+                        lo[0] = lo[1] = lo[2] = lo[3] = 0u;
+                    } else
+                        v3_split4(x[c], v3_lds4(sbS + 16u * c), v3_lds4(sbB + 16u * c), hi, lo);
+                    const uint32_t cg = c0 + (uint32_t)c;
+                    const uint32_t tc = ta + 16u * (cg >> 1) + 4u * (cg & 1u);      // chunk cg: 4 columns of the hi half, 4 of the lo half of its K step
+                    tmem_st4(tc, hi[0], hi[1], hi[2], hi[3]);
+                    tmem_st4(tc + 8u, lo[0], lo[1], lo[2], lo[3]);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane0) {
+                    mbar_arrive(barAFull + 8 * fi);
+                    if (fi == V3_FB - 1) mbar_arrive(barRawEmpty + 8 * s);
+                }
+                if (cw == 0) trace(2, 4 * b + fi, 3);
+            }
+        }
+    } else {
+        // ===================== recursion: thread = (row, model group) =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
+        const int rwp = warp - V4_REC_WARP0, q = rwp & 3, g = rwp >> 2, r = q * 32 + lane;
+        const int mbeg = p.mod0[g];
+        const uint32_t acc0 = pin_reg(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)mbeg * 8u);
+        const uint32_t acc1 = pin_reg(acc0 + (uint32_t)ncols);
+        const uint32_t lane0 = pin_reg(lane == 0 ? 1u : 0u);
+        const uint32_t bstride = pin_reg(p.Bpad);
+        uint32_t *const bpp = p.bp;
+        auto run = [&](auto MCc) {
+            constexpr int MC = decltype(MCc)::value;
+            float aex[MC];
+#pragma unroll
+            for (int k = 0; k < MC; k++) aex[k] = sTr[(mbeg + k) * TC_TRQ + 2].x;
+            // Rolling accumulator fetch: ev[k] holds model k's columns of the frame about to be stepped; as soon as a model has
+            // consumed its eight values, the same registers receive that model's columns of the NEXT frame, so the TMEM load
+            // latency, the wait and the hand-back of the stage (acc_empty) run under the arithmetic of the current frame.
+            uint32_t ev[MC][8];
+            if (my_tiles > 0) {
+                mbar_wait(barAccFull, 0);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < MC; k++) tmem_ld8(acc0 + 8u * k, ev[k]);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane0) mbar_arrive(barAccEmpty);
+            }
+            int tiles_left = my_tiles;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                tiles_left--;
+                const int ul = tile * TC_ROWS + r;
+                float W[MC][8], Wx[MC], base[MC];
+#pragma unroll
+                for (int k = 0; k < MC; k++) {
+                    Wx[k] = -INFINITY; base[k] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) W[k][j] = -INFINITY;
+                }
+                uint32_t bpo = (uint32_t)g * (uint32_t)Tpad * p.Bpad + (uint32_t)ul;
+                uint32_t sb = 0;
+                const int trole = rwp == 0 ? 3 : rwp == 15 ? 4 : -1;
+                const int fbase = ((tile - (int)blockIdx.x) / (int)gridDim.x) * Tpad;
+                // frame t0 + I: its columns are in ev; frame t0 + I + 1 (stage (I + 1) & 1, phase ((I + 1) >> 1) & 1 -- tiles start at a
+                // multiple of four frames) is fetched behind it unless this is the CTA's last frame
+                auto recurse = [&](auto Ic, auto GENc, int t0, bool more) {
+                    constexpr int I = decltype(Ic)::value;
+                    constexpr bool GEN = decltype(GENc)::value;
+                    constexpr int NS = (I + 1) & 1;
+                    const uint32_t nacc = NS ? acc1 : acc0;
+                    if (TRACE && trole >= 0) trace(trole, fbase + t0 + I, 0);
+                    if (!GEN || more) {
+                        mbar_wait(barAccFull + 8 * NS, ((I + 1) >> 1) & 1);
+                        tc_fence_after();
+                    }
+                    if (TRACE && trole >= 0) trace(trole, fbase + t0 + I, 1);
+                    const int t = t0 + I;
+                    if (!GEN) {
+                        if (EXP && (p.flags & 2)) {
+#pragma unroll
+                            for (int k = 0; k < MC; k++) { sb += ev[k][0]; tmem_ld8(nacc + 8u * k, ev[k]); }
+                        } else {
+                            // one sign-bit chain per model (independent instruction streams), merged bytewise
+                            uint32_t sbk[MC];
+#pragma unroll
+                            for (int k = 0; k < MC; k++) {
+                                sbk[k] = 0;
+                                v3_step(W[k], Wx[k], aex[k], ev[k], sbk[k]);
+                                tmem_ld8(nacc + 8u * k, ev[k]);
+                            }
+                            sb = sbk[0];
+                            if (MC == 2) sb = __byte_perm(sbk[0], sbk[1], 0x3340);
+                            if (MC == 3) sb = __byte_perm(__byte_perm(sbk[0], sbk[1], 0x3340), sbk[2], 0x3410);
+                        }
+                        if (!EXP || !(p.flags & 8)) bpp[bpo] = sb;
+                    } else {
+                        if (t < Tt) {
+                            if (t == 0) {
+#pragma unroll
+                                for (int k = 0; k < MC; k++) W[k][0] = sTr[(mbeg + k) * TC_TRQ + 2].y + __uint_as_float(ev[k][0]);   // ln A[0,1] + E[0,1] + ln A[1,1]
+                            } else if (t == 1) {
+#pragma unroll
+                                for (int k = MC - 1; k >= 0; k--) v3_step_entry(W[k], Wx[k], sTr[(mbeg + k) * TC_TRQ + 2].y, ev[k], sb);
+                            } else {
+#pragma unroll
+                                for (int k = MC - 1; k >= 0; k--) v3_step(W[k], Wx[k], aex[k], ev[k], sb);
+                            }
+                            bpp[bpo] = sb;
+                        }
+                        if (more) {
+#pragma unroll
+                            for (int k = 0; k < MC; k++) tmem_ld8(nacc + 8u * k, ev[k]);
+                        }
+                    }
+                    bpo += bstride;
+                    if (TRACE && trole >= 0) trace(trole, fbase + t0 + I, 2);
+                    if (!GEN || more) {
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane0) mbar_arrive(barAccEmpty + 8 * NS);            // the next frame's columns are in registers: its stage is free
+                    }
+                    if (TRACE && trole >= 0) trace(trole, fbase + t0 + I, 3);
+                };
+                constexpr std::integral_constant<bool, false> LEAN{};
+                constexpr std::integral_constant<bool, true> GENERIC{};
+                constexpr std::integral_constant<int, 0> F0{};
+                constexpr std::integral_constant<int, 1> F1{};
+                constexpr std::integral_constant<int, 2> F2{};
+                constexpr std::integral_constant<int, 3> F3{};
+                for (int t0 = 0; t0 < Tpad; t0 += V3_FB) {
+                    if (t0 != 0 && t0 + V3_FB < Tpad) {
+                        recurse(F0, LEAN, t0, true); recurse(F1, LEAN, t0, true); recurse(F2, LEAN, t0, true); recurse(F3, LEAN, t0, true);
+                    } else {
+                        const bool more = t0 + V3_FB < Tpad || tiles_left > 0;      // a frame follows the block's last one
+                        recurse(F0, GENERIC, t0, true); recurse(F1, GENERIC, t0, true); recurse(F2, GENERIC, t0, true); recurse(F3, GENERIC, t0, more);
+                    }
+                    if ((t0 & 4) != 0) {
+#pragma unroll
+                        for (int k = 0; k < MC; k++) v3_renorm(W[k], Wx[k], base[k]);
+                    }
+                }
+                if (ul < p.nu) {
+#pragma unroll
+                    for (int k = 0; k < MC; k++) {
+                        const float4 cm = sTr[(mbeg + k) * TC_TRQ + 2];
+                        const double sc = (Wx[k] > -INFINITY) ? ((double)Wx[k] + (double)base[k]) + ((double)cm.z + (double)cm.w) : -INFINITY;
+                        p.scores[(size_t)ul * M + mbeg + k] = sc;
+                    }
+                }
+            }
+        };
+        const int mcnt = p.nmod[g];
+        if (mcnt == 3) run(std::integral_constant<int, 3>{});
+        else if (mcnt == 2) run(std::integral_constant<int, 2>{});
+        else if (mcnt == 1) run(std::integral_constant<int, 1>{});
+        else __trap();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == V4_MMA_WARP) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // arg-max over models (strict >, first model wins: decoder.py:42-47) + back-trace of the winner from the packed words
 struct V3Map { int grp[16], shift[16]; };
 __global__ void __launch_bounds__(128)
@@ -418,9 +767,18 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
     const int M = m->M;
     const int Tt = (first_frames > 0 && first_frames < max_T) ? first_frames : max_T;
     if (Tt < 2 || ((uintptr_t)X & 15u) || nck % 2) return SAPR_OK;
-    // work split over the four worker groups: chunk pairs to the low groups, models to the high groups
     V3Params prm;
+    const char *vk_env = getenv("SAPR_VK");
+    const bool use_v4 = !(vk_env && vk_env[0] == '3') && (nck == 10 || nck == 4) && M >= TC_GROUPS;
     const int npairs = nck / 2;
+    if (use_v4) {      // models over the four recursion groups, as evenly as they go
+        int ma = 0;
+        for (int g = 0; g < TC_GROUPS; g++) {
+            prm.mod0[g] = ma; prm.nmod[g] = M / TC_GROUPS + (g < M % TC_GROUPS ? 1 : 0); ma += prm.nmod[g];
+            prm.pair0[g] = 0; prm.npair[g] = 0;
+        }
+    } else {
+    // work split over the four worker groups: chunk pairs to the low groups, models to the high groups
     if (npairs > 2 * TC_GROUPS || npairs < TC_GROUPS) return SAPR_OK;
     {
         int pc[TC_GROUPS], mcn[TC_GROUPS];
@@ -440,8 +798,10 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
             if (!ok) return SAPR_OK;
         }
     }
+    }
     const uint32_t rw = (uint32_t)(nck + 1) * 16u;
-    const V3Smem L = v3_smem_layout(M, nck, ncols, rw);
+    V3Smem L = v3_smem_layout(M, nck, ncols, rw);
+    if (use_v4) L.total = v4_smem_layout(M, nck, ncols, rw).total;
     if (L.total > 227 * 1024 || 2 * ncols + 4 * 8 * nck > 512) return SAPR_OK;
     const int Tpad = (Tt + V3_FB - 1) / V3_FB * V3_FB;
     const int64_t per_utt = (int64_t)TC_GROUPS * Tpad * sizeof(uint32_t);
@@ -463,7 +823,10 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
     V3Map map;
     for (int g = 0; g < TC_GROUPS; g++)
         for (int k = 0; k < prm.nmod[g]; k++) { map.grp[prm.mod0[g] + k] = g; map.shift[prm.mod0[g] + k] = 8 * k; }
-    auto kern = (nck == 10) ? k_viterbi_v3<5> : (nck == 4) ? k_viterbi_v3<2> : k_viterbi_v3<0>;
+    const int exp_flags = getenv("SAPR_V_EXP") ? atoi(getenv("SAPR_V_EXP")) : 0;
+    auto kern = use_v4 ? (nck == 10 ? (exp_flags ? k_viterbi_v4<5, false, true> : k_viterbi_v4<5>) : k_viterbi_v4<2>)
+                       : (nck == 10) ? k_viterbi_v3<5> : (nck == 4) ? k_viterbi_v3<2> : k_viterbi_v3<0>;
+    const int nthreads = use_v4 ? V4_THREADS : V3_THREADS;
     SAPR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     for (int u0 = 0; u0 < B; u0 += chunk) {
         const int nu = std::min(chunk, B - u0);
@@ -473,9 +836,34 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
         prm.sb = (const float *)((const char *)m->tc_image + w);
         prm.trp = (const float4 *)((const char *)m->tc_image + w + gsz);
         prm.bp = (uint32_t *)ctx->ws[0]; prm.Bpad = (uint32_t)chunk; prm.scores = (double *)ctx->ws[1]; prm.rw = rw;
+        prm.flags = exp_flags;
+        prm.trace = nullptr;
+        const char *trace_path = getenv("SAPR_V_TRACE");
+        if (trace_path && use_v4 && nck == 10 && u0 == 0) {      // tuning aid: one traced launch, stamps to a text file
+            const size_t nrec = (size_t)V4_TRACE_ROLES * V4_TRACE_FRAMES * 4;
+            long long *dtr = nullptr;
+            SAPR_CUDA(ctx, cudaMalloc(&dtr, nrec * sizeof(long long)));
+            SAPR_CUDA(ctx, cudaMemsetAsync(dtr, 0, nrec * sizeof(long long), ctx->stream));
+            prm.trace = dtr;
+            auto tk = k_viterbi_v4<5, true, false>;
+            SAPR_CUDA(ctx, cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+            tk<<<std::min(prm.ntiles, ctx->sm_count), nthreads, L.total, ctx->stream>>>(prm, tmap);
+            std::vector<long long> h(nrec);
+            cudaMemcpyAsync(h.data(), dtr, nrec * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(dtr);
+            if (FILE *fp = fopen(trace_path, "w")) {
+                for (int ro = 0; ro < V4_TRACE_ROLES; ro++)
+                    for (int fr = 0; fr < V4_TRACE_FRAMES; fr++)
+                        fprintf(fp, "%d %d %lld %lld %lld %lld\n", ro, fr, h[((size_t)ro * V4_TRACE_FRAMES + fr) * 4], h[((size_t)ro * V4_TRACE_FRAMES + fr) * 4 + 1],
+                                h[((size_t)ro * V4_TRACE_FRAMES + fr) * 4 + 2], h[((size_t)ro * V4_TRACE_FRAMES + fr) * 4 + 3]);
+                fclose(fp);
+            }
+            prm.trace = nullptr;
+        }
         {
             ProfScope ps(ctx, 0);
-            kern<<<std::min(prm.ntiles, ctx->sm_count), V3_THREADS, L.total, ctx->stream>>>(prm, tmap);
+            kern<<<std::min(prm.ntiles, ctx->sm_count), nthreads, L.total, ctx->stream>>>(prm, tmap);
         }
         SAPR_LAUNCH_CHECK(ctx);
         {
