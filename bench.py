@@ -10,7 +10,7 @@ One "step" = one pass of the fused Viterbi path (sapr_viterbi through the C ABI)
   value   : features already resident in HBM (3.2 GB per GPU > 126 MB L2, so no L2 flush is needed)
   e2e     : the same pass through the host-buffer entry point (sapr_viterbi_host): pinned host features ->
             chunked H2D overlapped with decoding -> words/scores/paths back to host, all inside the timed region
-  roofline: the dominant kernel (k_viterbi_fused) timed with CUDA events on the launching stream inside the
+  roofline: the dominant kernel (k_viterbi_v4) timed with CUDA events on the launching stream inside the
             timed region; algorithmic bytes = 31 412 B per utterance x utterances per launch
   cpu_baseline: the CPU oracle port (oracle/sapr_oracle.c, OpenMP) on a bounded sample of the same tensors
   estep   : secondary headline (configs[2] shape): Baum-Welch E-step + statistics (+ all-reduce + M-step)
@@ -244,12 +244,14 @@ def main():
     k_avg_ms = k_ms / max(k_n, 1)
     achieved = ALG_BYTES_PER_UTT * utt_per_launch / (k_avg_ms / 1e3) / 1e9
     tc = prec == engine.FP32 and os.environ.get("SAPR_TC", "1") != "0"
-    kname = "k_viterbi_tc<3,5> (tcgen05 emission, TMEM-resident operands, fused max-product recursion)" if tc \
-        else "k_viterbi_fused<R,u16,8> (SIMT emission)"
+    v4 = tc and os.environ.get("SAPR_V3", "1") != "0" and os.environ.get("SAPR_VK", "4") != "3"
+    kname = ("k_viterbi_v4<5> (TMA ring, conversion / tcgen05 emission / max-product recursion on separate warps, TMEM-resident operands)" if v4
+             else "k_viterbi_tc<3,5> (tcgen05 emission, TMEM-resident operands, fused max-product recursion)" if tc
+             else "k_viterbi_fused<R,u16,8> (SIMT emission)")
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        tj = json.load(open(tp)).get("k_viterbi_tc" if tc else "k_viterbi_fused")
+        tj = json.load(open(tp)).get("k_viterbi_v4" if v4 else "k_viterbi_tc" if tc else "k_viterbi_fused")
         if tj:
             traffic = tj["dram_bytes_per_launch"] / tj["utterances_per_launch"] * utt_per_launch
             traffic_src = tj["source"]
@@ -259,7 +261,7 @@ def main():
                 "avg_launch_ms": k_avg_ms, "alg_bytes_per_launch": ALG_BYTES_PER_UTT * utt_per_launch,
                 "kernel_share_of_step": k_ms / (ms_per_step * args.steps),
                 "finish_kernel_ms_per_step": f_ms / args.steps,
-                "note": ("instruction-issue bound (conversion + recursion share the SM sub-partitions' issue slots); "
+                "note": ("issue / ALU-pipe and hand-off latency bound (ncu: issue slots 67 % busy, ALU pipe 51 %, tensor pipe 58 %); "
                          "features are read once from HBM") if tc else "SIMT fp32 emission: FMA-issue bound (SURVEY 8d)"}
 
     # ---- end to end through the host-buffer C-ABI call (pinned host features) ----

@@ -31,7 +31,7 @@ struct V3Params {
     int mod0[TC_GROUPS], nmod[TC_GROUPS], pair0[TC_GROUPS], npair[TC_GROUPS];
     uint32_t rw;                        // bytes per row of the raw ring: (nck + 1) * 16
     long long *trace;                   // [V4_TRACE_ROLES][V4_TRACE_FRAMES][4] clock64 stamps of CTA 0 or null (SAPR_V_TRACE=file)
-    int flags;                          // tuning what-ifs (SAPR_V_EXP, k_viterbi_v4<.., EXP = true>): 1 = no MMAs, 2 = no recursion arithmetic, 4 = no conversion arithmetic, 8 = no back-pointer stores
+    int flags;                          // tuning what-ifs (SAPR_V_EXP, k_viterbi_v4<.., EXP = true>): 1 = no MMAs, 2 = no recursion arithmetic, 4 = no conversion arithmetic, 8 = no back-pointer stores, 16 = every tile of a CTA re-reads its first tile (L2 hits)
 };
 
 struct V3Smem { uint32_t w, raw, tr, sb, bar, total; };
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
             tma_prefetch_desc(&tmap);
             uint32_t G = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                const int urow = p.u0 + tile * TC_ROWS;
+                const int urow = (EXP && (p.flags & 16)) ? p.u0 + (int)blockIdx.x * TC_ROWS : p.u0 + tile * TC_ROWS;      // what-if 16: L2-resident features
                 for (int t0 = 0; t0 < Tpad; t0 += V3_FB, G++) {
                     const uint32_t s = G & 1u, ph = (G >> 1) & 1u;
                     const uint32_t bar = barRawFull + 8 * s;
@@ -479,6 +479,11 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
 #pragma unroll
             for (int i = 0; i < V3_FB; i++) {
                 trace(0, 4 * b + i, 0);
+                if (TRACE && blockIdx.x == 0 && lane == 0 && 4 * b + i < V4_TRACE_FRAMES) {      // wall clock (ns) beside the cycle stamp: the SM frequency under this kernel
+                    unsigned long long ns;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+                    p.trace[((size_t)0 * V4_TRACE_FRAMES + 4 * b + i) * 4 + 1] = (long long)ns;
+                }
                 mbar_wait2(barAFull + 8 * i, aph, barAccEmpty + 8 * (i & 1), ((i >> 1) & 1) ^ 1);
                 trace(0, 4 * b + i, 2);
                 tc_fence_after();
@@ -845,7 +850,7 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
             SAPR_CUDA(ctx, cudaMalloc(&dtr, nrec * sizeof(long long)));
             SAPR_CUDA(ctx, cudaMemsetAsync(dtr, 0, nrec * sizeof(long long), ctx->stream));
             prm.trace = dtr;
-            auto tk = k_viterbi_v4<5, true, false>;
+            auto tk = exp_flags ? k_viterbi_v4<5, true, true> : k_viterbi_v4<5, true, false>;
             SAPR_CUDA(ctx, cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
             tk<<<std::min(prm.ntiles, ctx->sm_count), nthreads, L.total, ctx->stream>>>(prm, tmap);
             std::vector<long long> h(nrec);

@@ -22,6 +22,9 @@ d = np.loadtxt(out).astype(np.int64)
 t0 = d[(d[:, 0] == 0) & (d[:, 1] == f0), 2][0]
 names = {0: "mma  [wait A_full | A_full ok | acc_empty ok | issued]", 1: "tma (per 4 frames) [ring stage free | issued | landed]",
          2: "conv w16 [start | raw ok (first of 4) | A_empty ok | A_full arrive]", 3: "rec w0 [wait acc_full | acc ok | acc_empty arrive | done]", 4: "rec w15"}
+mm = d[d[:, 0] == 0]
+a, b = mm[mm[:, 1] == 20][0], mm[mm[:, 1] == 220][0]
+print("SM clock under the kernel: %.0f MHz (%d cycles in %d ns over 200 frames)" % ((b[2] - a[2]) * 1e3 / (b[3] - a[3]), b[2] - a[2], b[3] - a[3]))
 for ro in range(5):
     print("role", ro, names.get(ro, ""))
     lo, hi = (f0 // 4, (f0 + nf) // 4 + 1) if ro == 1 else (f0, f0 + nf)
