@@ -166,7 +166,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sapr_b200")
     ap.add_argument("--utts", type=int, default=100_000, help="utterances per GPU")
-    ap.add_argument("--estep-utts", type=int, default=200_000, help="utterances per GPU for the E-step leg (0 = skip)")
+    ap.add_argument("--estep-utts", type=int, default=-1,
+                    help="utterances per GPU for the E-step leg (0 = skip; default: BASELINE configs[2], 1 M utterances in total, sharded over the GPUs)")
     ap.add_argument("--ergodic-utts", type=int, default=148 * 128,
                     help="utterances per GPU for the cfg 4 leg (N=256 dense states, T=1000; 0 = skip)")
     ap.add_argument("--audio-utts", type=int, default=8192,
@@ -291,10 +292,33 @@ def main():
                "call": "sapr_viterbi_host (chunked H2D on a copy stream overlapped with decoding)", "numa_node_rank0": numa}
         del Xh
 
+    # ---- strong-scaling entry: BASELINE configs[1] as worded, 100 k utterances IN TOTAL sharded over the GPUs ----
+    strong = None
+    if world > 1:
+        Bs = (100_000 + world - 1) // world
+        sb = engine.PackedBatch(X[:Bs * T_FRAMES], offsets[:Bs + 1], DIM, offs_host[:Bs + 1], labels[:Bs])
+        for _ in range(W):
+            models.viterbi(sb, None, prec, 0, want_scores=False, want_path=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            models.viterbi(sb, None, prec, 0, want_scores=False, want_path=True)
+        s1.record()
+        torch.cuda.synchronize()
+        sm = torch.tensor([s0.elapsed_time(s1) / args.steps], dtype=torch.float64, device=dev)
+        dist.max_(sm)
+        strong = {"scaling": "strong", "utterances_total": Bs * world, "utterances_per_gpu": Bs, "ms_per_step": float(sm.item()),
+                  "value": world * Bs * T_FRAMES * N_STATES * M_WORDS / (float(sm.item()) / 1e3), "unit": "updates/s",
+                  "tiles_per_gpu": (Bs + 127) // 128, "sms_per_gpu": 148,
+                  "note": "one 128-utterance tile per CTA: below 148 tiles per GPU the grid no longer fills the SMs"}
+        del sb
+
     # ---- secondary leg: Baum-Welch E-step (+ all-reduce + M-step) ----
     estep = None
-    if args.estep_utts > 0:
-        Be = args.estep_utts
+    if args.estep_utts != 0:
+        Be = args.estep_utts if args.estep_utts > 0 else (1_000_000 + world - 1) // world
         if Be != B:
             del X, batch
             torch.cuda.empty_cache()
@@ -396,19 +420,26 @@ def main():
         g_ms = float(gms.item())
         pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         tpeak = float(pk.get("bf16_tflops", 2250.0))
-        lf_bytes = 2.0 * Bg * Tg * Sg * 4            # emissions written once and read once
+        lf_bytes = 2.0 * Bg * Tg * Sg * 4            # emissions written once and read once (implementation traffic)
         fwd_tf = 4.0 * Bg * Tg * Sg * Sg / (ef_ms / n_it / 1e3) / 1e12
+        nk = 80                                       # K extent of the emission contraction: [x', x'^2, 1] for D = 39
+        alg_flops = float(Bg) * Tg * (2.0 * Sg * Sg + 2.0 * nk * Sg)      # one pass over each contraction, as the algorithm states it
+        alg_tf = alg_flops / (g_ms / 1e3) / 1e12
+        alg_in_bytes = float(Bg) * Tg * 40 * 4        # the features, read once
         ergodic = {"metric": "forward (score) state-pair updates/s, N=256 fully connected states",
                    "workload": f"cfg4: {Bg} utterances/GPU x T={Tg}, N={Sg}, D={DIM}, one dense model", "unit": "updates/s",
                    "value": world * Bg * Tg * Sg * Sg / (g_ms / 1e3), "ms_per_call": g_ms,
                    "mean_logprob_per_frame": float(lpg.mean().item()) / Tg,
                    "kernels": {"k_erg_emission_tc_ms": ee_ms / n_it, "k_erg_forward_tc_ms": ef_ms / n_it},
-                   "roofline": {"bound": "hbm", "achieved": lf_bytes / ((ee_ms + ef_ms) / n_it / 1e3) / 1e9, "peak": peak,
-                                "unit": "GB/s", "frac": lf_bytes / ((ee_ms + ef_ms) / n_it / 1e3) / 1e9 / peak,
-                                "note": "the two contractions are two kernels (TMEM cannot hold both 256-column accumulators "
-                                        "plus their A operands), coupled through fp32 emissions in HBM: 2 x N x 4 bytes per frame",
-                                "forward_tensor_tflops_fp16_hi_lo": fwd_tf, "tensor_peak_tflops": tpeak,
-                                "forward_tensor_frac": fwd_tf / tpeak}}
+                   "roofline": {"bound": "tensor", "achieved": alg_tf, "peak": tpeak, "unit": "TFLOP/s", "frac": alg_tf / tpeak,
+                                "alg_flops_per_call": alg_flops,
+                                "traffic": lf_bytes + alg_in_bytes, "alg_bytes_per_call": alg_in_bytes,
+                                "traffic_ratio": (lf_bytes + alg_in_bytes) / alg_in_bytes,
+                                "note": "algorithmic flops = frames x (2 S^2 + 2 K S), each contraction counted once (the kernels run fp16 hi + lo "
+                                        "passes: issued tensor work is about twice that); the two contractions are two kernels coupled through "
+                                        "fp32 emissions in HBM (2 x S x 4 bytes per frame on top of the feature read), so traffic is "
+                                        "(2 S 4 + 160) / 160 = 13.8 x the algorithmic input",
+                                "issued_forward_tensor_tflops_fp16_hi_lo": fwd_tf}}
         del Xg, lpg
         torch.cuda.empty_cache()
 
@@ -604,8 +635,9 @@ def main():
                            "N": N_STATES, "D": DIM, "topology": "sapr entry/exit (custom_hmm.py)",
                            "emission": "diagonal Gaussian", "sharding": f"utterances x{world}, no collective",
                            "l2": "inputs (3.2 GB/GPU) larger than L2; no flush needed"},
+                "estep": estep, "strong": strong,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "estep": estep, "ergodic": ergodic, "audio": audio_leg, "cfg1": cfg1}
+                "clocks": clocks, "ergodic": ergodic, "audio": audio_leg, "cfg1": cfg1}
         print(json.dumps(line), flush=True)
     dist.shutdown()
 

@@ -197,6 +197,18 @@ int64_t sapr_hl_stats_len(int S, int D);
 int sapr_hl_estep(sapr_ctx *ctx, sapr_models *m, int mi, const float *X, int ldx, const int64_t *offsets, int B,
                   int64_t total_frames, double *stats, double *logprob);
 
+/* ---- multi-GPU: the one collective of the path.  The reference accumulates gamma / xi / feature sums over all utterances
+ * in one process (custom_hmm.py:417-419, :434-439, :372-386); with utterances sharded over one process per GPU the packed
+ * statistics block (sapr_stats_stride doubles per model, + per-model log-likelihoods) is summed over the ranks once per
+ * Baum-Welch iteration.  NCCL is resolved at run time (dlopen libnccl.so.2).  uid128: 128 bytes from sapr_comm_unique_id on
+ * rank 0, handed to the other ranks by the host (any side channel).  sapr_stats_allreduce works in place on a DEVICE buffer
+ * and only enqueues on the context's stream. */
+typedef struct sapr_comm sapr_comm;
+int sapr_comm_unique_id(void *uid128);
+int sapr_comm_init_rank(sapr_ctx *ctx, const void *uid128, int rank, int world, sapr_comm **out);
+int sapr_stats_allreduce(sapr_ctx *ctx, sapr_comm *comm, double *stats, int64_t n);
+int sapr_comm_destroy(sapr_comm *comm);
+
 /* ---- MFCC front-end: assignment2/mfcc_extract.py:10-27 (librosa.feature.mfcc) as one fused
  * kernel: (pre-emphasis) -> framing + window -> DFT power -> mel filterbank -> log/dB -> DCT-II. */
 typedef struct {

@@ -65,6 +65,10 @@ SIGNATURES = {
     "sapr_hl_decode": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _i64, _vp, _vp]),
     "sapr_hl_stats_len": (_i64, [_i32, _i32]),
     "sapr_hl_estep": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _i64, _vp, _vp]),
+    "sapr_comm_unique_id": (_i32, [_vp]),
+    "sapr_comm_init_rank": (_i32, [_vp, _vp, _i32, _i32, _vp]),
+    "sapr_stats_allreduce": (_i32, [_vp, _vp, _vp, _i64]),
+    "sapr_comm_destroy": (_i32, [_vp]),
     "sapr_mfcc_num_frames": (_i64, [C.POINTER(MfccParams), _i64]),
     "sapr_mfcc": (_i32, [_vp, C.POINTER(MfccParams), _vp, _vp, _i32, _vp, _i32, _vp]),
 }

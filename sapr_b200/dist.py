@@ -80,10 +80,44 @@ class Dist:
                 torch.cuda.set_device(self.local_rank)
             td.init_process_group(backend=backend, rank=self.rank, world_size=self.world)
 
-    def allreduce_(self, t):
-        """In-place sum over ranks of one packed float64 buffer (57 KB at cfg 3: latency bound)."""
+        self._comm = None       # sapr_comm handle (C ABI, NCCL), created on the first device all-reduce
+        self._comm_ctx = None
+
+    def _native_comm(self, ctx):
+        """The library's own communicator (sapr_comm_init_rank): rank 0 draws the NCCL unique id, torch.distributed is
+        only the side channel that hands the 128 bytes to the other ranks."""
+        if self._comm is None:
+            import ctypes as C
+            import torch
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if self.rank == 0:
+                buf = (C.c_ubyte * 128)()
+                rc = ctx.lib.sapr_comm_unique_id(C.cast(buf, C.c_void_p))
+                if rc != 0:
+                    raise RuntimeError("sapr_comm_unique_id failed: libnccl.so.2 not loadable")
+                uid = torch.tensor(list(buf), dtype=torch.uint8)
+            dev_uid = uid.to(ctx.device) if self.td.get_backend() == "nccl" else uid
+            self.td.broadcast(dev_uid, src=0)
+            host = bytes(dev_uid.cpu().tolist())
+            h = C.c_void_p()
+            ctx.check(ctx.lib.sapr_comm_init_rank(ctx.h, C.c_char_p(host), self.rank, self.world, C.byref(h)))
+            self._comm, self._comm_ctx = h, ctx
+        return self._comm
+
+    def allreduce_(self, t, ctx=None):
+        """In-place sum over ranks of one packed float64 buffer (57 KB at cfg 3: latency bound).  Device float64 buffers go
+        through the C ABI (sapr_stats_allreduce: ncclAllReduce enqueued on the context's stream, no host sync); host
+        tensors (the gloo CPU tests) and other dtypes through torch.distributed."""
         if self.world > 1:
-            self.td.all_reduce(t, op=self.td.ReduceOp.SUM)
+            import torch
+            if t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and os.environ.get("SAPR_NATIVE_COMM", "1") != "0":
+                if ctx is None:
+                    from . import _lib
+                    ctx = _lib.default_context(t.device.index)
+                comm = self._native_comm(ctx)
+                ctx.check(ctx.lib.sapr_stats_allreduce(ctx.h, comm, t.data_ptr(), t.numel()))
+            else:
+                self.td.all_reduce(t, op=self.td.ReduceOp.SUM)
         return t
 
     def max_(self, t):
@@ -96,5 +130,10 @@ class Dist:
             self.td.barrier()
 
     def shutdown(self):
+        if self._comm is not None:
+            import torch
+            torch.cuda.synchronize()
+            self._comm_ctx.lib.sapr_comm_destroy(self._comm)
+            self._comm = None
         if self.world > 1 and self.td.is_initialized():
             self.td.destroy_process_group()
