@@ -619,6 +619,27 @@ def main():
                "sample": f"first {nu} utterances x 11 models of the same synth-v1 corpus, {dt:.1f} s "
                          f"(oracle/sapr_oracle.c float64, OpenMP {nt} threads); the Python reference itself runs "
                          f"~2.5e4 updates/s single-threaded (BASELINE.md)"}
+        # the reference's own Python (numpy custom_hmm.py / hmmlearn) does not travel to the GPU box: said here, not guessed
+        cpu["python_reference"] = {"unavailable": "frankcholula/sapr assignment2 is an unpackaged pure-Python project whose hmmlearn / librosa "
+                                                  "dependencies are in neither this image nor the wheelhouse; /root/reference does not exist on the "
+                                                  "GPU box (BASELINE.md quotes ~2.5e4 updates/s single-threaded for custom_hmm.py on other hardware)"}
+        # Rung 2: the hmmlearn GaussianHMM path (forward-backward statistics of one 10-state dense model, float64), restated in C
+        try:
+            from oracle import oracle as orc
+            S2 = N_STATES + 2
+            rng2 = np.random.default_rng(SEED + 5)
+            nu_h = 4096
+            Xh2 = Xs.cpu().numpy()[:nu_h * T_FRAMES, :DIM].astype(np.float64)
+            offh2 = np.arange(nu_h + 1, dtype=np.int64) * T_FRAMES
+            tmh = rng2.dirichlet(np.ones(S2), size=S2); sph = rng2.dirichlet(np.ones(S2))
+            mh = rng2.standard_normal((S2, DIM)); vh = rng2.uniform(0.5, 1.5, (S2, DIM))
+            th = time.perf_counter()
+            orc.hl_estep(Xh2, offh2, sph, tmh, mh, vh)
+            dth = time.perf_counter() - th
+            cpu["hmmlearn_restatement"] = {"value": nu_h * T_FRAMES * S2 / dth, "unit": "frame*state updates/s (fit E-step, 10 dense states)", "cores": 1,
+                                           "kind": "port", "sample": f"{nu_h} utterances, {dth:.1f} s (oracle orc_hl_estep, scalar float64)"}
+        except Exception as ex:
+            cpu["hmmlearn_restatement"] = {"error": repr(ex)}
         if estep is not None:
             v2, nu2, _, dt2 = cpu_sample(Xs.cpu().numpy(), offs_s.cpu().numpy(), labs_s.cpu().numpy(), A, means, var,
                                          "estep", 6.0)

@@ -197,6 +197,11 @@ int64_t sapr_hl_stats_len(int S, int D);
 int sapr_hl_estep(sapr_ctx *ctx, sapr_models *m, int mi, const float *X, int ldx, const int64_t *offsets, int B,
                   int64_t total_frames, double *stats, double *logprob);
 
+/* ---- evaluation metrics: assignment2/eval.py:28-38 (sklearn confusion_matrix + accuracy_score over the label indices).
+ * truth / pred int32[B] (device), cm int64[M][M + 1] (device, zeroed by the call; column M = no model reachable, pred < 0),
+ * correct int64[1] (device). */
+int sapr_confusion(sapr_ctx *ctx, const int32_t *truth, const int32_t *pred, int B, int M, int64_t *cm, int64_t *correct);
+
 /* ---- multi-GPU: the one collective of the path.  The reference accumulates gamma / xi / feature sums over all utterances
  * in one process (custom_hmm.py:417-419, :434-439, :372-386); with utterances sharded over one process per GPU the packed
  * statistics block (sapr_stats_stride doubles per model, + per-model log-likelihoods) is summed over the ranks once per

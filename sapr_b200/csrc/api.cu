@@ -365,3 +365,39 @@ extern "C" int sapr_init_stats(sapr_ctx *ctx, const float *X, int ldx, const int
     SAPR_LAUNCH_CHECK(ctx);
     return SAPR_OK;
 }
+
+// ----------------------------------------------------------------------------------------------
+// evaluation metrics on the device (assignment2/eval.py:28-38: confusion_matrix + accuracy_score over the label indices):
+// cm[t][p] counts (true word t, predicted word p); an utterance with no reachable model (predicted -1) goes to column M.
+__global__ void k_confusion(const int32_t *__restrict__ truth, const int32_t *__restrict__ pred, int B, int M,
+                            unsigned long long *__restrict__ cm, unsigned long long *__restrict__ correct) {
+    extern __shared__ unsigned int s_cm[];          // [M][M + 1] per CTA, flushed with one atomic per cell
+    const int cells = M * (M + 1);
+    for (int i = threadIdx.x; i < cells + 1; i += blockDim.x) s_cm[i] = 0;
+    __syncthreads();
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < B; u += gridDim.x * blockDim.x) {
+        const int t = truth[u];
+        int q = pred[u];
+        if (t < 0 || t >= M) continue;
+        if (q < 0 || q >= M) q = M;
+        atomicAdd(&s_cm[t * (M + 1) + q], 1u);
+        if (q == t) atomicAdd(&s_cm[cells], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cells; i += blockDim.x)
+        if (s_cm[i]) atomicAdd(&cm[i], (unsigned long long)s_cm[i]);
+    if (threadIdx.x == 0 && s_cm[cells]) atomicAdd(correct, (unsigned long long)s_cm[cells]);
+}
+
+extern "C" int sapr_confusion(sapr_ctx *ctx, const int32_t *truth, const int32_t *pred, int B, int M, int64_t *cm, int64_t *correct) {
+    if (!ctx || !truth || !pred || !cm || !correct || M <= 0 || B < 0) return SAPR_E_INVALID;
+    if ((size_t)(M * (M + 1) + 1) * sizeof(unsigned int) > 48 * 1024) SAPR_FAIL(ctx, SAPR_E_RANGE, "confusion: vocabulary too large (M <= 109)");
+    SAPR_CUDA(ctx, cudaMemsetAsync(cm, 0, sizeof(int64_t) * (size_t)M * (M + 1), ctx->stream));
+    SAPR_CUDA(ctx, cudaMemsetAsync(correct, 0, sizeof(int64_t), ctx->stream));
+    if (B == 0) return SAPR_OK;
+    const int grid = std::max(1, std::min(ctx->sm_count, (B + 255) / 256));
+    k_confusion<<<grid, 256, (size_t)(M * (M + 1) + 1) * sizeof(unsigned int), ctx->stream>>>(truth, pred, B, M, (unsigned long long *)cm,
+                                                                                              (unsigned long long *)correct);
+    SAPR_LAUNCH_CHECK(ctx);
+    return SAPR_OK;
+}

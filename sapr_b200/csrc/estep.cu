@@ -138,6 +138,7 @@ k_estep_fused(const float *__restrict__ X, int ldx, const int64_t *__restrict__ 
         for (int j = 0; j < NMAX; j++) if (j < N) { sa[row + (size_t)j * 32] = a[j]; se[row + (size_t)j * 32] = e[j]; }
     }
     // reported log-likelihood: logaddexp.reduce(alpha[T-1, :]) - max(alpha)
+    bool xi_live = true;
     if (T > 0) {
         R r = (T == 1) ? R(0) : NINF;                  // alpha[T-1, entry]
 #pragma unroll
@@ -145,6 +146,11 @@ k_estep_fused(const float *__restrict__ X, int ldx, const int64_t *__restrict__ 
         r = lae(r, ax);
         double scale = anan ? (double)NAN : amax;
         loglik[u] = ((double)r + base) - scale;
+        // the reference's un-normalised xi (custom_hmm.py:270-316) is exp(alpha + ln a + e + beta - logsumexp(alpha[T-1]));
+        // summed over the arcs of a frame that is P(O, path ends in exit) / sum(alpha[T-1]) = exp(ax - r) for every frame, so when
+        // ax - r < ln(2^-1075) every arc underflows to 0 in float64, the `if np.sum(xi[t]) > 0` guard (:319) skips the
+        // normalisation and the utterance adds nothing to the transition statistics.
+        xi_live = !((double)ax - (double)r < -745.13);
     }
 
     // ---------------- backward + gamma + xi (custom_hmm.py:213-322) ----------------
@@ -203,7 +209,7 @@ k_estep_fused(const float *__restrict__ X, int ldx, const int64_t *__restrict__ 
                 gG[j] += g; gO[j] += g;
                 if (go) go[j] = g;
                 R xs = at[j] + self[j];
-                if (xn > NINF && xs > NINF) gX[j] += fexp(xs - xn);
+                if (xi_live && xn > NINF && xs > NINF) gX[j] += fexp(xs - xn);
             }
         }
         // next beta, renormalised (offsets cancel in gamma / xi, so they are not kept)

@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
             float U[8], ax = -INFINITY, base = 0.f;
             float best_mx = 0.f, best_base = 0.f;
             double ll = 0.0;
-            bool exit_ok = false;
+            bool exit_ok = false, xi_live = true;
 #pragma unroll
             for (int j = 0; j < 8; j++) U[j] = -INFINITY;
             for (int t = 0; t < T; t++) {
@@ -427,6 +427,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
                     rr = eg_lae(rr, ax);
                     ll = ((double)rr + (double)base) - ((double)best_mx + (double)best_base);
                     exit_ok = (T > 1) && (ax > -INFINITY);
+                    xi_live = !(ax - rr < -745.13f);      // SURVEY D10 (see k_estep_fused): the reference's float64 xi underflows for the whole utterance
                 }
                 const float sh = (t == 0) ? 0.f : rintf(fminf(fmaxf(mx, -4194304.f), 4194304.f));
 #pragma unroll
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
                     const float xsum = (sum - pj[7]) + q7 + pe;
                     sum += pe;
                     const float inv = 1.0f / sum;
-                    const float xinv = (mxl > -INFINITY && xsum > 0.f) ? 1.0f / xsum : 0.f;
+                    const float xinv = (xi_live && mxl > -INFINITY && xsum > 0.f) ? 1.0f / xsum : 0.f;
                     float gm[8];
 #pragma unroll
                     for (int j = 0; j < 8; j++) {

@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_estep_tc(const EtParams p) {
                 float U[8], ax = -INFINITY, base = 0.f;
                 float best_mx = 0.f, best_base = 0.f;        // max over all alpha cells = best_mx + best_base; alpha[0,0] = 0
                 double ll = 0.0;
-                bool exit_ok = false;
+                bool exit_ok = false, xi_live = true;
 #pragma unroll
                 for (int j = 0; j < 8; j++) U[j] = -INFINITY;
                 for (int t = 0; t < Tt; t++, f++) {
@@ -425,6 +425,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_estep_tc(const EtParams p) {
                             rr = lae32(rr, ax);
                             ll = ((double)rr + (double)base) - ((double)best_mx + (double)best_base);
                             exit_ok = (T > 1) && (ax > -INFINITY);
+                            xi_live = !(ax - rr < -745.13f);      // SURVEY D10 (see k_estep_fused): the reference's float64 xi underflows for the whole utterance
                         }
                         // renormalise with an integer shift (exactly representable running offset)
                         const float sh = (t == 0) ? 0.f : rintf(fminf(fmaxf(mx, -4194304.f), 4194304.f));   // frame 0 stays unshifted (alpha[0, entry] = 0)
@@ -509,7 +510,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_estep_tc(const EtParams p) {
                         const float xsum = (sum - pj[7]) + q7 + pe;
                         sum += pe;
                         const float inv = 1.0f / sum;                                // all -inf row -> NaN like the reference
-                        const float xinv = (mxl > -INFINITY && xsum > 0.f) ? 1.0f / xsum : 0.f;
+                        const float xinv = (xi_live && mxl > -INFINITY && xsum > 0.f) ? 1.0f / xsum : 0.f;
                         float gm[8];
 #pragma unroll
                         for (int j = 0; j < 8; j++) {

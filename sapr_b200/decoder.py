@@ -75,11 +75,18 @@ class Decoder:
             self._dev = dev
         return self._dev
 
-    def decode_batch(self, features: List[np.ndarray]):
-        """features: list of (D, T_u) arrays.  Returns (words, scores, paths) for the whole list."""
+    def decode_batch(self, features: List[np.ndarray], true_labels=None):
+        """features: list of (D, T_u) arrays.  Returns (words, scores, paths) for the whole list; with ``true_labels``
+        (vocabulary indices) the confusion counts and the accuracy of eval.py:28-38 are accumulated on the device from the
+        kernel's predictions and left in ``self.last_confusion`` = (int64 [M, M + 1] array, accuracy)."""
         dev = self._word_models()
         batch = PackedBatch.from_features(features)
         out = dev.viterbi(batch, None, FP64 if self.precision == "fp64" else FP32, 0, want_path=True)
+        if true_labels is not None:
+            import torch
+            from .engine import confusion_on_device
+            cm, acc = confusion_on_device(torch.as_tensor(np.asarray(true_labels, dtype=np.int32)), out["best_word"], len(self.vocab), dev.ctx)
+            self.last_confusion = (cm.cpu().numpy(), acc)
         bw = out["best_word"].cpu().numpy(); bs = out["best_score"].cpu().numpy(); p = out["path"].cpu().numpy()
         offs = batch.offsets_host
         words = [self.vocab[i] if i >= 0 else None for i in bw]

@@ -297,3 +297,18 @@ def train_words(models: WordModels, batch: PackedBatch, labels, n_iter: int, flo
         prev = tot
         models.mstep(stats, floor_var)
     return np.asarray(history)
+
+
+def confusion_on_device(truth, pred, M: int, ctx=None):
+    """eval.py:28-38 on the device: (cm int64 [M, M + 1] tensor, accuracy) from int32 label / prediction tensors that
+    stay on the GPU (the predictions are the Viterbi kernel's best_word output); column M counts utterances no model reaches."""
+    torch = _torch()
+    ctx = ctx or _lib.default_context()
+    truth = truth.to(device=pred.device, dtype=torch.int32).contiguous()
+    pred = pred.to(dtype=torch.int32).contiguous()
+    B = int(pred.numel())
+    cm = torch.empty((M, M + 1), dtype=torch.int64, device=pred.device)
+    correct = torch.empty(1, dtype=torch.int64, device=pred.device)
+    ctx.check(ctx.lib.sapr_confusion(ctx.h, ptr(truth), ptr(pred), B, M, ptr(cm), ptr(correct)))
+    acc = float(correct.item()) / B if B else float("nan")
+    return cm, acc

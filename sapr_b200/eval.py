@@ -51,7 +51,8 @@ def decode_vocabulary_batched(decoder: Decoder, feature_set_path: str) -> Dict[s
     """Same result dictionary as Decoder.decode_vocabulary, one Viterbi launch for the whole set."""
     per_word = {word: load_mfccs_by_word(feature_set_path, word) for word in decoder.vocab}
     flat = [f for word in decoder.vocab for f in per_word[word]]
-    words, scores, paths = decoder.decode_batch(flat) if flat else ([], [], [])
+    truth = [i for i, word in enumerate(decoder.vocab) for _ in per_word[word]]
+    words, scores, paths = decoder.decode_batch(flat, true_labels=truth) if flat else ([], [], [])
     all_results, k = {}, 0
     for word in decoder.vocab:
         res = []
@@ -72,7 +73,14 @@ def eval_hmm(implementation: Literal["custom", "hmmlearn"] = "hmmlearn", feature
     else:
         all_results = decoder.decode_vocabulary(feature_set_path, verbose=False)
     true_labels, predicted_labels = extract_labels(all_results)
-    cm, accuracy = calculate_metrics(true_labels, predicted_labels, decoder.vocab)
+    dev_cm = getattr(decoder, "last_confusion", None) if batched else None
+    if dev_cm is not None and None not in predicted_labels:
+        # counts accumulated on the device (sapr_confusion); rows / columns restricted to the labels that occur, as sklearn does
+        full, accuracy = dev_cm
+        present_idx = np.nonzero((full[:, :-1].sum(axis=0) + full[:, :-1].sum(axis=1)) > 0)[0]
+        cm = full[np.ix_(present_idx, present_idx)]
+    else:
+        cm, accuracy = calculate_metrics(true_labels, predicted_labels, decoder.vocab)
     present = sorted({decoder.vocab.index(w) for w in true_labels + predicted_labels})
     names = [decoder.vocab[i] for i in present]
     cm_df = pd.DataFrame(cm, index=names, columns=names)

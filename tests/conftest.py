@@ -41,6 +41,13 @@ def rung1_d13():
 
 
 @pytest.fixture(scope="session")
+def rung1_mismatch_d39():
+    """Models moved off the generating parameters (an early Baum-Welch iteration): contains utterances whose xi underflows in
+    the reference's float64 arithmetic and therefore drop out of the transition statistics."""
+    return load_golden("rung1_mismatch_d39")
+
+
+@pytest.fixture(scope="session")
 def edge():
     return load_golden("edge_cases")
 

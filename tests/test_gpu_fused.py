@@ -149,11 +149,13 @@ def test_viterbi_short_utterances(eng, edge, T):
     assert np.array_equal(o_tc["all_paths"].cpu().numpy()[0, 37:37 + T], edge[f"T{T}_dec_path"])
 
 
-@pytest.mark.parametrize("name", ["rung1_d39", "rung1_d13"])
+@pytest.mark.parametrize("name", ["rung1_d39", "rung1_d13", "rung1_mismatch_d39"])
 @pytest.mark.parametrize("prec", ["fp64", "fp32"])
 def test_estep_vs_reference(eng, name, prec, request):
     import torch
     g = request.getfixturevalue(name)
+    if name == "rung1_mismatch_d39":
+        assert int((g["es_xi_rows_zero"] >= 39).sum()) >= 1      # the golden exercises the D10 underflow (whole utterances without xi)
     feats = split_features(g)
     m = _models(eng, g)
     batch = eng.PackedBatch.from_features(feats)
@@ -184,7 +186,7 @@ def test_estep_vs_reference(eng, name, prec, request):
         assert np.max(np.abs(st["s2"] - o2) / scale ** 2) < tol * 60 * 10
 
 
-@pytest.mark.parametrize("name", ["rung1_d39", "rung1_d13"])
+@pytest.mark.parametrize("name", ["rung1_d39", "rung1_d13", "rung1_mismatch_d39"])
 @pytest.mark.parametrize("prec", ["fp64", "fp32"])
 def test_mstep_vs_reference_baum_welch_iteration(eng, name, prec, request):
     """One E-step + M-step for all words at once == the reference's baum_welch(max_iter=1) per word

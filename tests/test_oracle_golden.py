@@ -96,7 +96,7 @@ def test_decode_errors_like_reference(rung0):
         h.decode(feats[0][:, :10])       # T_frames < D
 
 
-@pytest.mark.parametrize("name", ["rung1_d39", "rung1_d13"])
+@pytest.mark.parametrize("name", ["rung1_d39", "rung1_d13", "rung1_mismatch_d39"])
 def test_rung1_per_function_and_estep(name, request):
     g = request.getfixturevalue(name)
     feats = split_features(g)
@@ -124,7 +124,7 @@ def test_rung1_per_function_and_estep(name, request):
         assert_close(stats[w, 2 * S:3 * S], g["es_occ"][sel].sum(0) * emit, 0, 1e-10, what="occ")
 
 
-@pytest.mark.parametrize("name", ["rung1_d39", "rung1_d13"])
+@pytest.mark.parametrize("name", ["rung1_d39", "rung1_d13", "rung1_mismatch_d39"])
 def test_rung1_baum_welch_one_iteration(name, request):
     g = request.getfixturevalue(name)
     feats = split_features(g)
