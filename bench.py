@@ -230,6 +230,7 @@ def main():
     t1 = time.time()
     dist.barrier()
     launches = ctx.launches() - l0
+    flagged = ctx.viterbi_flagged()          # word near-ties of the last step, re-decoded in float64 inside the call
     k_ms, k_n = ctx.profile_read(0)
     f_ms, f_n = ctx.profile_read(1)
     ctx.profile(False)
@@ -656,6 +657,7 @@ def main():
                            "N": N_STATES, "D": DIM, "topology": "sapr entry/exit (custom_hmm.py)",
                            "emission": "diagonal Gaussian", "sharding": f"utterances x{world}, no collective",
                            "l2": "inputs (3.2 GB/GPU) larger than L2; no flush needed"},
+                "word_near_ties_redecoded_f64_per_step": flagged,
                 "estep": estep, "strong": strong,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "ergodic": ergodic, "audio": audio_leg, "cfg1": cfg1}

@@ -99,6 +99,12 @@ int sapr_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const i
                  int64_t total_frames, int max_T, const int32_t *model_of_utt, int precision,
                  int first_frames, int32_t *best_word, double *best_score, double *scores,
                  uint8_t *best_path, uint8_t *all_paths);
+/* fp32 production mode (tensor-core kernels, all models, all_paths == NULL): an utterance whose best and second-best word
+ * scores differ by less than 8e-6 |best| -- closer than the fp32 scores resolve -- is re-decoded in float64 inside the same
+ * call (word, score, score row and path then are the verification mode's), so the recognised word equals the float64 one
+ * except on exact float64 ties (decoder.py:42-47 keeps the first).  n = utterances flagged by the last call on this context
+ * (synchronises the stream); at most 8192 per 1 GB scratch chunk are re-decoded.  SAPR_EXACT_WORDS=0 disables the pass. */
+int sapr_viterbi_flagged(sapr_ctx *ctx, int64_t *n);
 
 /* Parity/debug: the tensor-core emission tile of the fused Viterbi kernel written out, E_out float32
  * [sum_T][*ncols_out], column m*8 + (j-1) = state j of model m (compute_emission_matrix, custom_hmm.py:146-174,

@@ -65,6 +65,7 @@ SIGNATURES = {
     "sapr_hl_decode": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _i64, _vp, _vp]),
     "sapr_hl_stats_len": (_i64, [_i32, _i32]),
     "sapr_hl_estep": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _i64, _vp, _vp]),
+    "sapr_viterbi_flagged": (_i32, [_vp, _vp]),
     "sapr_confusion": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "sapr_comm_unique_id": (_i32, [_vp]),
     "sapr_comm_init_rank": (_i32, [_vp, _vp, _i32, _i32, _vp]),
@@ -128,6 +129,12 @@ class Context:
 
     def sync(self):
         self.check(self.lib.sapr_sync(self.h))
+
+    def viterbi_flagged(self) -> int:
+        """Utterances the last fp32 Viterbi call flagged as word near-ties and re-decoded in float64."""
+        n = _i64(0)
+        self.check(self.lib.sapr_viterbi_flagged(self.h, C.byref(n)))
+        return int(n.value)
 
     def profile(self, enable: bool):
         self.check(self.lib.sapr_profile(self.h, int(enable)))

@@ -38,6 +38,8 @@ struct sapr_ctx {
     std::vector<ProfRec> prof_pool;  // recycled event pairs
     // sapr_estep_grouped: the tile table of the last call (re-uploaded only when the grouping changes)
     std::vector<int32_t> eg_tab;
+    bool flag_valid = false;         // ws[5] holds the flag counters of the last fp32 Viterbi call (sapr_viterbi_flagged)
+    int flag_maxT = 0, flag_M = 0;   // longest utterance / models of that call (size the re-decoding scratch)
 };
 
 // RAII bracket: records an event pair around one kernel launch when profiling is on
@@ -114,6 +116,30 @@ struct sapr_models {
             return SAPR_E_CUDA;                                                  \
         }                                                                        \
     } while (0)
+
+// fp32 production Viterbi: utterances whose best and second-best word scores are closer than the fp32 scores resolve are
+// listed (arg-max kernels) and re-decoded in float64 (sapr_viterbi_redo_flagged), so the recognised word is the float64 one
+struct SaprFlag {
+    int32_t *list = nullptr;    // [cap] utterance indices
+    int32_t *count = nullptr;   // [0] entries of this chunk (may exceed cap: the surplus is not re-decoded), [1] running total of the call
+    int cap = 0;
+    float rel = 0.f;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ void sapr_flag_word(const SaprFlag &f, int u, double best, double second) {
+    if (!f.list || !(best > -INFINITY) || !(second > -INFINITY)) return;
+    if (best - second < (double)f.rel * fabs(best)) {
+        const int pos = atomicAdd(f.count, 1);
+        atomicAdd(f.count + 1, 1);
+        if (pos < f.cap) f.list[pos] = u;
+    }
+}
+#endif
+#define SAPR_FLAG_CAP 8192
+#define SAPR_FLAG_REL 8e-6f
+int sapr_viterbi_redo_flagged(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int first_frames,
+                              const SaprFlag &flag, int32_t *best_word, double *best_score, double *scores, uint8_t *best_path);
+int sapr_flag_setup(sapr_ctx *ctx, SaprFlag *flag, bool first_chunk);   // workspace slot 5; zeroes the per-chunk counter
 
 int sapr_ws_reserve(sapr_ctx *ctx, int slot, size_t bytes);   // grows ctx->ws[slot]
 int sapr_pin_reserve(sapr_ctx *ctx, int slot, size_t bytes);  // grows ctx->pin[slot]

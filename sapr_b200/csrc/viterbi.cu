@@ -52,7 +52,12 @@ __global__ void __launch_bounds__(32 * 16)
 k_viterbi_fused(const float *__restrict__ X, int ldx, const int64_t *__restrict__ offsets, int u0, int nu, int M,
                 int N, int nchunk, const R *__restrict__ pk, const R *__restrict__ cst_g, const R *__restrict__ la_g,
                 const R *__restrict__ lb_g, const int32_t *__restrict__ model_of_utt, int first_frames,
-                BP *__restrict__ bp, int64_t Bpad, int maxT, int nslots, double *__restrict__ scores) {
+                BP *__restrict__ bp, int64_t Bpad, int maxT, int nslots, double *__restrict__ scores,
+                const int32_t *__restrict__ utt_list = nullptr, const int32_t *__restrict__ utt_count = nullptr,
+                const R *__restrict__ E_pre = nullptr) {
+    // utt_list / utt_count: decode the listed utterances only (the float64 re-decoding of the utterances the fp32 pass flagged);
+    // the scratch and the score rows are then indexed by the position in the list.  E_pre: the emissions of the listed
+    // utterances, computed frame-parallel by k_redo_emission with the same operation order ([list pos][model][frame][8])
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *spk = reinterpret_cast<R *>(smem_raw);
     const int S = N + 2;
@@ -60,6 +65,7 @@ k_viterbi_fused(const float *__restrict__ X, int ldx, const int64_t *__restrict_
     const bool own = (model_of_utt != nullptr);
     const int m0 = own ? 0 : blockIdx.y * blockDim.y;
     const int nm = own ? M : min((int)blockDim.y, M - m0);
+    if (utt_list && (int)blockIdx.x * 32 >= min(*utt_count, nu)) return;      // blocks beyond the list leave before staging anything
     {   // stage the packed emission parameters of this CTA's models
         const int tid = threadIdx.y * 32 + threadIdx.x, nt = blockDim.x * blockDim.y;
         const R *src = pk + (size_t)m0 * per_model;
@@ -69,7 +75,8 @@ k_viterbi_fused(const float *__restrict__ X, int ldx, const int64_t *__restrict_
     const int ul = blockIdx.x * 32 + threadIdx.x;   // utterance within this chunk
     const int slot = own ? 0 : m0 + threadIdx.y;
     if (ul >= nu || slot >= nslots || (own && threadIdx.y > 0)) return;
-    const int u = u0 + ul;
+    if (utt_list && ul >= min(*utt_count, nu)) return;
+    const int u = utt_list ? utt_list[ul] : u0 + ul;
     const int m = own ? model_of_utt[u] : slot;
     const R *spk_model = spk + (size_t)(m - m0) * per_model;
 
@@ -93,13 +100,22 @@ k_viterbi_fused(const float *__restrict__ X, int ldx, const int64_t *__restrict_
     for (int j = 0; j <= NMAX; j++) V[j] = NINF;
     R Vx = NINF;
     double base = 0.0;
+    const R *ep = E_pre ? E_pre + ((size_t)ul * nslots + slot) * maxT * 8 : nullptr;
+    auto emit = [&](int t) {
+        if (ep) {
+#pragma unroll
+            for (int j = 0; j < NMAX; j++) e[j] = (j < N && j < 8) ? ep[(size_t)t * 8 + j] : R(0);
+        } else {
+            emit_diag<R, NMAX>(X + (size_t)(off + t) * ldx, nchunk, N, spk_model, cst, e);
+        }
+    };
     if (Te > 0) {
-        emit_diag<R, NMAX>(X + (size_t)off * ldx, nchunk, N, spk_model, cst, e);
+        emit(0);
         V[0] = lb[0] + e[0];   // V[0,1] = ln A01 + E[0,1]   (custom_hmm.py:473)
     }
     BP *bpp = bp + ((size_t)slot * maxT) * Bpad + ul;
     for (int t = 1; t < Te; t++) {
-        emit_diag<R, NMAX>(X + (size_t)(off + t) * ldx, nchunk, N, spk_model, cst, e);
+        emit(t);
         unsigned bits = 0;
         // exit state first (reads the old V[N-1]); open only for t >= N (custom_hmm.py:481-485)
         R nx = NINF;
@@ -212,13 +228,15 @@ __global__ void __launch_bounds__(128)
 k_viterbi_finish_fast(const int64_t *__restrict__ offsets, int u0, int nu, int N, int nslots,
                       const int32_t *__restrict__ model_of_utt, int first_frames, const BP *__restrict__ bp, int64_t Bpad,
                       int maxT, const double *__restrict__ scores, int32_t *__restrict__ best_word,
-                      double *__restrict__ best_score, double *__restrict__ scores_out, uint8_t *__restrict__ best_path) {
+                      double *__restrict__ best_score, double *__restrict__ scores_out, uint8_t *__restrict__ best_path,
+                      const int32_t *__restrict__ utt_list = nullptr, const int32_t *__restrict__ utt_count = nullptr,
+                      SaprFlag flag = SaprFlag()) {
     constexpr int CH = 32;
     __shared__ uint8_t sp[4][32][CH + 4];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int ul = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = ul < nu;
-    const int u = u0 + ul;
+    const bool live = ul < (utt_list ? min(*utt_count, nu) : nu);
+    const int u = live ? (utt_list ? utt_list[ul] : u0 + ul) : 0;
     const int S = N + 2;
     int64_t off = 0;
     int Te = 0;
@@ -228,13 +246,16 @@ k_viterbi_finish_fast(const int64_t *__restrict__ offsets, int u0, int nu, int N
         off = offsets[u];
         const int T = (int)(offsets[u + 1] - off);
         Te = (first_frames > 0 && first_frames < T) ? first_frames : T;
+        double second = -INFINITY;
         for (int s = 0; s < nslots; s++) {
             const double sc = scores[(size_t)ul * nslots + s];
             if (scores_out) scores_out[(size_t)u * nslots + s] = sc;
-            if (sc > bs) { bs = sc; bslot = s; }
+            if (sc > bs) { second = bs; bs = sc; bslot = s; }
+            else if (sc > second) second = sc;
         }
         if (best_word) best_word[u] = (bslot < 0) ? -1 : (model_of_utt ? model_of_utt[u] : bslot);
         if (best_score) best_score[u] = bs;
+        sapr_flag_word(flag, u, bs, second);
     }
     if (!best_path) return;
     const int wslot = bslot < 0 ? 0 : bslot;
@@ -272,13 +293,14 @@ k_viterbi_finish_fast(const int64_t *__restrict__ offsets, int u0, int nu, int N
 int sapr_viterbi_finish_u16(sapr_ctx *ctx, const int64_t *offsets, int u0, int nu, int N, int nslots, int first_frames,
                             const uint16_t *bp, int64_t Bpad, int maxT, const double *scores, int32_t *best_word,
                             double *best_score, double *scores_out, int M, uint8_t *best_path, uint8_t *all_paths,
-                            int64_t total_frames) {
+                            int64_t total_frames, const SaprFlag *flag) {
     {
         ProfScope ps(ctx, 1);
         if (!all_paths)
             k_viterbi_finish_fast<uint16_t><<<(nu + 127) / 128, 128, 0, ctx->stream>>>(offsets, u0, nu, N, nslots, nullptr, first_frames,
                                                                                        bp, Bpad, maxT, scores, best_word, best_score,
-                                                                                       scores_out, best_path);
+                                                                                       scores_out, best_path, nullptr, nullptr,
+                                                                                       flag ? *flag : SaprFlag());
         else
             k_viterbi_finish<uint16_t><<<(nu + 127) / 128, 128, 0, ctx->stream>>>(offsets, u0, nu, N, nslots, nullptr, first_frames, bp,
                                                                                   Bpad, maxT, scores, best_word, best_score,
@@ -324,7 +346,7 @@ static int launch_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx
         {
             ProfScope ps(ctx, 0);
             kern<<<grid, block, smem, ctx->stream>>>(X, ldx, offsets, u0, nu, m->M, m->N, nchunk, pk, cst, la, lb,
-                                                     model_of_utt, first_frames, bp, Bpad, Tm, nslots, sc_ws);
+                                                     model_of_utt, first_frames, bp, Bpad, Tm, nslots, sc_ws, nullptr, nullptr, nullptr);
         }
         SAPR_LAUNCH_CHECK(ctx);
         {
@@ -340,6 +362,169 @@ static int launch_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx
         }
         SAPR_LAUNCH_CHECK(ctx);
     }
+    return SAPR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// word exactness of the fp32 production path: flag buffers and the float64 re-decoding of the flagged utterances.
+// The float64 emissions of the listed utterances are computed frame-parallel (one thread per (list entry, model, frame,
+// state), the same fma order as emit_diag<double>, so the values are bit-identical to the verification mode's); the serial
+// recursion then only reads them -- a thread walking 200 frames with 320 dependent float64 fmas each took 1.4 ms.
+__global__ void k_redo_emission(const float *__restrict__ X, int ldx, const int64_t *__restrict__ offsets, const int32_t *__restrict__ utt_list,
+                                const int32_t *__restrict__ utt_count, int cap, int M, int N, int nchunk, int maxT, int first_frames,
+                                const double *__restrict__ pk, const double *__restrict__ cst_g, double *__restrict__ E) {
+    // persistent blocks over (list entry, model, 32-frame slab): the list is usually a handful of utterances
+    const int n = min(*utt_count, cap);
+    const int nslab = (maxT + 31) / 32;
+    const int t_in = threadIdx.x >> 3, j = threadIdx.x & 7;
+    for (int w = blockIdx.x; w < n * M * nslab; w += gridDim.x) {
+        const int slab = w % nslab, m = (w / nslab) % M, pos = w / (nslab * M);
+        const int u = utt_list[pos];
+        const int64_t off = offsets[u];
+        const int T = (int)(offsets[u + 1] - off);
+        const int Te = (first_frames > 0 && first_frames < T) ? first_frames : T;
+        const int t = slab * 32 + t_in;
+        if (t >= Te || t >= maxT || j >= N) continue;
+        const float4 *xr = reinterpret_cast<const float4 *>(X + (size_t)(off + t) * ldx);
+        const double *pm = pk + (size_t)m * nchunk * N * 8;
+        double acc = 0.0;
+        for (int c = 0; c < nchunk; c++) {
+            const float4 xv = __ldg(xr + c);
+            const double *p = pm + ((size_t)c * N + j) * 8;
+            const double d0 = (double)xv.x - p[0], d1 = (double)xv.y - p[1], d2 = (double)xv.z - p[2], d3 = (double)xv.w - p[3];
+            acc = fma(d0 * d0, p[4], acc);
+            acc = fma(d1 * d1, p[5], acc);
+            acc = fma(d2 * d2, p[6], acc);
+            acc = fma(d3 * d3, p[7], acc);
+        }
+        E[(((size_t)pos * M + m) * maxT + t) * 8 + j] = cst_g[(size_t)m * N + j] - acc;
+    }
+}
+
+// float64 max-product recursion of the listed utterances from the precomputed emissions: one warp per (list entry, model),
+// lane j < N = emitting state j + 1, lane N = exit state; the candidates, their order and the strict comparisons are those of
+// k_viterbi_fused<double> (custom_hmm.py:475-503), so scores and back-pointer words are bit-identical to the verification
+// mode's.  A frame is a shuffle, two adds and two compares instead of ~60 dependent float64 operations in one thread.
+__global__ void __launch_bounds__(256) k_redo_recursion(const int64_t *__restrict__ offsets, const int32_t *__restrict__ utt_list,
+                                                        const int32_t *__restrict__ utt_count, int cap, int M, int N, int maxT, int first_frames,
+                                                        const double *__restrict__ la_g, const double *__restrict__ lb_g,
+                                                        const double *__restrict__ E, uint16_t *__restrict__ bp, int64_t Bpad,
+                                                        double *__restrict__ scores) {
+    const int lane = threadIdx.x & 31, S = N + 2;
+    const int n = min(*utt_count, cap);
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n * M; w += nw) {
+        const int pos = w / M, m = w % M;
+        const int u = utt_list[pos];
+        const int64_t off = offsets[u];
+        const int T = (int)(offsets[u + 1] - off);
+        const int Te = min((first_frames > 0 && first_frames < T) ? first_frames : T, maxT);
+        const double NINF = -INFINITY;
+        // per-lane constants: advance arc into this state, self-loop of this state
+        double c_in = NINF, c_self = NINF;
+        if (lane >= 1 && lane < N) { c_in = lb_g[(size_t)m * S + lane]; c_self = la_g[(size_t)m * S + lane + 1]; }
+        else if (lane == 0) { c_in = lb_g[(size_t)m * S]; c_self = la_g[(size_t)m * S + 1]; }         // entry arc, self-loop of state 1
+        else if (lane == N) { c_in = lb_g[(size_t)m * S + N]; c_self = la_g[(size_t)m * S + S - 1]; }  // ln A[N, exit], ln A[exit, exit]
+        const double *ep = E + ((size_t)pos * M + m) * maxT * 8;
+        double v = NINF;
+        if (lane == 0 && Te > 0) v = c_in + ep[0];                                   // V[0, 1] = ln A01 + E[0, 1]
+        uint16_t *bpp = bp + ((size_t)m * maxT) * Bpad + pos;
+        double e_nx = (lane < N && Te > 1) ? ep[8 + lane] : 0.0;
+        for (int t = 1; t < Te; t++) {
+            const double e = e_nx;
+            if (t + 1 < Te && lane < N) e_nx = ep[(size_t)(t + 1) * 8 + lane];         // next frame's emission under this frame's arithmetic
+            const double up = __shfl_up_sync(0xffffffffu, v, 1);
+            double best = NINF;
+            bool adv = false;
+            if (lane >= 1 && lane < N) {
+                const double c_adv = up + c_in, c_stay = v + c_self;
+                if (c_adv > best) { best = c_adv; adv = true; }
+                if (c_stay > best) { best = c_stay; adv = false; }
+                v = (best > NINF) ? best + e : NINF;
+            } else if (lane == 0) {
+                const double c_stay = v + c_self;
+                if (c_stay > best) best = c_stay;
+                if (t == 1) {
+                    const double c_ent = 0.0 + c_in;
+                    if (c_ent > best) { best = c_ent; adv = true; }
+                }
+                v = (best > NINF) ? best + e : NINF;
+            } else if (lane == N) {
+                if (t >= N) {
+                    const double c_adv = up + c_in, c_stay = v + c_self;
+                    if (c_adv > best) { best = c_adv; adv = true; }
+                    if (c_stay > best) { best = c_stay; adv = false; }
+                }
+                v = best;
+            }
+            const unsigned bits = __ballot_sync(0xffffffffu, adv);
+            if (lane == 0) bpp[(size_t)t * Bpad] = (uint16_t)bits;
+        }
+        if (lane == N) scores[(size_t)pos * M + m] = (Te > 0 && (v > NINF || v != v)) ? v : NINF;
+    }
+}
+
+int sapr_flag_setup(sapr_ctx *ctx, SaprFlag *flag, bool first_chunk) {
+    int rc = sapr_ws_reserve(ctx, 5, sizeof(int32_t) * (SAPR_FLAG_CAP + 4));
+    if (rc) return rc;
+    int32_t *base = (int32_t *)ctx->ws[5];
+    // list capacity: the re-decoding scratch (float64 emissions of every model and frame) stays below 256 MB
+    const int64_t per = (int64_t)std::max(ctx->flag_M, 1) * std::max(ctx->flag_maxT, 1) * 8 * (int64_t)sizeof(double);
+    flag->count = base; flag->list = base + 4; flag->rel = SAPR_FLAG_REL;
+    flag->cap = (int)std::max<int64_t>(32, std::min<int64_t>(SAPR_FLAG_CAP, ((int64_t)256 << 20) / per));
+    SAPR_CUDA(ctx, cudaMemsetAsync(base, 0, sizeof(int32_t) * (first_chunk ? 2 : 1), ctx->stream));
+    ctx->flag_valid = true;
+    return SAPR_OK;
+}
+
+int sapr_viterbi_redo_flagged(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int first_frames,
+                              const SaprFlag &flag, int32_t *best_word, double *best_score, double *scores, uint8_t *best_path) {
+    // float64 emissions (frame-parallel) + recursion (state-parallel) + arg-max / back-trace over the listed utterances; the kernels
+    // read the list length on the device (no host round trip)
+    if (m->N > 8) return SAPR_OK;
+    const int nslots = m->M, nchunk = m->Dp / 4, cap = flag.cap;
+    // the longest utterance bounds the scratch: taken from the caller's max_T through first_frames / offsets is not possible
+    // here, so the scratch is sized by the caller (maxT argument below = ctx-side value)
+    const int maxT = ctx->flag_maxT;
+    const int Tm = (first_frames > 0 && first_frames < maxT) ? first_frames : maxT;
+    const int Tq = Tm > 0 ? Tm : 1;
+    const size_t bp_bytes = ((size_t)nslots * Tq * cap * sizeof(uint16_t) + 255) / 256 * 256;
+    const size_t sc_bytes = ((size_t)cap * nslots * sizeof(double) + 255) / 256 * 256;
+    const size_t e_bytes = (size_t)cap * nslots * Tq * 8 * sizeof(double);
+    int rc = sapr_ws_reserve(ctx, 4, bp_bytes + sc_bytes + e_bytes);
+    if (rc) return rc;
+    uint16_t *bp = (uint16_t *)ctx->ws[4];
+    double *sc_ws = (double *)((char *)ctx->ws[4] + bp_bytes);
+    double *E = (double *)((char *)ctx->ws[4] + bp_bytes + sc_bytes);
+    ProfScope ps(ctx, 6);
+    {
+    ProfScope ps7(ctx, 7);
+    k_redo_emission<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(X, ldx, offsets, flag.list, flag.count, cap, m->M, m->N,
+                                                                                     nchunk, Tq, first_frames, m->pk64, m->cst64, E);
+    }
+    SAPR_LAUNCH_CHECK(ctx);
+    {
+    ProfScope ps8(ctx, 8);
+    k_redo_recursion<<<2 * ctx->sm_count, 256, 0, ctx->stream>>>(offsets, flag.list, flag.count, cap, m->M, m->N, Tq, first_frames, m->la64,
+                                                                m->lb64, E, bp, (int64_t)cap, sc_ws);
+    }
+    SAPR_LAUNCH_CHECK(ctx);
+    k_viterbi_finish_fast<uint16_t><<<(cap + 127) / 128, 128, 0, ctx->stream>>>(offsets, 0, cap, m->N, nslots, nullptr, first_frames, bp,
+                                                                               (int64_t)cap, Tm, sc_ws, best_word, best_score, scores,
+                                                                               best_path, flag.list, flag.count);
+    SAPR_LAUNCH_CHECK(ctx);
+    return SAPR_OK;
+}
+
+// utterances the last fp32 sapr_viterbi call flagged as word near-ties (and re-decoded in float64, up to SAPR_FLAG_CAP per chunk)
+extern "C" int sapr_viterbi_flagged(sapr_ctx *ctx, int64_t *n) {
+    if (!ctx || !n) return SAPR_E_INVALID;
+    *n = 0;
+    if (!ctx->flag_valid || !ctx->ws[5]) return SAPR_OK;
+    int32_t h[2] = {0, 0};
+    SAPR_CUDA(ctx, cudaMemcpyAsync(h, ctx->ws[5], sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    SAPR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n = h[1];
     return SAPR_OK;
 }
 
@@ -367,6 +552,7 @@ extern "C" int sapr_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int l
     if (ldx % 4 || ldx < m->Dp) SAPR_FAIL(ctx, SAPR_E_INVALID, "viterbi: ldx must be a multiple of 4 and >= D padded");
     if (B <= 0) return SAPR_OK;
     if (max_T <= 0) SAPR_FAIL(ctx, SAPR_E_INVALID, "viterbi: max_T must be positive");
+    ctx->flag_valid = false;
 #define GO(R, BP, NM)                                                                                       \
     return launch_viterbi<R, BP, NM>(ctx, m, X, ldx, offsets, B, total_frames, max_T, model_of_utt,        \
                                      first_frames, best_word, best_score, scores, best_path, all_paths)

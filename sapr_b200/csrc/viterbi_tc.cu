@@ -1002,7 +1002,7 @@ int sapr_tc_prepare(sapr_models *m) {
 int sapr_viterbi_finish_u16(sapr_ctx *ctx, const int64_t *offsets, int u0, int nu, int N, int nslots, int first_frames,
                             const uint16_t *bp, int64_t Bpad, int maxT, const double *scores, int32_t *best_word,
                             double *best_score, double *scores_out, int M, uint8_t *best_path, uint8_t *all_paths,
-                            int64_t total_frames);
+                            int64_t total_frames, const SaprFlag *flag);
 
 int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int B, int max_T,
                            int first_frames, int32_t *best_word, double *best_score, double *scores, uint8_t *best_path,
@@ -1092,8 +1092,14 @@ int sapr_viterbi_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
         SAPR_LAUNCH_CHECK(ctx);
         return SAPR_OK;
     };
+    // word exactness: near-ties of the fp32 word scores are listed by the arg-max kernel and re-decoded in float64
+    const char *ex_env = getenv("SAPR_EXACT_WORDS");
+    const bool exact = !dbgE && !all_paths && (!ex_env || ex_env[0] != '0');
+    SaprFlag flag;
+    ctx->flag_maxT = max_T; ctx->flag_M = m->M;
     for (int u0 = 0; u0 < B; u0 += chunk) {
         const int nu = std::min(chunk, B - u0);
+        if (exact && (rc = sapr_flag_setup(ctx, &flag, u0 == 0))) return rc;
         TcParams prm;
         prm.X = X; prm.ldx = ldx; prm.offsets = offsets; prm.u0 = u0; prm.nu = nu; prm.M = M; prm.D = m->D; prm.nck = nck;
         prm.ncols = ncols; prm.first_frames = first_frames; prm.wimg = (const __half *)m->tc_image;
@@ -1162,7 +1168,9 @@ int sapr_viterbi_tc_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
         else rc = launch(k_viterbi_tc<3, 0, false>, prm, grid);
         if (rc) return rc;
         if ((rc = sapr_viterbi_finish_u16(ctx, offsets, u0, nu, m->N, M, first_frames, bp, Bpad, Tm, sc_ws, best_word, best_score,
-                                          scores, M, best_path, all_paths, total_frames)))
+                                          scores, M, best_path, all_paths, total_frames, exact ? &flag : nullptr)))
+            return rc;
+        if (exact && (rc = sapr_viterbi_redo_flagged(ctx, m, X, ldx, offsets, first_frames, flag, best_word, best_score, scores, best_path)))
             return rc;
     }
     return SAPR_OK;

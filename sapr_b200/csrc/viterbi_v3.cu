@@ -707,7 +707,7 @@ struct V3Map { int grp[16], shift[16]; };
 __global__ void __launch_bounds__(128)
 k_viterbi_finish_v3(const int64_t *__restrict__ offsets, int u0, int nu, int M, int Tt, int Tpad, const uint32_t *__restrict__ bp,
                     uint32_t Bpad, const V3Map map, const double *__restrict__ scores, int32_t *__restrict__ best_word,
-                    double *__restrict__ best_score, double *__restrict__ scores_out, uint8_t *__restrict__ best_path) {
+                    double *__restrict__ best_score, double *__restrict__ scores_out, uint8_t *__restrict__ best_path, const SaprFlag flag) {
     constexpr int CH = 32;
     __shared__ uint8_t sp[4][32][CH + 4];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -719,13 +719,16 @@ k_viterbi_finish_v3(const int64_t *__restrict__ offsets, int u0, int nu, int M, 
     int64_t off = 0;
     if (live) {
         off = offsets[u];
+        double second = -INFINITY;
         for (int s = 0; s < M; s++) {
             const double sc = scores[(size_t)ul * M + s];
             if (scores_out) scores_out[(size_t)u * M + s] = sc;
-            if (sc > bs) { bs = sc; bslot = s; }
+            if (sc > bs) { second = bs; bs = sc; bslot = s; }
+            else if (sc > second) second = sc;
         }
         if (best_word) best_word[u] = bslot;
         if (best_score) best_score[u] = bs;
+        sapr_flag_word(flag, u, bs, second);      // word near-tie in fp32: re-decoded in float64 by the launcher
     }
     if (!best_path) return;
     const int wslot = bslot < 0 ? 0 : bslot;
@@ -833,8 +836,13 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
                        : (nck == 10) ? k_viterbi_v3<5> : (nck == 4) ? k_viterbi_v3<2> : k_viterbi_v3<0>;
     const int nthreads = use_v4 ? V4_THREADS : V3_THREADS;
     SAPR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    const char *ex_env = getenv("SAPR_EXACT_WORDS");
+    const bool exact = !ex_env || ex_env[0] != '0';
+    SaprFlag flag;
+    ctx->flag_maxT = max_T; ctx->flag_M = m->M;
     for (int u0 = 0; u0 < B; u0 += chunk) {
         const int nu = std::min(chunk, B - u0);
+        if (exact && (rc = sapr_flag_setup(ctx, &flag, u0 == 0))) return rc;
         prm.u0 = u0; prm.nu = nu; prm.M = M; prm.nck = nck; prm.ncols = ncols; prm.Tt = Tt; prm.Tpad = Tpad;
         prm.ntiles = (nu + TC_ROWS - 1) / TC_ROWS;
         prm.wimg = (const __half *)m->tc_image;
@@ -874,9 +882,11 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
         {
             ProfScope ps(ctx, 1);
             k_viterbi_finish_v3<<<(nu + 127) / 128, 128, 0, ctx->stream>>>(offsets, u0, nu, M, Tt, Tpad, prm.bp, prm.Bpad, map, prm.scores,
-                                                                          best_word, best_score, scores, best_path);
+                                                                          best_word, best_score, scores, best_path, exact ? flag : SaprFlag());
         }
         SAPR_LAUNCH_CHECK(ctx);
+        if (exact && (rc = sapr_viterbi_redo_flagged(ctx, m, X, ldx, offsets, first_frames, flag, best_word, best_score, scores, best_path)))
+            return rc;
     }
     *taken = true;
     return SAPR_OK;

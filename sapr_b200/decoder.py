@@ -104,10 +104,24 @@ class Decoder:
                             "state_sequence": state_sequence})
         return results
 
+    def _batchable(self) -> bool:
+        return self.implementation == "custom" and all(getattr(m, "semantics", None) == "standard" for m in self.models.values())
+
     def decode_vocabulary(self, feature_set: str = "feature_set", verbose: bool = True) -> Dict[str, List[Dict]]:
+        """decoder.py:79-95.  Custom models with the standard (diagonal, all-frames) semantics are recognised in ONE fused
+        Viterbi launch per word list instead of utterances x models calls (same result dictionaries; SAPR_DECODE_LOOP=1 keeps the
+        reference's per-sequence loop)."""
+        import os
+        batched = self._batchable() and os.environ.get("SAPR_DECODE_LOOP", "0") != "1"
         all_results = {}
         for word in self.vocab:
-            results = self.decode_word_samples(word, feature_set)
+            if batched:
+                feats = load_mfccs_by_word(feature_set, word)
+                words, scores, paths = self.decode_batch(feats) if feats else ([], [], [])
+                results = [{"sample_index": i + 1, "true_word": word, "predicted_word": words[i], "log_likelihood": float(scores[i]),
+                            "correct": words[i] == word, "state_sequence": paths[i]} for i in range(len(feats))]
+            else:
+                results = self.decode_word_samples(word, feature_set)
             all_results[word] = results
             if verbose:
                 correct = sum(r["correct"] for r in results)

@@ -404,3 +404,40 @@ def test_estep_feature_dims_vs_oracle(eng, D):
         st = stats.cpu().numpy()
         assert np.max(np.abs(st[:, :3 * S] - ost[:, :3 * S]) / scale[:, :3 * S]) < ra, "occupancies"
         assert np.max(np.abs(st[:, 3 * S:] - ost[:, 3 * S:]) / scale[:, 3 * S:]) < ra * 10, "feature sums"
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_fp32_word_near_ties_are_redecoded_in_float64(eng, ragged, monkeypatch):
+    """fp32 production mode: an utterance whose two best word scores are closer than fp32 resolves is flagged by the arg-max
+    kernel and re-decoded in float64 inside the same call, so the recognised word (decoder.py:42-47, strict > over the models),
+    its score and its path are the verification mode's.  Two word models that differ by 1e-7 sigma make most margins far smaller
+    than the fp32 score error; equal-length batches take k_viterbi_v4, ragged ones k_viterbi_tc."""
+    import torch
+    from sapr_b200 import synth
+    B, M, D = 900, 11, 39
+    feats, labels, mu, sd = synth.make_corpus(B, M, 8, D, 40, 64 if ragged else 40, seed=77)
+    A, means, var = synth.truth_models(mu, sd, 0.9)
+    rng = np.random.default_rng(5)
+    means[5] = means[3] + 1e-7 * np.sqrt(var[3]) * rng.standard_normal(means[3].shape)
+    var[5] = var[3]; A[5] = A[3]
+    m = eng.WordModels(M, 8, D)
+    m.set(means, var, A)
+    batch = eng.PackedBatch.from_features(feats)
+    ref = m.viterbi(batch, None, eng.FP64, 0, want_scores=True, want_path=True)
+    out = m.viterbi(batch, None, eng.FP32, 0, want_scores=True, want_path=True)
+    flagged = m.ctx.viterbi_flagged()
+    rw, ow = ref["best_word"].cpu().numpy(), out["best_word"].cpu().numpy()
+    near = np.isin(rw, (3, 5))
+    assert near.sum() > 30 and flagged >= near.sum()                        # every 3-vs-5 utterance is a near-tie
+    assert np.array_equal(ow, rw)                                           # words: exactly the float64 ones
+    rs, os_ = ref["best_score"].cpu().numpy(), out["best_score"].cpu().numpy()
+    assert np.array_equal(os_[near], rs[near])                              # re-decoded utterances carry the float64 score ...
+    offs = batch.offsets_host
+    rp, op = ref["path"].cpu().numpy(), out["path"].cpu().numpy()
+    for u in np.nonzero(near)[0][:200]:
+        assert np.array_equal(op[offs[u]:offs[u + 1]], rp[offs[u]:offs[u + 1]])   # ... and the float64 path
+    assert_close(out["scores"].cpu().numpy(), ref["scores"].cpu().numpy(), 1e-6, what="scores")
+    monkeypatch.setenv("SAPR_EXACT_WORDS", "0")                             # without the pass fp32 cannot tell the two models apart
+    raw = m.viterbi(batch, None, eng.FP32, 0, want_scores=False, want_path=False)["best_word"].cpu().numpy()
+    assert m.ctx.viterbi_flagged() == 0
+    assert np.mean(raw[near] != rw[near]) > 0.05

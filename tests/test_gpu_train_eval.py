@@ -20,7 +20,7 @@ def corpus_dir(tmp_path_factory):
     return root, feats, labels
 
 
-def test_train_eval_custom_standard(corpus_dir):
+def test_train_eval_custom_standard(corpus_dir, monkeypatch):
     from sapr_b200.train import train_hmm
     from sapr_b200.eval import eval_hmm
     from sapr_b200.decoder import Decoder
@@ -34,7 +34,11 @@ def test_train_eval_custom_standard(corpus_dir):
         assert 1 <= len(h) <= 4 and np.all(np.isfinite(h))
         assert all(b >= a - 1e-6 * abs(a) for a, b in zip(h, h[1:]))                     # EM with a true diagonal Gaussian is monotone
         assert np.allclose(hmms[w].A.sum(axis=1), 1.0)
+    monkeypatch.setenv("SAPR_DECODE_LOOP", "1")        # the reference's utterances x models loop (decoder.py:42-47) ...
     seq = eval_hmm("custom", str(root / "feature_set"), model_iter=4, models_dir=str(root / "trained_models"), vocab_order=WORDS)
+    monkeypatch.delenv("SAPR_DECODE_LOOP")             # ... against the default route (one fused launch per word) and the whole-set launch
+    dflt = eval_hmm("custom", str(root / "feature_set"), model_iter=4, models_dir=str(root / "trained_models"), vocab_order=WORDS)
+    assert dflt["predicted_labels"] == seq["predicted_labels"] and dflt["confusion_matrix"].equals(seq["confusion_matrix"])
     bat = eval_hmm("custom", str(root / "feature_set"), model_iter=4, models_dir=str(root / "trained_models"), vocab_order=WORDS,
                    batched=True)
     # no accuracy bar here: the reference's exit state is free once t >= N, so a custom-model score only
