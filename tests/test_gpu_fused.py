@@ -441,3 +441,28 @@ def test_fp32_word_near_ties_are_redecoded_in_float64(eng, ragged, monkeypatch):
     raw = m.viterbi(batch, None, eng.FP32, 0, want_scores=False, want_path=False)["best_word"].cpu().numpy()
     assert m.ctx.viterbi_flagged() == 0
     assert np.mean(raw[near] != rw[near]) > 0.05
+
+
+def test_viterbi_blocked_forward_arc_scores_minus_inf(eng):
+    """A word model whose chain is cut (A[j, j+1] = 0) cannot reach the exit state: custom_hmm.py:462-514 returns -inf for it and
+    decoder.py:42-47 never picks it.  The equal-length fp32 kernel folds the transition constants out of its recursion (their sum
+    is added to the final score only), so this is the case where that sum is -inf; words / scores of the other models must not
+    be disturbed."""
+    from sapr_b200 import synth
+    B, M, D, T = 384, 11, 39, 48
+    feats, labels, mu, sd = synth.make_corpus(B, M, 8, D, T, T, seed=91)
+    A, means, var = synth.truth_models(mu, sd, 0.9)
+    A[4, 3, 3] += A[4, 3, 4]; A[4, 3, 4] = 0.0                  # model 4: state 3 can no longer advance
+    m = eng.WordModels(M, 8, D)
+    m.set(means, var, A)
+    batch = eng.PackedBatch.from_features(feats)
+    X, offs = orc.pack(feats)
+    with np.errstate(divide="ignore"):
+        bw, bs, sc, bp = orc.viterbi_batch(X, offs, A, means, var)
+    assert np.all(np.isneginf(sc[:, 4])) and np.all(bw != 4)
+    out = m.viterbi(batch, None, eng.FP32, 0, want_scores=True, want_path=True)
+    got = out["scores"].cpu().numpy()
+    assert np.all(np.isneginf(got[:, 4]))
+    assert_close(got, sc, 1e-6, what="scores")
+    assert np.array_equal(out["best_word"].cpu().numpy(), bw)
+    assert np.mean(out["path"].cpu().numpy() == bp) > 0.999
