@@ -52,12 +52,7 @@ __global__ void __launch_bounds__(32 * 16)
 k_viterbi_fused(const float *__restrict__ X, int ldx, const int64_t *__restrict__ offsets, int u0, int nu, int M,
                 int N, int nchunk, const R *__restrict__ pk, const R *__restrict__ cst_g, const R *__restrict__ la_g,
                 const R *__restrict__ lb_g, const int32_t *__restrict__ model_of_utt, int first_frames,
-                BP *__restrict__ bp, int64_t Bpad, int maxT, int nslots, double *__restrict__ scores,
-                const int32_t *__restrict__ utt_list = nullptr, const int32_t *__restrict__ utt_count = nullptr,
-                const R *__restrict__ E_pre = nullptr) {
-    // utt_list / utt_count: decode the listed utterances only (the float64 re-decoding of the utterances the fp32 pass flagged);
-    // the scratch and the score rows are then indexed by the position in the list.  E_pre: the emissions of the listed
-    // utterances, computed frame-parallel by k_redo_emission with the same operation order ([list pos][model][frame][8])
+                BP *__restrict__ bp, int64_t Bpad, int maxT, int nslots, double *__restrict__ scores) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *spk = reinterpret_cast<R *>(smem_raw);
     const int S = N + 2;
@@ -65,7 +60,6 @@ k_viterbi_fused(const float *__restrict__ X, int ldx, const int64_t *__restrict_
     const bool own = (model_of_utt != nullptr);
     const int m0 = own ? 0 : blockIdx.y * blockDim.y;
     const int nm = own ? M : min((int)blockDim.y, M - m0);
-    if (utt_list && (int)blockIdx.x * 32 >= min(*utt_count, nu)) return;      // blocks beyond the list leave before staging anything
     {   // stage the packed emission parameters of this CTA's models
         const int tid = threadIdx.y * 32 + threadIdx.x, nt = blockDim.x * blockDim.y;
         const R *src = pk + (size_t)m0 * per_model;
@@ -75,8 +69,7 @@ k_viterbi_fused(const float *__restrict__ X, int ldx, const int64_t *__restrict_
     const int ul = blockIdx.x * 32 + threadIdx.x;   // utterance within this chunk
     const int slot = own ? 0 : m0 + threadIdx.y;
     if (ul >= nu || slot >= nslots || (own && threadIdx.y > 0)) return;
-    if (utt_list && ul >= min(*utt_count, nu)) return;
-    const int u = utt_list ? utt_list[ul] : u0 + ul;
+    const int u = u0 + ul;
     const int m = own ? model_of_utt[u] : slot;
     const R *spk_model = spk + (size_t)(m - m0) * per_model;
 
@@ -100,15 +93,7 @@ k_viterbi_fused(const float *__restrict__ X, int ldx, const int64_t *__restrict_
     for (int j = 0; j <= NMAX; j++) V[j] = NINF;
     R Vx = NINF;
     double base = 0.0;
-    const R *ep = E_pre ? E_pre + ((size_t)ul * nslots + slot) * maxT * 8 : nullptr;
-    auto emit = [&](int t) {
-        if (ep) {
-#pragma unroll
-            for (int j = 0; j < NMAX; j++) e[j] = (j < N && j < 8) ? ep[(size_t)t * 8 + j] : R(0);
-        } else {
-            emit_diag<R, NMAX>(X + (size_t)(off + t) * ldx, nchunk, N, spk_model, cst, e);
-        }
-    };
+    auto emit = [&](int t) { emit_diag<R, NMAX>(X + (size_t)(off + t) * ldx, nchunk, N, spk_model, cst, e); };
     if (Te > 0) {
         emit(0);
         V[0] = lb[0] + e[0];   // V[0,1] = ln A01 + E[0,1]   (custom_hmm.py:473)
@@ -346,7 +331,7 @@ static int launch_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx
         {
             ProfScope ps(ctx, 0);
             kern<<<grid, block, smem, ctx->stream>>>(X, ldx, offsets, u0, nu, m->M, m->N, nchunk, pk, cst, la, lb,
-                                                     model_of_utt, first_frames, bp, Bpad, Tm, nslots, sc_ws, nullptr, nullptr, nullptr);
+                                                     model_of_utt, first_frames, bp, Bpad, Tm, nslots, sc_ws);
         }
         SAPR_LAUNCH_CHECK(ctx);
         {
@@ -367,13 +352,16 @@ static int launch_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx
 
 // ------------------------------------------------------------------------------------------------
 // word exactness of the fp32 production path: flag buffers and the float64 re-decoding of the flagged utterances.
-// The float64 emissions of the listed utterances are computed frame-parallel (one thread per (list entry, model, frame,
-// state), the same fma order as emit_diag<double>, so the values are bit-identical to the verification mode's); the serial
-// recursion then only reads them -- a thread walking 200 frames with 320 dependent float64 fmas each took 1.4 ms.
+// float64 re-decoding of the listed utterances.  k_redo_emission: one thread per (list entry, model, frame, state), each with the
+// fma order of emit_diag<double>.  k_redo_f64: one warp per (list entry, model); phase 1 pulls the emissions into shared memory, phase 2 is the
+// max-product recursion, lane j < N = emitting state j + 1, lane N = exit state; the candidates, their order and the strict
+// comparisons are those of k_viterbi_fused<double> (custom_hmm.py:475-503).  Scores and back-pointer words are bit-identical to
+// the verification mode's; a frame of the recursion is a shuffle, two adds and two compares with the emission a shared-memory
+// read away (one thread walking 200 frames of ~60 dependent float64 operations each took 1.4 ms).
 __global__ void k_redo_emission(const float *__restrict__ X, int ldx, const int64_t *__restrict__ offsets, const int32_t *__restrict__ utt_list,
                                 const int32_t *__restrict__ utt_count, int cap, int M, int N, int nchunk, int maxT, int first_frames,
                                 const double *__restrict__ pk, const double *__restrict__ cst_g, double *__restrict__ E) {
-    // persistent blocks over (list entry, model, 32-frame slab): the list is usually a handful of utterances
+    // persistent blocks over (list entry, model, 32-frame slab), one thread per (frame, state): the list is usually a handful of utterances
     const int n = min(*utt_count, cap);
     const int nslab = (maxT + 31) / 32;
     const int t_in = threadIdx.x >> 3, j = threadIdx.x & 7;
@@ -384,33 +372,35 @@ __global__ void k_redo_emission(const float *__restrict__ X, int ldx, const int6
         const int T = (int)(offsets[u + 1] - off);
         const int Te = (first_frames > 0 && first_frames < T) ? first_frames : T;
         const int t = slab * 32 + t_in;
-        if (t >= Te || t >= maxT || j >= N) continue;
-        const float4 *xr = reinterpret_cast<const float4 *>(X + (size_t)(off + t) * ldx);
-        const double *pm = pk + (size_t)m * nchunk * N * 8;
-        double acc = 0.0;
-        for (int c = 0; c < nchunk; c++) {
-            const float4 xv = __ldg(xr + c);
-            const double *p = pm + ((size_t)c * N + j) * 8;
-            const double d0 = (double)xv.x - p[0], d1 = (double)xv.y - p[1], d2 = (double)xv.z - p[2], d3 = (double)xv.w - p[3];
-            acc = fma(d0 * d0, p[4], acc);
-            acc = fma(d1 * d1, p[5], acc);
-            acc = fma(d2 * d2, p[6], acc);
-            acc = fma(d3 * d3, p[7], acc);
+        if (t >= Te || t >= maxT) continue;
+        double ev = 0.0;
+        if (j < N) {
+            const float4 *xr = reinterpret_cast<const float4 *>(X + (size_t)(off + t) * ldx);
+            const double *pm = pk + (size_t)m * nchunk * N * 8;
+            double acc = 0.0;
+            for (int c = 0; c < nchunk; c++) {
+                const float4 xv = __ldg(xr + c);
+                const double *p = pm + ((size_t)c * N + j) * 8;
+                const double d0 = (double)xv.x - p[0], d1 = (double)xv.y - p[1], d2 = (double)xv.z - p[2], d3 = (double)xv.w - p[3];
+                acc = fma(d0 * d0, p[4], acc);
+                acc = fma(d1 * d1, p[5], acc);
+                acc = fma(d2 * d2, p[6], acc);
+                acc = fma(d3 * d3, p[7], acc);
+            }
+            ev = cst_g[(size_t)m * N + j] - acc;
         }
-        E[(((size_t)pos * M + m) * maxT + t) * 8 + j] = cst_g[(size_t)m * N + j] - acc;
+        E[(((size_t)pos * M + m) * maxT + t) * 8 + j] = ev;
     }
 }
 
-// float64 max-product recursion of the listed utterances from the precomputed emissions: one warp per (list entry, model),
-// lane j < N = emitting state j + 1, lane N = exit state; the candidates, their order and the strict comparisons are those of
-// k_viterbi_fused<double> (custom_hmm.py:475-503), so scores and back-pointer words are bit-identical to the verification
-// mode's.  A frame is a shuffle, two adds and two compares instead of ~60 dependent float64 operations in one thread.
-__global__ void __launch_bounds__(256) k_redo_recursion(const int64_t *__restrict__ offsets, const int32_t *__restrict__ utt_list,
-                                                        const int32_t *__restrict__ utt_count, int cap, int M, int N, int maxT, int first_frames,
-                                                        const double *__restrict__ la_g, const double *__restrict__ lb_g,
-                                                        const double *__restrict__ E, uint16_t *__restrict__ bp, int64_t Bpad,
-                                                        double *__restrict__ scores) {
-    const int lane = threadIdx.x & 31, S = N + 2;
+__global__ void __launch_bounds__(256) k_redo_f64(const int64_t *__restrict__ offsets, const int32_t *__restrict__ utt_list,
+                                                  const int32_t *__restrict__ utt_count, int cap, int M, int N, int maxT, int first_frames,
+                                                  const double *__restrict__ E, const double *__restrict__ la_g,
+                                                  const double *__restrict__ lb_g, uint16_t *__restrict__ bp, int64_t Bpad,
+                                                  double *__restrict__ scores) {
+    extern __shared__ double s_e[];                       // [warps per block][maxT][8]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, S = N + 2;
+    double *se = s_e + (size_t)wib * maxT * 8;
     const int n = min(*utt_count, cap);
     const int nw = (gridDim.x * blockDim.x) >> 5;
     for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n * M; w += nw) {
@@ -420,47 +410,41 @@ __global__ void __launch_bounds__(256) k_redo_recursion(const int64_t *__restric
         const int T = (int)(offsets[u + 1] - off);
         const int Te = min((first_frames > 0 && first_frames < T) ? first_frames : T, maxT);
         const double NINF = -INFINITY;
-        // per-lane constants: advance arc into this state, self-loop of this state
-        double c_in = NINF, c_self = NINF;
+        // ---- phase 1: the utterance's emissions (k_redo_emission) into shared memory, all loads in flight at once ----
+        const double *eg = E + ((size_t)pos * M + m) * maxT * 8;
+        for (int idx = lane; idx < Te * 8; idx += 32) se[idx] = eg[idx];
+        __syncwarp();
+        // ---- phase 2: recursion ----
+        double c_in = NINF, c_self = NINF;     // advance arc into this lane's state, its self-loop
         if (lane >= 1 && lane < N) { c_in = lb_g[(size_t)m * S + lane]; c_self = la_g[(size_t)m * S + lane + 1]; }
         else if (lane == 0) { c_in = lb_g[(size_t)m * S]; c_self = la_g[(size_t)m * S + 1]; }         // entry arc, self-loop of state 1
         else if (lane == N) { c_in = lb_g[(size_t)m * S + N]; c_self = la_g[(size_t)m * S + S - 1]; }  // ln A[N, exit], ln A[exit, exit]
-        const double *ep = E + ((size_t)pos * M + m) * maxT * 8;
         double v = NINF;
-        if (lane == 0 && Te > 0) v = c_in + ep[0];                                   // V[0, 1] = ln A01 + E[0, 1]
+        if (lane == 0 && Te > 0) v = c_in + se[0];                                   // V[0, 1] = ln A01 + E[0, 1]
         uint16_t *bpp = bp + ((size_t)m * maxT) * Bpad + pos;
-        double e_nx = (lane < N && Te > 1) ? ep[8 + lane] : 0.0;
+        const int le = lane < 8 ? lane : 0;
+        // one instruction stream for all lanes: a = the candidate tried first, b = the second one (replaces on strict > only).
+        // States 2..N and the exit try the predecessor first (custom_hmm.py:488: prev_states = [j-1, j]); state 1 tries its
+        // self-loop first and the entry state (alive at t == 1 only) second (:477-480).
+        const bool adv_first = lane >= 1;
+        const bool emits = lane < N;
         for (int t = 1; t < Te; t++) {
-            const double e = e_nx;
-            if (t + 1 < Te && lane < N) e_nx = ep[(size_t)(t + 1) * 8 + lane];         // next frame's emission under this frame's arithmetic
-            const double up = __shfl_up_sync(0xffffffffu, v, 1);
-            double best = NINF;
-            bool adv = false;
-            if (lane >= 1 && lane < N) {
-                const double c_adv = up + c_in, c_stay = v + c_self;
-                if (c_adv > best) { best = c_adv; adv = true; }
-                if (c_stay > best) { best = c_stay; adv = false; }
-                v = (best > NINF) ? best + e : NINF;
-            } else if (lane == 0) {
-                const double c_stay = v + c_self;
-                if (c_stay > best) best = c_stay;
-                if (t == 1) {
-                    const double c_ent = 0.0 + c_in;
-                    if (c_ent > best) { best = c_ent; adv = true; }
-                }
-                v = (best > NINF) ? best + e : NINF;
-            } else if (lane == N) {
-                if (t >= N) {
-                    const double c_adv = up + c_in, c_stay = v + c_self;
-                    if (c_adv > best) { best = c_adv; adv = true; }
-                    if (c_stay > best) { best = c_stay; adv = false; }
-                }
-                v = best;
-            }
-            const unsigned bits = __ballot_sync(0xffffffffu, adv);
+            const double e = emits ? se[t * 8 + le] : 0.0;
+            double up = __shfl_up_sync(0xffffffffu, v, 1);
+            if (lane == 0) up = (t == 1) ? 0.0 : NINF;                  // V[0, entry] = 0
+            const bool open = lane < N || (lane == N && t >= N);        // the exit state opens at t >= N (:481-485)
+            const double c_adv = open ? up + c_in : NINF, c_stay = open ? v + c_self : NINF;
+            const double a = adv_first ? c_adv : c_stay, b2 = adv_first ? c_stay : c_adv;
+            double best = (a > NINF) ? a : NINF;
+            const bool took_b = b2 > best;
+            best = took_b ? b2 : best;
+            const bool adv = adv_first ? (!took_b && a > NINF) : took_b;
+            v = emits ? ((best > NINF) ? best + e : NINF) : best;
+            const unsigned bits = __ballot_sync(0xffffffffu, adv && lane <= N);
             if (lane == 0) bpp[(size_t)t * Bpad] = (uint16_t)bits;
         }
         if (lane == N) scores[(size_t)pos * M + m] = (Te > 0 && (v > NINF || v != v)) ? v : NINF;
+        __syncwarp();
     }
 }
 
@@ -496,18 +480,16 @@ int sapr_viterbi_redo_flagged(sapr_ctx *ctx, sapr_models *m, const float *X, int
     uint16_t *bp = (uint16_t *)ctx->ws[4];
     double *sc_ws = (double *)((char *)ctx->ws[4] + bp_bytes);
     double *E = (double *)((char *)ctx->ws[4] + bp_bytes + sc_bytes);
+    const size_t per_warp = (size_t)Tq * 8 * sizeof(double);
+    if (per_warp > 200 * 1024) return SAPR_OK;            // utterances too long for the shared-memory emission staging: no re-decoding
+    const int wpb = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_warp));
+    SAPR_CUDA(ctx, cudaFuncSetAttribute(k_redo_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wpb * per_warp)));
     ProfScope ps(ctx, 6);
-    {
-    ProfScope ps7(ctx, 7);
-    k_redo_emission<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(X, ldx, offsets, flag.list, flag.count, cap, m->M, m->N,
-                                                                                     nchunk, Tq, first_frames, m->pk64, m->cst64, E);
-    }
+    k_redo_emission<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(X, ldx, offsets, flag.list, flag.count, cap, m->M, m->N, nchunk, Tq, first_frames,
+                                                               m->pk64, m->cst64, E);
     SAPR_LAUNCH_CHECK(ctx);
-    {
-    ProfScope ps8(ctx, 8);
-    k_redo_recursion<<<2 * ctx->sm_count, 256, 0, ctx->stream>>>(offsets, flag.list, flag.count, cap, m->M, m->N, Tq, first_frames, m->la64,
-                                                                m->lb64, E, bp, (int64_t)cap, sc_ws);
-    }
+    k_redo_f64<<<ctx->sm_count, 32 * wpb, wpb * per_warp, ctx->stream>>>(offsets, flag.list, flag.count, cap, m->M, m->N, Tq, first_frames, E,
+                                                                      m->la64, m->lb64, bp, (int64_t)cap, sc_ws);
     SAPR_LAUNCH_CHECK(ctx);
     k_viterbi_finish_fast<uint16_t><<<(cap + 127) / 128, 128, 0, ctx->stream>>>(offsets, 0, cap, m->N, nslots, nullptr, first_frames, bp,
                                                                                (int64_t)cap, Tm, sc_ws, best_word, best_score, scores,
