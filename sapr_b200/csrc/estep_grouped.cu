@@ -101,7 +101,7 @@ struct Ring {
     __device__ __forceinline__ void next(uint32_t n) { if (++s == n) { s = 0; ph ^= 1u; } }
 };
 
-template <int NCH>   // NCH = chunks per converter half (nck / 2), 0 = run-time
+template <int NCH, bool EXP = false>   // NCH = chunks per converter half (nck / 2), 0 = run-time; EXP: the what-if flags are honoured (tuning builds)
 __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int nck = p.nck, M = p.M, T = p.T, nraw = p.nraw;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
                     const int t = i < T ? i : npf - 1 - i;
                     if (p.pfd > 0) prefetch_next();
                     mbar_wait(bRawEmpty + 8 * rr.s, rr.ph ^ 1u);
-                    if (p.flags & 16) { mbar_arrive(bRawFull + 8 * rr.s); rr.next((uint32_t)nraw); continue; }   // tuning experiment: no loads
+                    if (EXP && (p.flags & 16)) { mbar_arrive(bRawFull + 8 * rr.s); rr.next((uint32_t)nraw); continue; }   // tuning experiment: no loads
                     mbar_arrive_tx(bRawFull + 8 * rr.s, frame_bytes);
                     tma_load_3d(sRaw + rr.s * frame_bytes, &tmap, 0, t, u0, bRawFull + 8 * rr.s);
                     rr.next((uint32_t)nraw);
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
                     if (elect_one()) {
                         const uint32_t d = tmem_st + sr.s * 16u;
                         const uint32_t ab = sA + astage * a_stage, gb = sG + gr.s * 4096u;
-                        if (!(p.flags & 8)) {
+                        if (!EXP || !(p.flags & 8)) {
 #pragma unroll
                         for (int ks = 0; ks < 8; ks++)
                             umma_f16_ss(d, make_desc(ab + 2u * ks * rg_stride, rg_stride, 128), make_desc(gb + 2u * ks * 256u, 256, 128), idesc_mn,
@@ -289,9 +289,10 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
 #pragma unroll
         for (int c = 0; c < NCMAX; c++)
             if (c < nch) { rsc[c] = lds4(sbS + 16u * c); rof[c] = lds4(sbB + 16u * c); }
-        const uint32_t raw_row = sRaw + (uint32_t)r * rw + 16u * c0;
-        const uint32_t a_row = sA + (uint32_t)(r >> 3) * rg_stride + (uint32_t)c0 * 128u + (uint32_t)(r & 7) * 16u;
-        const uint32_t ta_row = tmem_a + ((uint32_t)(q * 32) << 16);
+        const uint32_t raw_row = pin_reg(sRaw + (uint32_t)r * rw + 16u * c0);
+        const uint32_t a_row = pin_reg(sA + (uint32_t)(r >> 3) * rg_stride + (uint32_t)c0 * 128u + (uint32_t)(r & 7) * 16u);
+        const uint32_t ta_row = pin_reg(tmem_a + ((uint32_t)(q * 32) << 16));
+        const uint32_t lane0 = pin_reg(lane == 0 ? 1u : 0u);
         Ring rr = {0, 0}, ar = {0, 0}, ir = {0, 0};
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             for (int i = 0; i < npf; i++) {
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
 #pragma unroll
                 for (int c = 0; c < NCMAX; c++)
                     if (c < nch) xr[c] = lds4(src + 16u * c);
-                if (!(p.flags & 4)) {
+                if (!EXP || !(p.flags & 4)) {
 #pragma unroll
                     for (int c = 0; c < NCMAX; c++) {
                         if (c < nch) {
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
                 tc_fence_before();
                 if (img) fence_proxy_async();                         // generic-proxy stores -> visible to the tensor core's reads
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(bAFull + 8 * ar.s); mbar_arrive(bRawEmpty + 8 * rr.s); }
+                if (lane0) { mbar_arrive(bAFull + 8 * ar.s); mbar_arrive(bRawEmpty + 8 * rr.s); }
                 rr.next((uint32_t)nraw);
                 ar.next(EG_A_STAGES);
                 if (img) ir.next(EG_A_STAGES);
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
             for (int t = 0; t < T; t++) {
                 float e[8];
                 fetch(e);
-                if (p.flags & 2) continue;                            // tuning experiment: pipeline without the recursion arithmetic
+                if (EXP && (p.flags & 2)) continue;                            // tuning experiment: pipeline without the recursion arithmetic
                 float *sp = scr + (size_t)t * 8 * TC_ROWS;
                 if (t == 0) {
                     U[0] = lb0 + e[0];
@@ -463,7 +464,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
                 fetch(e);
                 if (t == T - 1) {
                     glast = exit_ok ? 0.f : NAN;
-                } else if (p.flags & 2) {                           // tuning experiment: zero posteriors, barrier protocol only
+                } else if (EXP && (p.flags & 2)) {                           // tuning experiment: zero posteriors, barrier protocol only
                     mbar_wait(bGamFree + 8 * gr.s, gr.ph ^ 1u);
                     const uint32_t gb = sG + gr.s * 4096u + g_row;
                     sts128(gb, 0, 0, 0, 0); sts128(gb + 128u, 0, 0, 0, 0);
@@ -682,7 +683,7 @@ extern "C" int sapr_estep_grouped(sapr_ctx *ctx, sapr_models *m, const float *X,
     prm.rw = rw; prm.trace = nullptr;
     prm.flags = getenv("SAPR_EG_EXP") ? atoi(getenv("SAPR_EG_EXP")) : 0;
     prm.pfd = getenv("SAPR_EG_PFD") ? atoi(getenv("SAPR_EG_PFD")) : 0;
-    auto kern = (nck == 10) ? k_estep_grouped<5> : (nck == 4) ? k_estep_grouped<2> : k_estep_grouped<0>;
+    auto kern = (nck == 10) ? (prm.flags ? k_estep_grouped<5, true> : k_estep_grouped<5>) : (nck == 4) ? k_estep_grouped<2> : k_estep_grouped<0>;
     SAPR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     {
         ProfScope ps(ctx, 2);
