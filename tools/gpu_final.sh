@@ -9,7 +9,7 @@ CMD="python bench.py --steps 2 --warmup 3 --utts 18944 --estep-utts 37888 --ergo
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?"
-CMD2="python bench.py --steps 2 --warmup 3 --utts 18944 --estep-utts 37888 --ergodic-utts 0 --no-cpu --no-e2e"
+CMD2="python bench.py --steps 2 --warmup 3 --utts 18944 --estep-utts 37888 --ergodic-utts 0 --audio-utts 0 --no-cfg1 --no-cpu --no-e2e"
 $CMD2 > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"k_viterbi_tc|k_estep_tc|k_stats_diag8|k_viterbi_finish_fast" -s 6 -c 6 -o gpurun_out/prof_final $CMD2 > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_viterbi_v4|k_estep_tc|k_stats_diag8|k_viterbi_finish_v3" -s 6 -c 6 -f -o gpurun_out/prof_final $CMD2 > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"
