@@ -89,6 +89,8 @@ int sapr_init_stats(sapr_ctx *ctx, const float *X, int ldx, const int64_t *offse
 /* ---- batched Viterbi: custom_hmm.py:462-514 (decode) for every utterance x model, plus the
  * strict-'>' argmax over models of decoder.py:42-47.  DIAG emission + ENTRY_EXIT topology, fused.
  *   model_of_utt  int32[B] or NULL; NULL = score against all M models
+ *   max_T         the longest utterance of the batch; it sizes the scratch, and an utterance longer than max_T is decoded
+ *                 on its first max_T frames only (never past the scratch)
  *   first_frames  > 0 walks only that many frames (the reference walks D frames), 0 = all
  *   best_word     int32[B]      index of the winning model (first best wins ties)
  *   best_score    float64[B]    V[T-1, S-1] of the winner (-inf if the exit state is unreachable)

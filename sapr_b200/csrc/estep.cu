@@ -85,7 +85,7 @@ k_estep_fused(const float *__restrict__ X, int ldx, const int64_t *__restrict__ 
     }
     const R lbN = lb_g[(size_t)m * S + N];   // ln A[N, exit]
     const int64_t off = offsets[u];
-    const int T = (int)(offsets[u + 1] - off);
+    const int T = min((int)(offsets[u + 1] - off), maxT);      // the lattice scratch holds maxT frames per utterance
     const R NINF = Num<R>::ninf();
     const int lane = pl & 31;
     const size_t blk = (size_t)(pl >> 5) * maxT * N * 32;

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_estep_tc(const EtParams p) {
         pos = p.model_start[m] + idx;
         const int u = p.order[pos];
         off = p.offsets[u];
-        return (int)(p.offsets[u + 1] - off);
+        return min((int)(p.offsets[u + 1] - off), p.maxT);      // the scratch holds maxT frames per row
     };
     auto tile_frames = [&](int tile) -> int {
         int Tt = 0;

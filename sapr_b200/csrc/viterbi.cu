@@ -84,7 +84,7 @@ k_viterbi_fused(const float *__restrict__ X, int ldx, const int64_t *__restrict_
     const R lbN = lb_g[(size_t)m * S + N], laX = la_g[(size_t)m * S + S - 1];   // ln A[N, exit], ln A[exit, exit]
     const int64_t off = offsets[u];
     const int T = (int)(offsets[u + 1] - off);
-    const int Te = (first_frames > 0 && first_frames < T) ? first_frames : T;
+    const int Te = min((first_frames > 0 && first_frames < T) ? first_frames : T, maxT);   // the scratch holds maxT frames
     const R NINF = Num<R>::ninf();
 
     R V[NMAX + 1];   // V[j] = state j+1 (emitting), j < N;  exit kept separately
@@ -173,7 +173,7 @@ __global__ void k_viterbi_finish(const int64_t *__restrict__ offsets, int u0, in
     const int S = N + 2;
     const int64_t off = offsets[u];
     const int T = (int)(offsets[u + 1] - off);
-    const int Te = (first_frames > 0 && first_frames < T) ? first_frames : T;
+    const int Te = min((first_frames > 0 && first_frames < T) ? first_frames : T, maxT);
     double bs = -INFINITY;
     int bslot = -1;
     for (int s = 0; s < nslots; s++) {
@@ -230,7 +230,7 @@ k_viterbi_finish_fast(const int64_t *__restrict__ offsets, int u0, int nu, int N
     if (live) {
         off = offsets[u];
         const int T = (int)(offsets[u + 1] - off);
-        Te = (first_frames > 0 && first_frames < T) ? first_frames : T;
+        Te = min((first_frames > 0 && first_frames < T) ? first_frames : T, maxT);
         double second = -INFINITY;
         for (int s = 0; s < nslots; s++) {
             const double sc = scores[(size_t)ul * nslots + s];

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_viterbi_tc(const TcParams p) 
         off = 0;
         if (ul >= p.nu) return 0;
         off = p.offsets[p.u0 + ul];
-        const int T = (int)(p.offsets[p.u0 + ul + 1] - off);
+        const int T = min((int)(p.offsets[p.u0 + ul + 1] - off), p.maxT);     // the scratch is sized by the caller's max_T: never walk past it
         return (p.first_frames > 0 && p.first_frames < T) ? p.first_frames : T;
     };
     auto tile_frames = [&](int tile) -> int {
