@@ -1112,6 +1112,7 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
     const int Tpad = (Tt + fb - 1) / fb * fb;
     const int64_t per_utt = (int64_t)TC_GROUPS * Tpad * sizeof(uint32_t);
     int chunk = (int)std::min<int64_t>(B, std::max<int64_t>(TC_ROWS, ((int64_t)1024 << 20) / per_utt));
+    if (const char *ce = getenv("SAPR_V_CHUNK")) chunk = std::max(1, std::min(chunk, atoi(ce)));     // tests: force the multi-chunk path
     chunk = (chunk + TC_ROWS - 1) / TC_ROWS * TC_ROWS;
     int rc;
     if ((rc = sapr_ws_reserve(ctx, 0, (size_t)per_utt * chunk))) return rc;

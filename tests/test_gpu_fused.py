@@ -466,3 +466,22 @@ def test_viterbi_blocked_forward_arc_scores_minus_inf(eng):
     assert_close(got, sc, 1e-6, what="scores")
     assert np.array_equal(out["best_word"].cpu().numpy(), bw)
     assert np.mean(out["path"].cpu().numpy() == bp) > 0.999
+
+
+def test_viterbi_equal_length_multi_chunk(eng, monkeypatch):
+    """Batches whose back-pointer scratch exceeds 1 GB are decoded in chunks of utterances (335 k at cfg 2); SAPR_V_CHUNK forces
+    that path at a small size: words, scores, paths and the near-tie re-decoding must equal the single-chunk call."""
+    from sapr_b200 import synth
+    feats, labels, mu, sd = synth.make_corpus(1000, 11, 8, 39, 40, 40, seed=17)
+    A, means, var = synth.truth_models(mu, sd, 0.9)
+    means[7] = means[2] + 1e-7 * np.sqrt(var[2]); var[7] = var[2]; A[7] = A[2]        # some near-ties in every chunk
+    m = eng.WordModels(11, 8, 39)
+    m.set(means, var, A)
+    batch = eng.PackedBatch.from_features(feats)
+    one = m.viterbi(batch, None, eng.FP32, 0, want_scores=True, want_path=True)
+    f1 = m.ctx.viterbi_flagged()
+    monkeypatch.setenv("SAPR_V_CHUNK", "256")
+    many = m.viterbi(batch, None, eng.FP32, 0, want_scores=True, want_path=True)
+    assert m.ctx.viterbi_flagged() == f1 and f1 > 0
+    for k in ("best_word", "best_score", "scores", "path"):
+        assert np.array_equal(one[k].cpu().numpy(), many[k].cpu().numpy()), k
