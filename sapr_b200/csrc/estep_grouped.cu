@@ -33,7 +33,17 @@
 #define EG_MMA_WARP (EG_REC_WARPS + EG_CONV_WARPS)
 #define EG_TMA_WARP (EG_MMA_WARP + 1)
 #define EG_THREADS (32 * (EG_TMA_WARP + 1))
-#define EG_A_STAGES 3
+#ifndef EG_T_STAGES
+#define EG_T_STAGES 4         /* A-operand stages of the emission product in TMEM */
+#endif
+#define EG_I_STAGES 3         /* shared-memory image stages (statistics product, backward frames) */
+#ifndef EG_ACC
+#define EG_ACC 6              /* emission accumulator stages (16 TMEM columns each): deep, so the conversion -> product -> recursion hand-offs overlap */
+#endif
+#ifndef EG_GAM
+#define EG_GAM 4              /* posterior operand stages */
+#endif
+#define EG_NBAR (2 * EG_MAX_RAW + 2 * EG_T_STAGES + EG_I_STAGES + 2 * EG_ACC + 2 * EG_GAM + 4)
 #define EG_MAX_RAW 8
 #define EG_GROUP 8            /* frames per statistics accumulation group */
 #define EG_PF 3               /* backward sweep: L1 prefetch distance of the alpha-hat scratch, in frames */
@@ -58,13 +68,13 @@ __host__ __device__ inline EgSmem eg_smem_layout(int M, int nck, int nraw, uint3
     EgSmem L;
     const uint32_t stage = 2u * 16u * nck * 128u;     // hi plane + lo plane, [16 row groups][nck chunks][8 rows][8 halves]
     L.a = 0;
-    L.raw = EG_A_STAGES * stage;
+    L.raw = EG_I_STAGES * stage;
     L.w = L.raw + (uint32_t)nraw * TC_ROWS * rw;
     L.gam = L.w + 2u * (2u * nck * 128u);             // two W buffers (alternate tiles)
-    L.tr = L.gam + 2u * 4096u;                        // two posterior operands [16 row groups][2][8 rows][8 halves]
+    L.tr = L.gam + (uint32_t)EG_GAM * 4096u;          // posterior operands [16 row groups][2][8 rows][8 halves]
     L.sb = L.tr + (uint32_t)M * TC_TRQ * 16;
     L.bar = (L.sb + (uint32_t)8 * nck * 4 + 15u) & ~15u;
-    L.total = L.bar + (2 * EG_MAX_RAW + 3 * EG_A_STAGES + 12) * 8 + 16;
+    L.total = L.bar + EG_NBAR * 8 + 16;
     return L;
 }
 
@@ -114,13 +124,13 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
     const uint32_t sA = smem_u32(smem + L.a), sRaw = smem_u32(smem + L.raw), sW = smem_u32(smem + L.w), sG = smem_u32(smem + L.gam);
     const float4 *sTr = reinterpret_cast<const float4 *>(smem + L.tr);
     uint64_t *sBar = reinterpret_cast<uint64_t *>(smem + L.bar);
-    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 2 * EG_MAX_RAW + 3 * EG_A_STAGES + 12);
+    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + EG_NBAR);
     const uint32_t bRawFull = smem_u32(sBar), bRawEmpty = bRawFull + 8 * EG_MAX_RAW;
-    const uint32_t bAFull = bRawEmpty + 8 * EG_MAX_RAW, bAFree = bAFull + 8 * EG_A_STAGES;
-    const uint32_t bImgFree = bAFree + 8 * EG_A_STAGES;          // shared-memory image stages (backward frames only)
-    const uint32_t bAccFull = bImgFree + 8 * EG_A_STAGES, bAccEmpty = bAccFull + 16;
-    const uint32_t bGamFull = bAccEmpty + 16, bGamFree = bGamFull + 16;
-    const uint32_t bStFull = bGamFree + 16, bStEmpty = bStFull + 16;
+    const uint32_t bAFull = bRawEmpty + 8 * EG_MAX_RAW, bAFree = bAFull + 8 * EG_T_STAGES;
+    const uint32_t bImgFree = bAFree + 8 * EG_T_STAGES;          // shared-memory image stages (backward frames only)
+    const uint32_t bAccFull = bImgFree + 8 * EG_I_STAGES, bAccEmpty = bAccFull + 8 * EG_ACC;
+    const uint32_t bGamFull = bAccEmpty + 8 * EG_ACC, bGamFree = bGamFull + 8 * EG_GAM;
+    const uint32_t bStFull = bGamFree + 8 * EG_GAM, bStEmpty = bStFull + 16;
 
     {
         float4 *dtr = reinterpret_cast<float4 *>(smem + L.tr);
@@ -132,29 +142,28 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
         uint4 *za = reinterpret_cast<uint4 *>(smem + L.a);
         for (uint32_t i = tid; i < (L.w - L.a) / 16; i += EG_THREADS) za[i] = make_uint4(0, 0, 0, 0);
         uint4 *zg = reinterpret_cast<uint4 *>(smem + L.gam);
-        for (uint32_t i = tid; i < 2 * 4096 / 16; i += EG_THREADS) zg[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = tid; i < EG_GAM * 4096 / 16; i += EG_THREADS) zg[i] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
         for (int s = 0; s < nraw; s++) { mbar_init(bRawFull + 8 * s, 1); mbar_init(bRawEmpty + 8 * s, EG_CONV_WARPS); }
-        for (int s = 0; s < EG_A_STAGES; s++) { mbar_init(bAFull + 8 * s, EG_CONV_WARPS); mbar_init(bAFree + 8 * s, 1); mbar_init(bImgFree + 8 * s, 1); }
-        for (int s = 0; s < 2; s++) {
-            mbar_init(bAccFull + 8 * s, 1); mbar_init(bAccEmpty + 8 * s, EG_REC_WARPS);
-            mbar_init(bGamFull + 8 * s, EG_REC_WARPS); mbar_init(bGamFree + 8 * s, 1);
-            mbar_init(bStFull + 8 * s, 1); mbar_init(bStEmpty + 8 * s, EG_REC_WARPS);
-        }
+        for (int s = 0; s < EG_T_STAGES; s++) { mbar_init(bAFull + 8 * s, EG_CONV_WARPS); mbar_init(bAFree + 8 * s, 1); }
+        for (int s = 0; s < EG_I_STAGES; s++) mbar_init(bImgFree + 8 * s, 1);
+        for (int s = 0; s < EG_ACC; s++) { mbar_init(bAccFull + 8 * s, 1); mbar_init(bAccEmpty + 8 * s, EG_REC_WARPS); }
+        for (int s = 0; s < EG_GAM; s++) { mbar_init(bGamFull + 8 * s, EG_REC_WARPS); mbar_init(bGamFree + 8 * s, 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(bStFull + 8 * s, 1); mbar_init(bStEmpty + 8 * s, EG_REC_WARPS); }
         fence_barrier_init();
     }
     const uint32_t a_cols = 8u * nck;                             // TMEM columns of one A-operand stage: per K step [hi 8 | lo 8]
     uint32_t tcols = 128;
-    while (tcols < 64u + EG_A_STAGES * a_cols) tcols <<= 1;
+    while (tcols < 16u * EG_ACC + 32u + EG_T_STAGES * a_cols) tcols <<= 1;
     if (warp == EG_MMA_WARP) tmem_alloc(smem_u32(sTmem), tcols);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *sTmem;
-    const uint32_t tmem_acc = tmem_base, tmem_st = tmem_base + 32u;    // 2 x 16 emission columns, 2 x 16 statistics columns
-    const uint32_t tmem_a = tmem_base + 64u;                           // EG_A_STAGES A-operand stages of the emission product
+    const uint32_t tmem_acc = tmem_base, tmem_st = tmem_base + 16u * EG_ACC;   // EG_ACC x 16 emission columns, 2 x 16 statistics columns
+    const uint32_t tmem_a = tmem_st + 32u;                                      // EG_T_STAGES A-operand stages of the emission product
     const int npf = 2 * T;                                            // pipeline frames per tile: forward, then backward
 
     if (warp == EG_TMA_WARP) {
@@ -231,9 +240,9 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
                         umma_commit(bAFree + 8 * ar.s);               // the TMEM operand is free once the emission product has read it
                     }
                     __syncwarp();
-                    if (ei > T) { a_hist[ei & 3] = ir.s; ir.next(EG_A_STAGES); }   // backward frames with statistics also have a shared-memory image
-                    ar.next(EG_A_STAGES);
-                    cr.next(2);
+                    if (ei > T) { a_hist[ei & 3] = ir.s; ir.next(EG_I_STAGES); }   // backward frames with statistics also have a shared-memory image
+                    ar.next(EG_T_STAGES);
+                    cr.next(EG_ACC);
                     ei++;
                     did = true;
                 }
@@ -261,7 +270,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
                     }
                     __syncwarp();
                     if (last) sr.next(2);
-                    gr.next(2);
+                    gr.next(EG_GAM);
                     sf++; si++;
                     did = true;
                 }
@@ -335,8 +344,8 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
                 __syncwarp();
                 if (lane0) { mbar_arrive(bAFull + 8 * ar.s); mbar_arrive(bRawEmpty + 8 * rr.s); }
                 rr.next((uint32_t)nraw);
-                ar.next(EG_A_STAGES);
-                if (img) ir.next(EG_A_STAGES);
+                ar.next(EG_T_STAGES);
+                if (img) ir.next(EG_I_STAGES);
             }
         }
     } else {
@@ -359,7 +368,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bAccEmpty + 8 * cr.s);
-            cr.next(2);
+            cr.next(EG_ACC);
 #pragma unroll
             for (int j = 0; j < 8; j++) e[j] = __uint_as_float(ev[j]) + __uint_as_float(ev[8 + j]);
         };
@@ -471,7 +480,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bGamFull + 8 * gr.s);
-                    gr.next(2);
+                    gr.next(EG_GAM);
                     sf++;
                     if (sf >= (drained + 1) * EG_GROUP + 2) { drain(); drained++; }
                 } else {
@@ -529,7 +538,7 @@ __global__ void __launch_bounds__(EG_THREADS, 1) k_estep_grouped(const EgParams 
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bGamFull + 8 * gr.s);
-                        gr.next(2);
+                        gr.next(EG_GAM);
                         sf++;
                     }
                     float mb = fmaxf(fmaxf(nb[0], nb[1]), nb[2]);
