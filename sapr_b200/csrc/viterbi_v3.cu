@@ -1004,8 +1004,6 @@ k_viterbi_finish_v3(const int64_t *__restrict__ offsets, int u0, int nu, int M, 
                     uint32_t Bpad, const V3Map map, const double *__restrict__ scores, int32_t *__restrict__ best_word,
                     double *__restrict__ best_score, double *__restrict__ scores_out, uint8_t *__restrict__ best_path, const SaprFlag flag) {
     constexpr int CH = 32;
-    __shared__ uint8_t sp[4][32][CH + 4];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int ul = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = ul < nu;
     const int u = u0 + ul;
@@ -1032,30 +1030,46 @@ k_viterbi_finish_v3(const int64_t *__restrict__ offsets, int u0, int nu, int M, 
     const int sh = map.shift[wslot];
     const int Te = live ? Tt : 0;
     int cur = 9;
+    // every utterance has Tt frames: lane = utterance, 32 frames per chunk.  The chunk's words are fetched with 32 independent
+    // loads (pointer walks by a fixed stride), the traced states of the chunk are packed four per register and written with
+    // 8-byte stores when the utterance's path is 8-byte aligned (byte stores otherwise).  The winner's model group differs from
+    // lane to lane, so a lane's 4-byte word costs a 32-byte sector (3.2 KB per utterance): memory-bound at ~0.08 ms per 100 k.
+    const uint8_t *bpb = reinterpret_cast<const uint8_t *>(bpp);
+    const size_t fstride = (size_t)Bpad * sizeof(uint32_t);
+    uint8_t *out = best_path + off;
+    const bool al8 = ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
     for (int t0 = (Tt - 1) / CH * CH; t0 >= 0; t0 -= CH) {
         uint32_t bits[CH];
+        const uint8_t *q = bpb + (size_t)t0 * fstride;
 #pragma unroll
-        for (int j = 0; j < CH; j++) {
+        for (int j = 0; j < CH; j++, q += fstride) {
             const int t = t0 + j;
-            bits[j] = (reachable && t >= 1 && t < Te) ? (bpp[(size_t)t * Bpad] >> sh) & 0xFFu : 0xFFu;
+            bits[j] = (reachable && t >= 1 && t < Te) ? (*reinterpret_cast<const uint32_t *>(q) >> sh) & 0xFFu : 0xFFu;
         }
+        uint32_t pk[CH / 4];
+#pragma unroll
+        for (int k = 0; k < CH / 4; k++) pk[k] = 0;
 #pragma unroll
         for (int j = CH - 1; j >= 0; j--) {
             const int t = t0 + j;
             if (t < Te) {
-                sp[w][lane][j] = (uint8_t)cur;
+                pk[j >> 2] |= (uint32_t)cur << (8 * (j & 3));
                 if (!reachable) cur = 0;                                          // unreachable cell: back-pointer stays 0 (:470)
                 else if (cur >= 2) cur -= (int)(((bits[j] >> (cur - 2)) & 1u) ^ 1u);   // a set bit = stayed (frame 0 reads as all set)
                 else if (cur == 1 && t == 1) cur -= (int)(bits[j] >> 7);         // entry arc (exit slot at t == 1)
             }
         }
-        __syncwarp();
-        for (int row = 0; row < 32; row++) {
-            const int Te_r = __shfl_sync(0xffffffffu, Te, row);
-            const int64_t off_r = __shfl_sync(0xffffffffu, off, row);
-            if (t0 + lane < Te_r) best_path[off_r + t0 + lane] = sp[w][row][lane];
+        if (live) {
+            const int nb = min(CH, Te - t0);                                      // bytes of this chunk
+            if (al8 && (t0 & 7) == 0 && nb == CH) {
+#pragma unroll
+                for (int k = 0; k < CH / 8; k++) *reinterpret_cast<uint2 *>(out + t0 + 8 * k) = make_uint2(pk[2 * k], pk[2 * k + 1]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < CH; j++)
+                    if (j < nb) out[t0 + j] = (uint8_t)(pk[j >> 2] >> (8 * (j & 3)));
+            }
         }
-        __syncwarp();
     }
 }
 
