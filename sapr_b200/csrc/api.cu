@@ -16,6 +16,7 @@ extern "C" int sapr_ctx_create(int device, void *cuda_stream, sapr_ctx **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SAPR_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SAPR_E_CUDA; }
     for (int i = 0; i < 8; i++)
         if (cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming) != cudaSuccess) { delete c; return SAPR_E_CUDA; }
     *out = c;
@@ -32,6 +33,7 @@ extern "C" int sapr_ctx_destroy(sapr_ctx *ctx) {
     for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto &r : ctx->prof_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
     delete ctx;
     return SAPR_OK;
 }

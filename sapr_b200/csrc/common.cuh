@@ -30,6 +30,7 @@ struct sapr_ctx {
     void *pin[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t pin_bytes[4] = {0, 0, 0, 0};
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;      // float64 re-decoding of word near-ties beside the fp32 back-trace
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // optional per-kernel event timing (bench.py roofline)
     bool profiling = false;
@@ -140,6 +141,11 @@ __device__ __forceinline__ void sapr_flag_word(const SaprFlag &f, int u, double 
 int sapr_viterbi_redo_flagged(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int first_frames,
                               const SaprFlag &flag, int32_t *best_word, double *best_score, double *scores, uint8_t *best_path);
 int sapr_flag_setup(sapr_ctx *ctx, SaprFlag *flag, bool first_chunk);   // workspace slot 5; zeroes the per-chunk counter
+int sapr_viterbi_flag_words(sapr_ctx *ctx, const double *scores, int u0, int nu, int M, const SaprFlag &flag);
+int sapr_viterbi_redo_compute(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int first_frames,
+                              const SaprFlag &flag, cudaStream_t st);
+int sapr_viterbi_redo_finish(sapr_ctx *ctx, sapr_models *m, const int64_t *offsets, int first_frames, const SaprFlag &flag,
+                             int32_t *best_word, double *best_score, double *scores, uint8_t *best_path);
 
 int sapr_ws_reserve(sapr_ctx *ctx, int slot, size_t bytes);   // grows ctx->ws[slot]
 int sapr_pin_reserve(sapr_ctx *ctx, int slot, size_t bytes);  // grows ctx->pin[slot]

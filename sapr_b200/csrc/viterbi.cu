@@ -461,39 +461,82 @@ int sapr_flag_setup(sapr_ctx *ctx, SaprFlag *flag, bool first_chunk) {
     return SAPR_OK;
 }
 
-int sapr_viterbi_redo_flagged(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int first_frames,
-                              const SaprFlag &flag, int32_t *best_word, double *best_score, double *scores, uint8_t *best_path) {
-    // float64 emissions (frame-parallel) + recursion (state-parallel) + arg-max / back-trace over the listed utterances; the kernels
-    // read the list length on the device (no host round trip)
+// float64 emissions (frame-parallel) + recursion (state-parallel) of the listed utterances on stream `st`; the kernels read the
+// list length on the device (no host round trip).  sapr_viterbi_redo_finish then takes the arg-max / back-trace of the listed
+// utterances on the context's stream and overwrites their word, score, score row and path.
+struct RedoPlan { int cap, Tm, Tq, nslots; uint16_t *bp; double *sc_ws, *E; bool ok; };
+static int redo_plan(sapr_ctx *ctx, sapr_models *m, int first_frames, const SaprFlag &flag, RedoPlan *pl) {
+    pl->ok = false;
     if (m->N > 8) return SAPR_OK;
-    const int nslots = m->M, nchunk = m->Dp / 4, cap = flag.cap;
-    // the longest utterance bounds the scratch: taken from the caller's max_T through first_frames / offsets is not possible
-    // here, so the scratch is sized by the caller (maxT argument below = ctx-side value)
+    pl->nslots = m->M; pl->cap = flag.cap;
     const int maxT = ctx->flag_maxT;
-    const int Tm = (first_frames > 0 && first_frames < maxT) ? first_frames : maxT;
-    const int Tq = Tm > 0 ? Tm : 1;
-    const size_t bp_bytes = ((size_t)nslots * Tq * cap * sizeof(uint16_t) + 255) / 256 * 256;
-    const size_t sc_bytes = ((size_t)cap * nslots * sizeof(double) + 255) / 256 * 256;
-    const size_t e_bytes = (size_t)cap * nslots * Tq * 8 * sizeof(double);
+    pl->Tm = (first_frames > 0 && first_frames < maxT) ? first_frames : maxT;
+    pl->Tq = pl->Tm > 0 ? pl->Tm : 1;
+    const size_t bp_bytes = ((size_t)pl->nslots * pl->Tq * pl->cap * sizeof(uint16_t) + 255) / 256 * 256;
+    const size_t sc_bytes = ((size_t)pl->cap * pl->nslots * sizeof(double) + 255) / 256 * 256;
+    const size_t e_bytes = (size_t)pl->cap * pl->nslots * pl->Tq * 8 * sizeof(double);
+    if ((size_t)pl->Tq * 8 * sizeof(double) > 200 * 1024) return SAPR_OK;   // utterances too long for the shared-memory emission staging: no re-decoding
     int rc = sapr_ws_reserve(ctx, 4, bp_bytes + sc_bytes + e_bytes);
     if (rc) return rc;
-    uint16_t *bp = (uint16_t *)ctx->ws[4];
-    double *sc_ws = (double *)((char *)ctx->ws[4] + bp_bytes);
-    double *E = (double *)((char *)ctx->ws[4] + bp_bytes + sc_bytes);
-    const size_t per_warp = (size_t)Tq * 8 * sizeof(double);
-    if (per_warp > 200 * 1024) return SAPR_OK;            // utterances too long for the shared-memory emission staging: no re-decoding
+    pl->bp = (uint16_t *)ctx->ws[4];
+    pl->sc_ws = (double *)((char *)ctx->ws[4] + bp_bytes);
+    pl->E = (double *)((char *)ctx->ws[4] + bp_bytes + sc_bytes);
+    pl->ok = true;
+    return SAPR_OK;
+}
+
+int sapr_viterbi_redo_compute(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int first_frames,
+                              const SaprFlag &flag, cudaStream_t st) {
+    RedoPlan pl;
+    int rc = redo_plan(ctx, m, first_frames, flag, &pl);
+    if (rc || !pl.ok) return rc;
+    const size_t per_warp = (size_t)pl.Tq * 8 * sizeof(double);
     const int wpb = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_warp));
     SAPR_CUDA(ctx, cudaFuncSetAttribute(k_redo_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wpb * per_warp)));
+    k_redo_emission<<<4 * ctx->sm_count, 256, 0, st>>>(X, ldx, offsets, flag.list, flag.count, pl.cap, m->M, m->N, m->Dp / 4, pl.Tq, first_frames,
+                                                      m->pk64, m->cst64, pl.E);
+    SAPR_LAUNCH_CHECK(ctx);
+    k_redo_f64<<<ctx->sm_count, 32 * wpb, wpb * per_warp, st>>>(offsets, flag.list, flag.count, pl.cap, m->M, m->N, pl.Tq, first_frames, pl.E, m->la64,
+                                                             m->lb64, pl.bp, (int64_t)pl.cap, pl.sc_ws);
+    SAPR_LAUNCH_CHECK(ctx);
+    return SAPR_OK;
+}
+
+int sapr_viterbi_redo_finish(sapr_ctx *ctx, sapr_models *m, const int64_t *offsets, int first_frames, const SaprFlag &flag,
+                             int32_t *best_word, double *best_score, double *scores, uint8_t *best_path) {
+    RedoPlan pl;
+    int rc = redo_plan(ctx, m, first_frames, flag, &pl);
+    if (rc || !pl.ok) return rc;
+    k_viterbi_finish_fast<uint16_t><<<(pl.cap + 127) / 128, 128, 0, ctx->stream>>>(offsets, 0, pl.cap, m->N, pl.nslots, nullptr, first_frames, pl.bp,
+                                                                                  (int64_t)pl.cap, pl.Tm, pl.sc_ws, best_word, best_score, scores,
+                                                                                  best_path, flag.list, flag.count);
+    SAPR_LAUNCH_CHECK(ctx);
+    return SAPR_OK;
+}
+
+int sapr_viterbi_redo_flagged(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int first_frames,
+                              const SaprFlag &flag, int32_t *best_word, double *best_score, double *scores, uint8_t *best_path) {
     ProfScope ps(ctx, 6);
-    k_redo_emission<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(X, ldx, offsets, flag.list, flag.count, cap, m->M, m->N, nchunk, Tq, first_frames,
-                                                               m->pk64, m->cst64, E);
-    SAPR_LAUNCH_CHECK(ctx);
-    k_redo_f64<<<ctx->sm_count, 32 * wpb, wpb * per_warp, ctx->stream>>>(offsets, flag.list, flag.count, cap, m->M, m->N, Tq, first_frames, E,
-                                                                      m->la64, m->lb64, bp, (int64_t)cap, sc_ws);
-    SAPR_LAUNCH_CHECK(ctx);
-    k_viterbi_finish_fast<uint16_t><<<(cap + 127) / 128, 128, 0, ctx->stream>>>(offsets, 0, cap, m->N, nslots, nullptr, first_frames, bp,
-                                                                               (int64_t)cap, Tm, sc_ws, best_word, best_score, scores,
-                                                                               best_path, flag.list, flag.count);
+    int rc = sapr_viterbi_redo_compute(ctx, m, X, ldx, offsets, first_frames, flag, ctx->stream);
+    if (rc) return rc;
+    return sapr_viterbi_redo_finish(ctx, m, offsets, first_frames, flag, best_word, best_score, scores, best_path);
+}
+
+// arg-max + runner-up over the models of every utterance of a chunk -> the near-tie list only (the equal-length path runs the
+// float64 re-decoding on a second stream beside the fp32 back-trace, so the list is needed before that kernel)
+__global__ void k_flag_words(const double *__restrict__ scores, int u0, int nu, int M, SaprFlag flag) {
+    const int ul = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ul >= nu) return;
+    double bs = -INFINITY, second = -INFINITY;
+    for (int s = 0; s < M; s++) {
+        const double sc = scores[(size_t)ul * M + s];
+        if (sc > bs) { second = bs; bs = sc; }
+        else if (sc > second) second = sc;
+    }
+    sapr_flag_word(flag, u0 + ul, bs, second);
+}
+int sapr_viterbi_flag_words(sapr_ctx *ctx, const double *scores, int u0, int nu, int M, const SaprFlag &flag) {
+    k_flag_words<<<(nu + 255) / 256, 256, 0, ctx->stream>>>(scores, u0, nu, M, flag);
     SAPR_LAUNCH_CHECK(ctx);
     return SAPR_OK;
 }

@@ -1193,14 +1193,26 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
             kern<<<std::min(prm.ntiles, ctx->sm_count), nthreads, L.total, ctx->stream>>>(prm, tmap);
         }
         SAPR_LAUNCH_CHECK(ctx);
+        if (exact) {
+            // the near-tie list first, then the float64 re-decoding of the listed utterances on the auxiliary stream BESIDE the fp32
+            // arg-max / back-trace; its results overwrite the listed utterances once both are done
+            if ((rc = sapr_viterbi_flag_words(ctx, prm.scores, u0, nu, M, flag))) return rc;
+            SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+            SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev[6], 0));
+            if ((rc = sapr_viterbi_redo_compute(ctx, m, X, ldx, offsets, first_frames, flag, ctx->aux_stream))) return rc;
+            SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->aux_stream));
+        }
         {
             ProfScope ps(ctx, 1);
             k_viterbi_finish_v3<<<(nu + 127) / 128, 128, 0, ctx->stream>>>(offsets, u0, nu, M, Tt, Tpad, prm.bp, prm.Bpad, map, prm.scores,
-                                                                          best_word, best_score, scores, best_path, exact ? flag : SaprFlag());
+                                                                          best_word, best_score, scores, best_path, SaprFlag());
         }
         SAPR_LAUNCH_CHECK(ctx);
-        if (exact && (rc = sapr_viterbi_redo_flagged(ctx, m, X, ldx, offsets, first_frames, flag, best_word, best_score, scores, best_path)))
-            return rc;
+        if (exact) {
+            SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[7], 0));
+            ProfScope ps(ctx, 6);
+            if ((rc = sapr_viterbi_redo_finish(ctx, m, offsets, first_frames, flag, best_word, best_score, scores, best_path))) return rc;
+        }
     }
     *taken = true;
     return SAPR_OK;
