@@ -485,3 +485,31 @@ def test_viterbi_equal_length_multi_chunk(eng, monkeypatch):
     assert m.ctx.viterbi_flagged() == f1 and f1 > 0
     for k in ("best_word", "best_score", "scores", "path"):
         assert np.array_equal(one[k].cpu().numpy(), many[k].cpu().numpy()), k
+
+
+@pytest.mark.parametrize("M,D", [(4, 39), (7, 36), (12, 38), (11, 12), (12, 15), (5, 13)])
+def test_viterbi_equal_length_shape_sweep_vs_oracle(eng, M, D):
+    """k_viterbi_v4 over the shapes it takes (4 <= M <= 12 models split 1-3 per recursion group, D in the 10- and 4-chunk
+    classes) and the lengths around its special frames (t = 0, 1; exit closed below 8 frames; padding frames when T is not a
+    multiple of four; one and 130 utterances = partial tiles): words, scores and paths against the CPU oracle."""
+    from sapr_b200 import synth
+    for T, B in ((2, 130), (3, 1), (5, 130), (8, 33), (9, 130), (13, 1), (16, 130), (30, 257)):
+        Tg = max(T, 16)                                        # the generator needs a frame per state; short cases are truncated
+        feats, labels, mu, sd = synth.make_corpus(B, M, 8, D, Tg, Tg, seed=7 * T + B + M)
+        feats = [np.ascontiguousarray(f[:, :T]) for f in feats]
+        A, means, var = synth.truth_models(mu, sd, 0.85)
+        m = eng.WordModels(M, 8, D)
+        m.set(means, var, A)
+        batch = eng.PackedBatch.from_features(feats)
+        X, offs = orc.pack(feats)
+        with np.errstate(all="ignore"):
+            bw, bs, sc, bp = orc.viterbi_batch(X, offs, A, means, var)
+        out = m.viterbi(batch, None, eng.FP32, 0, want_scores=True, want_path=True)
+        assert_close(out["scores"].cpu().numpy(), sc, 1e-6, what=f"scores T={T} B={B}")
+        assert np.array_equal(out["best_word"].cpu().numpy(), bw), (T, B)            # near-ties are re-decoded in float64
+        got = out["path"].cpu().numpy().astype(np.int32)
+        if T >= 9:
+            assert np.mean(got == bp) > 0.995, (T, B, np.mean(got == bp))
+        else:
+            # no model reaches the exit below 9 frames: every score is -inf, decoder.py:42-47 picks no word and returns no path
+            assert np.all(out["best_word"].cpu().numpy() == -1) and np.all(np.isneginf(sc))
