@@ -269,7 +269,9 @@ def train_words(models: WordModels, batch: PackedBatch, labels, n_iter: int, flo
     torch = _torch()
     import os
     grouped = None
-    if GroupedBatch.eligible(models, batch, precision) and os.environ.get("SAPR_GROUPED", "1") != "0":
+    # the fused grouped kernel (csrc/estep_grouped.cu) moves 30 % less DRAM traffic but is slower than the general path at every
+    # size measured (tools/train_bench.py: 0.32 vs 0.25 ms at 330 utterances, 4.6 vs 3.9 ms at 200 k): opt-in
+    if GroupedBatch.eligible(models, batch, precision) and os.environ.get("SAPR_GROUPED", "0") == "1":
         grouped = GroupedBatch(batch, labels, models.M)       # once per fit: utterances re-stored grouped by word
     elif order is None:
         order = group_by_model(labels)

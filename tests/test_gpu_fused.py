@@ -513,3 +513,26 @@ def test_viterbi_equal_length_shape_sweep_vs_oracle(eng, M, D):
         else:
             # no model reaches the exit below 9 frames: every score is -inf, decoder.py:42-47 picks no word and returns no path
             assert np.all(out["best_word"].cpu().numpy() == -1) and np.all(np.isneginf(sc))
+
+
+def test_train_words_grouped_path_matches_general(eng, monkeypatch):
+    """engine.train_words: the opt-in fused grouped E-step (SAPR_GROUPED=1) and the default general path give the same
+    Baum-Welch trajectory (custom_hmm.py:402-460 for the whole vocabulary) on an equal-length corpus."""
+    import torch
+    from sapr_b200 import synth
+    feats, labels, mu, sd = synth.make_corpus(600, 11, 8, 39, 40, 40, seed=33)
+    A, means, var = synth.truth_models(mu, sd, 0.9)
+    rng = np.random.default_rng(1)
+    means0 = means + 0.2 * np.sqrt(var) * rng.standard_normal(means.shape)
+    batch = eng.PackedBatch.from_features(feats)
+    lab = torch.as_tensor(np.asarray(labels, dtype=np.int32), device="cuda")
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SAPR_GROUPED", mode)
+        m = eng.WordModels(11, 8, 39)
+        m.set(means0, var, A)
+        hist = eng.train_words(m, batch, lab, 3, 1e-3, eng.FP32, tol=0.0)
+        out[mode] = (hist, m.get())
+    assert_close(out["1"][0], out["0"][0], 1e-6, what="log-likelihood history")
+    assert np.max(np.abs(out["1"][1][0] - out["0"][1][0]) / np.sqrt(var)) < 1e-3          # means, relative to sigma
+    assert_close(out["1"][1][2], out["0"][1][2], 1e-4, atol=1e-6, what="transitions")
