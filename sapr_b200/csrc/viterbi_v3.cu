@@ -31,6 +31,7 @@ struct V3Params {
     int mod0[TC_GROUPS], nmod[TC_GROUPS], pair0[TC_GROUPS], npair[TC_GROUPS];
     uint32_t rw;                        // bytes per row of the raw ring: (nck + 1) * 16
     long long *trace;                   // [V4_TRACE_ROLES][V4_TRACE_FRAMES][4] clock64 stamps of CTA 0 or null (SAPR_V_TRACE=file)
+    int split_col;                      // SPLIT kernels: accumulator columns of model groups 0-1 (a multiple of 16)
     int flags;                          // tuning what-ifs (SAPR_V_EXP, k_viterbi_v4<.., EXP = true>): 1 = no MMAs, 2 = no recursion arithmetic, 4 = no conversion arithmetic, 8 = no back-pointer stores, 16 = every tile of a CTA re-reads its first tile (L2 hits)
 };
 
@@ -378,7 +379,7 @@ __host__ __device__ inline V4Smem v4_smem_layout(int M, int nck, int ncols, uint
     L.tr = L.raw + 2u * V3_FB * TC_ROWS * rw;
     L.sb = L.tr + (uint32_t)M * TC_TRQ * 16;
     L.bar = (L.sb + (uint32_t)8 * nck * 4 + 15u) & ~15u;
-    L.total = L.bar + 16 * 8 + 16;      // raw_full[2], raw_empty[2], A_full[4], A_empty[4], acc_full[2], acc_empty[2]
+    L.total = L.bar + 24 * 8 + 16;      // raw_full[2], raw_empty[2], A_full[4], A_empty[4], acc_full[2][2], acc_empty[2][2] (stage, column half)
     return L;
 }
 
@@ -400,7 +401,9 @@ __device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t par_a, uint3
         ::"r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b) : "memory");
 }
 
-template <int NKS, bool TRACE = false, bool EXP = false>      // nck = 2 * NKS feature chunks; EXP: the what-if flags are honoured
+// SPLIT: each frame's product is issued as two column halves (model groups 0-1 | 2-3) with their own acc_full / acc_empty
+// barriers, so a recursion warp waits for half the MMAs and hands its half of a stage back on its own.
+template <int NKS, bool TRACE = false, bool EXP = false, bool SPLIT = false>      // nck = 2 * NKS feature chunks; EXP: the what-if flags are honoured
 __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int nck = 2 * NKS;
@@ -413,9 +416,9 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
     const uint32_t sRaw = smem_u32(smem + L.raw);
     const float4 *sTr = reinterpret_cast<const float4 *>(smem + L.tr);
     uint64_t *sBar = reinterpret_cast<uint64_t *>(smem + L.bar);
-    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 16);
+    uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 24);
     const uint32_t barRawFull = smem_u32(sBar), barRawEmpty = barRawFull + 16, barAFull = barRawFull + 32, barAEmpty = barRawFull + 64;
-    const uint32_t barAccFull = barRawFull + 96, barAccEmpty = barRawFull + 112;
+    const uint32_t barAccFull = barRawFull + 96, barAccEmpty = barRawFull + 128;      // + 16 * stage + 8 * half
 
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.wimg);
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
     if (tid == 0) {
         for (int s = 0; s < 2; s++) { mbar_init(barRawFull + 8 * s, 1); mbar_init(barRawEmpty + 8 * s, V4_CONV_WARPS); }
         for (int s = 0; s < 4; s++) { mbar_init(barAFull + 8 * s, V4_CONV_WARPS); mbar_init(barAEmpty + 8 * s, 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(barAccFull + 8 * s, 1); mbar_init(barAccEmpty + 8 * s, V4_REC_WARPS); }
+        for (int s = 0; s < 4; s++) { mbar_init(barAccFull + 8 * s, 1); mbar_init(barAccEmpty + 8 * s, SPLIT ? V4_REC_WARPS / 2 : V4_REC_WARPS); }
         fence_barrier_init();
     }
     constexpr uint32_t a_cols = 8u * nck;
@@ -474,6 +477,10 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
         const uint32_t sW_hi = smem_u32(sW), sW_lo = sW_hi + w_plane;
         const uint32_t sboW = (uint32_t)nck * 128u;
         const uint64_t dW_hi = make_desc(sW_hi, 128, sboW), dW_lo = make_desc(sW_lo, 128, sboW);
+        const uint32_t colA = (uint32_t)p.split_col;                                       // columns of model groups 0-1
+        const uint32_t idescA = (1u << 4) | ((colA >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+        const uint32_t idescB = (1u << 4) | ((((uint32_t)ncols - colA) >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+        const uint64_t wofs = (uint64_t)(((colA >> 3) * sboW) >> 4);                           // descriptor address units of 16 bytes
         uint32_t aph = 0;
         for (int b = 0; b < nblk; b++, aph ^= 1u) {
 #pragma unroll
@@ -484,23 +491,44 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
                     p.trace[((size_t)0 * V4_TRACE_FRAMES + 4 * b + i) * 4 + 1] = (long long)ns;
                 }
-                mbar_wait2(barAFull + 8 * i, aph, barAccEmpty + 8 * (i & 1), ((i >> 1) & 1) ^ 1);
+                mbar_wait2(barAFull + 8 * i, aph, barAccEmpty + 16 * (i & 1), ((i >> 1) & 1) ^ 1);
                 trace(0, 4 * b + i, 2);
                 tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t d_tmem = tmem_acc + (uint32_t)(i & 1) * (uint32_t)ncols;
-                    const uint32_t a_hi = tmem_a + (uint32_t)i * a_cols, a_lo = a_hi + 8u;
-                    // the two correction products first: the large hi * W_hi partial sums see the fewest truncating steps
-                    if (!EXP || !(p.flags & 1)) {
+                const uint32_t d_tmem = tmem_acc + (uint32_t)(i & 1) * (uint32_t)ncols;
+                const uint32_t a_hi = tmem_a + (uint32_t)i * a_cols, a_lo = a_hi + 8u;
+                if (!SPLIT) {
+                    if (elect_one()) {
+                        // the two correction products first: the large hi * W_hi partial sums see the fewest truncating steps
+                        if (!EXP || !(p.flags & 1)) {
 #pragma unroll
-                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_lo + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, ks > 0);
+                            for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_lo + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, ks > 0);
 #pragma unroll
-                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_lo + (uint64_t)(16 * ks), idesc, 1);
+                            for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_lo + (uint64_t)(16 * ks), idesc, 1);
 #pragma unroll
-                        for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, 1);
+                            for (int ks = 0; ks < NKS; ks++) umma_f16_ts(d_tmem, a_hi + ks * 16, dW_hi + (uint64_t)(16 * ks), idesc, 1);
+                        }
+                        umma_commit(barAccFull + 16 * (i & 1));
+                        umma_commit(barAEmpty + 8 * i);
                     }
-                    umma_commit(barAccFull + 8 * (i & 1));
-                    umma_commit(barAEmpty + 8 * i);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        if (h == 1) { mbar_wait(barAccEmpty + 16 * (i & 1) + 8, ((i >> 1) & 1) ^ 1); tc_fence_after(); }
+                        if (elect_one()) {
+                            const uint32_t dh = d_tmem + (h ? colA : 0u);
+                            const uint32_t idh = h ? idescB : idescA;
+                            const uint64_t wh = dW_hi + (h ? wofs : 0ull), wl = dW_lo + (h ? wofs : 0ull);
+#pragma unroll
+                            for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dh, a_lo + ks * 16, wh + (uint64_t)(16 * ks), idh, ks > 0);
+#pragma unroll
+                            for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dh, a_hi + ks * 16, wl + (uint64_t)(16 * ks), idh, 1);
+#pragma unroll
+                            for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dh, a_hi + ks * 16, wh + (uint64_t)(16 * ks), idh, 1);
+                            umma_commit(barAccFull + 16 * (i & 1) + 8 * h);
+                            if (h == 1) umma_commit(barAEmpty + 8 * i);
+                        }
+                        __syncwarp();
+                    }
                 }
                 __syncwarp();
                 trace(0, 4 * b + i, 3);
@@ -565,6 +593,8 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
         const uint32_t acc0 = pin_reg(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)mbeg * 8u);
         const uint32_t acc1 = pin_reg(acc0 + (uint32_t)ncols);
         const uint32_t lane0 = pin_reg(lane == 0 ? 1u : 0u);
+        const uint32_t hb = SPLIT ? 8u * (uint32_t)(g >> 1) : 0u;                          // this group's column half
+        const uint32_t bFull = pin_reg(barAccFull + hb), bEmpty = pin_reg(barAccEmpty + hb);
         const uint32_t bstride = pin_reg(p.Bpad);
         uint32_t *const bpp = p.bp;
         auto run = [&](auto MCc) {
@@ -577,14 +607,14 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
             // latency, the wait and the hand-back of the stage (acc_empty) run under the arithmetic of the current frame.
             uint32_t ev[MC][8];
             if (my_tiles > 0) {
-                mbar_wait(barAccFull, 0);
+                mbar_wait(bFull, 0);
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < MC; k++) tmem_ld8(acc0 + 8u * k, ev[k]);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane0) mbar_arrive(barAccEmpty);
+                if (lane0) mbar_arrive(bEmpty);
             }
             int tiles_left = my_tiles;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -610,7 +640,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
                     const uint32_t nacc = NS ? acc1 : acc0;
                     if (TRACE && trole >= 0) trace(trole, fbase + t0 + I, 0);
                     if (!GEN || more) {
-                        mbar_wait(barAccFull + 8 * NS, ((I + 1) >> 1) & 1);
+                        mbar_wait(bFull + 16 * NS, ((I + 1) >> 1) & 1);
                         tc_fence_after();
                     }
                     if (TRACE && trole >= 0) trace(trole, fbase + t0 + I, 1);
@@ -658,7 +688,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
                         tmem_ld_wait();
                         tc_fence_before();
                         __syncwarp();
-                        if (lane0) mbar_arrive(barAccEmpty + 8 * NS);            // the next frame's columns are in registers: its stage is free
+                        if (lane0) mbar_arrive(bEmpty + 16 * NS);            // the next frame's columns are in registers: its stage is free
                     }
                     if (TRACE && trole >= 0) trace(trole, fbase + t0 + I, 3);
                 };
@@ -1145,8 +1175,16 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
     for (int g = 0; g < TC_GROUPS; g++)
         for (int k = 0; k < prm.nmod[g]; k++) { map.grp[prm.mod0[g] + k] = g; map.shift[prm.mod0[g] + k] = 8 * k; }
     const int exp_flags = getenv("SAPR_V_EXP") ? atoi(getenv("SAPR_V_EXP")) : 0;
+    // SAPR_V_SPLIT=1: column-half products (model groups 0-1 | 2-3 split the accumulator at a multiple of 16 columns).  MEASURED SLOWER
+    // (0.93 vs 0.84 ms per 94 720 utterances): an N = 48 tcgen05.mma costs nearly what an N = 96 one does, so 30 small products per
+    // frame load the tensor pipe more than the earlier hand-off saves; kept as the record of that experiment
+    prm.split_col = 8 * prm.mod0[2];
+    const char *sp_env = getenv("SAPR_V_SPLIT");
+    const bool split = use_v4 && !use_v5 && !exp_flags && (sp_env && sp_env[0] == '1') && prm.split_col >= 16 && prm.split_col % 16 == 0 &&
+                       ncols - prm.split_col >= 16 && (ncols - prm.split_col) % 16 == 0;
     auto kern = use_v5 ? (nck == 10 ? k_viterbi_v5<5> : k_viterbi_v5<2>)
-                : use_v4 ? (nck == 10 ? (exp_flags ? k_viterbi_v4<5, false, true> : k_viterbi_v4<5>) : k_viterbi_v4<2>)
+                : use_v4 ? (nck == 10 ? (exp_flags ? k_viterbi_v4<5, false, true> : split ? k_viterbi_v4<5, false, false, true> : k_viterbi_v4<5>)
+                                      : (split ? k_viterbi_v4<2, false, false, true> : k_viterbi_v4<2>))
                        : (nck == 10) ? k_viterbi_v3<5> : (nck == 4) ? k_viterbi_v3<2> : k_viterbi_v3<0>;
     const int nthreads = use_v4 ? V4_THREADS : V3_THREADS;
     SAPR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
