@@ -17,7 +17,7 @@ extern "C" int sapr_ctx_create(int device, void *cuda_stream, sapr_ctx **out) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SAPR_E_CUDA; }
     if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SAPR_E_CUDA; }
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 10; i++)
         if (cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming) != cudaSuccess) { delete c; return SAPR_E_CUDA; }
     *out = c;
     return SAPR_OK;
@@ -29,7 +29,7 @@ extern "C" int sapr_ctx_destroy(sapr_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 8; i++) if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     for (int i = 0; i < 4; i++) if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);
-    for (int i = 0; i < 8; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 10; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto &r : ctx->prof_pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

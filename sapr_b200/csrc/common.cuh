@@ -31,7 +31,7 @@ struct sapr_ctx {
     size_t pin_bytes[4] = {0, 0, 0, 0};
     cudaStream_t copy_stream = nullptr;
     cudaStream_t aux_stream = nullptr;      // float64 re-decoding of word near-ties beside the fp32 back-trace
-    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[10] = {};
     // optional per-kernel event timing (bench.py roofline)
     bool profiling = false;
     struct ProfRec { cudaEvent_t a, b; int which; };
@@ -45,17 +45,17 @@ struct sapr_ctx {
 
 // RAII bracket: records an event pair around one kernel launch when profiling is on
 struct ProfScope {
-    sapr_ctx *ctx; sapr_ctx::ProfRec r; bool on;
-    ProfScope(sapr_ctx *c, int which) : ctx(c), on(c->profiling) {
+    sapr_ctx *ctx; sapr_ctx::ProfRec r; bool on; cudaStream_t st;
+    ProfScope(sapr_ctx *c, int which, cudaStream_t stream = nullptr) : ctx(c), on(c->profiling), st(stream ? stream : c->stream) {
         if (!on) return;
         if (!c->prof_pool.empty()) { r = c->prof_pool.back(); c->prof_pool.pop_back(); }
         else { cudaEventCreate(&r.a); cudaEventCreate(&r.b); }
         r.which = which;
-        cudaEventRecord(r.a, c->stream);
+        cudaEventRecord(r.a, st);
     }
     ~ProfScope() {
         if (!on) return;
-        cudaEventRecord(r.b, ctx->stream);
+        cudaEventRecord(r.b, st);
         ctx->prof.push_back(r);
     }
 };

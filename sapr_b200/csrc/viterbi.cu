@@ -204,6 +204,17 @@ __global__ void k_viterbi_finish(const int64_t *__restrict__ offsets, int u0, in
     }
 }
 
+__device__ __forceinline__ unsigned ldg_nc_bp(const uint32_t *p) {
+    unsigned v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned ldg_nc_bp(const uint16_t *p) {
+    unsigned short v;
+    asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return v;
+}
+
 // Fast path of the above for the production call (winner's path only): a warp owns 32 utterances (lane = utterance).
 // Back-pointer words of a 32-frame chunk are fetched with 32 independent loads per lane (the address does not depend
 // on the state being traced), the traced states are staged in shared memory and written out row by row so every
@@ -245,25 +256,31 @@ k_viterbi_finish_fast(const int64_t *__restrict__ offsets, int u0, int nu, int N
     if (!best_path) return;
     const int wslot = bslot < 0 ? 0 : bslot;
     const bool reachable = live && scores[(size_t)ul * nslots + wslot] != -INFINITY;
-    const BP *bpp = bp + ((size_t)wslot * maxT) * Bpad + ul;
+    const BP *bpp = bp + ((size_t)wslot * maxT) * Bpad + (live ? ul : 0);      // loads are unconditional: idle lanes read column 0
     int Tm = Te;
     for (int o = 16; o > 0; o >>= 1) Tm = max(Tm, __shfl_xor_sync(0xffffffffu, Tm, o));
     int cur = S - 1;
     for (int t0 = (Tm - 1) / CH * CH; t0 >= 0; t0 -= CH) {
+        // volatile loads + an empty asm that "modifies" the values: every load of the chunk is issued before the first is consumed
         unsigned bits[CH];
+#pragma unroll
+        for (int j = 0; j < CH; j++) bits[j] = ldg_nc_bp(bpp + (size_t)min(t0 + j, maxT - 1) * Bpad);
+#pragma unroll
+        for (int j = 0; j < CH; j += 8)
+            asm volatile("" : "+r"(bits[j]), "+r"(bits[j + 1]), "+r"(bits[j + 2]), "+r"(bits[j + 3]), "+r"(bits[j + 4]), "+r"(bits[j + 5]),
+                         "+r"(bits[j + 6]), "+r"(bits[j + 7]));
 #pragma unroll
         for (int j = 0; j < CH; j++) {
             const int t = t0 + j;
-            bits[j] = (reachable && t >= 1 && t < Te) ? (unsigned)bpp[(size_t)t * Bpad] : 0u;
+            bits[j] = (reachable && t >= 1 && t < Te) ? bits[j] : 0u;
         }
+        // one dependent shift / and / subtract per frame, no branch (the trace is the latency of a small launch): bits[] is 0 for
+        // frames outside [1, Te), bit c - 1 = state c advanced (exit (S-1) -> N uses bit N), so shifted left by one the entry
+        // state's bit is 0 and it stays.  An unreachable winner keeps the exit state in its last frame and 0 before (:470).
 #pragma unroll
         for (int j = CH - 1; j >= 0; j--) {
-            const int t = t0 + j;
-            if (t < Te) {
-                sp[w][lane][j] = (uint8_t)cur;
-                if (!reachable) cur = 0;                                   // unreachable cell: back-pointer stays 0 (:470)
-                else if (cur >= 1 && t >= 1) cur -= (int)((bits[j] >> (cur - 1)) & 1u);   // exit (S-1) -> N uses bit N
-            }
+            sp[w][lane][j] = (uint8_t)(reachable ? cur : (t0 + j == Te - 1 ? S - 1 : 0));
+            cur -= (int)(((bits[j] << 1) >> cur) & 1u);
         }
         __syncwarp();
         for (int row = 0; row < 32; row++) {
@@ -358,10 +375,17 @@ static int launch_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx
 // comparisons are those of k_viterbi_fused<double> (custom_hmm.py:475-503).  Scores and back-pointer words are bit-identical to
 // the verification mode's; a frame of the recursion is a shuffle, two adds and two compares with the emission a shared-memory
 // read away (one thread walking 200 frames of ~60 dependent float64 operations each took 1.4 ms).
-__global__ void k_redo_emission(const float *__restrict__ X, int ldx, const int64_t *__restrict__ offsets, const int32_t *__restrict__ utt_list,
-                                const int32_t *__restrict__ utt_count, int cap, int M, int N, int nchunk, int maxT, int first_frames,
-                                const double *__restrict__ pk, const double *__restrict__ cst_g, double *__restrict__ E) {
-    // persistent blocks over (list entry, model, 32-frame slab), one thread per (frame, state): the list is usually a handful of utterances
+__global__ void __launch_bounds__(256) k_redo_emission(const float *__restrict__ X, int ldx, const int64_t *__restrict__ offsets,
+                                                       const int32_t *__restrict__ utt_list, const int32_t *__restrict__ utt_count, int cap, int M,
+                                                       int N, int nchunk, int maxT, int first_frames, const double *__restrict__ pk,
+                                                       const double *__restrict__ cst_g, double *__restrict__ E) {
+    // persistent blocks over (list entry, model, 32-frame slab), one thread per (frame, state): the list is usually a handful of
+    // utterances, so the launch costs the latency of ONE item.  The slab's features and the model's packed parameters are staged
+    // in shared memory with one round of independent loads; the dependent fma chain then runs out of shared memory (a thread
+    // that loads chunk by chunk pays a memory round trip per chunk).
+    extern __shared__ __align__(16) unsigned char s_em[];
+    float4 *sx = reinterpret_cast<float4 *>(s_em);                                  // [32 frames][nchunk]
+    double2 *sp = reinterpret_cast<double2 *>(s_em + (size_t)32 * nchunk * 16);      // [nchunk][N][4]
     const int n = min(*utt_count, cap);
     const int nslab = (maxT + 31) / 32;
     const int t_in = threadIdx.x >> 3, j = threadIdx.x & 7;
@@ -370,22 +394,29 @@ __global__ void k_redo_emission(const float *__restrict__ X, int ldx, const int6
         const int u = utt_list[pos];
         const int64_t off = offsets[u];
         const int T = (int)(offsets[u + 1] - off);
-        const int Te = (first_frames > 0 && first_frames < T) ? first_frames : T;
+        const int Te = min((first_frames > 0 && first_frames < T) ? first_frames : T, maxT);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 32 * nchunk; idx += 256) {
+            const int t = slab * 32 + idx / nchunk;
+            if (t < Te) sx[idx] = __ldg(reinterpret_cast<const float4 *>(X + (size_t)(off + t) * ldx) + idx % nchunk);
+        }
+        const double2 *pm2 = reinterpret_cast<const double2 *>(pk + (size_t)m * nchunk * N * 8);
+        for (int idx = threadIdx.x; idx < nchunk * N * 4; idx += 256) sp[idx] = __ldg(pm2 + idx);
+        __syncthreads();
         const int t = slab * 32 + t_in;
-        if (t >= Te || t >= maxT) continue;
+        if (t >= Te) continue;
         double ev = 0.0;
         if (j < N) {
-            const float4 *xr = reinterpret_cast<const float4 *>(X + (size_t)(off + t) * ldx);
-            const double *pm = pk + (size_t)m * nchunk * N * 8;
             double acc = 0.0;
             for (int c = 0; c < nchunk; c++) {
-                const float4 xv = __ldg(xr + c);
-                const double *p = pm + ((size_t)c * N + j) * 8;
-                const double d0 = (double)xv.x - p[0], d1 = (double)xv.y - p[1], d2 = (double)xv.z - p[2], d3 = (double)xv.w - p[3];
-                acc = fma(d0 * d0, p[4], acc);
-                acc = fma(d1 * d1, p[5], acc);
-                acc = fma(d2 * d2, p[6], acc);
-                acc = fma(d3 * d3, p[7], acc);
+                const float4 xv = sx[t_in * nchunk + c];
+                const double2 *p = sp + ((size_t)c * N + j) * 4;
+                const double2 m01 = p[0], m23 = p[1], w01 = p[2], w23 = p[3];
+                const double d0 = (double)xv.x - m01.x, d1 = (double)xv.y - m01.y, d2 = (double)xv.z - m23.x, d3 = (double)xv.w - m23.y;
+                acc = fma(d0 * d0, w01.x, acc);
+                acc = fma(d1 * d1, w01.y, acc);
+                acc = fma(d2 * d2, w23.x, acc);
+                acc = fma(d3 * d3, w23.y, acc);
             }
             ev = cst_g[(size_t)m * N + j] - acc;
         }
@@ -412,7 +443,12 @@ __global__ void __launch_bounds__(256) k_redo_f64(const int64_t *__restrict__ of
         const double NINF = -INFINITY;
         // ---- phase 1: the utterance's emissions (k_redo_emission) into shared memory, all loads in flight at once ----
         const double *eg = E + ((size_t)pos * M + m) * maxT * 8;
-        for (int idx = lane; idx < Te * 8; idx += 32) se[idx] = eg[idx];
+        {
+            const double2 *eg2 = reinterpret_cast<const double2 *>(eg);
+            double2 *se2 = reinterpret_cast<double2 *>(se);
+#pragma unroll 8
+            for (int idx = lane; idx < Te * 4; idx += 32) se2[idx] = __ldg(eg2 + idx);
+        }
         __syncwarp();
         // ---- phase 2: recursion ----
         double c_in = NINF, c_self = NINF;     // advance arc into this lane's state, its self-loop
@@ -446,6 +482,64 @@ __global__ void __launch_bounds__(256) k_redo_f64(const int64_t *__restrict__ of
         if (lane == N) scores[(size_t)pos * M + m] = (Te > 0 && (v > NINF || v != v)) ? v : NINF;
         __syncwarp();
     }
+}
+
+// arg-max / back-trace of the re-decoded list: ONE WARP per list entry (the list is a handful of utterances, so the launch is
+// the latency of one entry).  The lanes take the arg-max over the models together (strict >, first model wins, NaN never wins:
+// decoder.py:42-47), fetch the winner's back-pointer words of all frames at once into shared memory, lane 0 walks them (one
+// shift / and / subtract per frame) and the lanes write the path out together.
+__global__ void __launch_bounds__(128) k_redo_finish(const int64_t *__restrict__ offsets, const int32_t *__restrict__ utt_list,
+                                                     const int32_t *__restrict__ utt_count, int cap, int N, int M, int first_frames,
+                                                     const uint16_t *__restrict__ bp, int64_t Bpad, int maxT, const double *__restrict__ sc,
+                                                     int32_t *__restrict__ best_word, double *__restrict__ best_score,
+                                                     double *__restrict__ scores_out, uint8_t *__restrict__ best_path) {
+    extern __shared__ __align__(16) unsigned char s_rf[];            // per warp: maxT words (uint16) + maxT path bytes
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int pos = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (pos >= min(*utt_count, cap)) return;
+    const size_t per_warp = ((size_t)maxT * 3 + 15) / 16 * 16;
+    uint16_t *sw = reinterpret_cast<uint16_t *>(s_rf + wib * per_warp);
+    uint8_t *spath = reinterpret_cast<uint8_t *>(sw + maxT);
+    const int u = utt_list[pos];
+    const int64_t off = offsets[u];
+    const int T = (int)(offsets[u + 1] - off);
+    const int Te = min((first_frames > 0 && first_frames < T) ? first_frames : T, maxT);
+    const int S = N + 2;
+    double bs = -INFINITY;
+    int bslot = 0x7fffffff;
+    for (int s0 = lane; s0 < M; s0 += 32) {
+        const double v = sc[(size_t)pos * M + s0];
+        if (scores_out) scores_out[(size_t)u * M + s0] = v;
+        if (v > bs) { bs = v; bslot = s0; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bs, o);
+        const int os = __shfl_xor_sync(0xffffffffu, bslot, o);
+        if (ov > bs || (ov == bs && os < bslot)) { bs = ov; bslot = os; }
+    }
+    if (bslot == 0x7fffffff) bslot = -1;                              // every score -inf (or NaN)
+    if (lane == 0) {
+        if (best_word) best_word[u] = bslot;
+        if (best_score) best_score[u] = bs;
+    }
+    if (!best_path) return;
+    const int wslot = bslot < 0 ? 0 : bslot;
+    const bool reachable = sc[(size_t)pos * M + wslot] != -INFINITY;
+    const uint16_t *bpp = bp + ((size_t)wslot * maxT) * Bpad + pos;
+    for (int t = lane; t < Te; t += 32) sw[t] = (reachable && t >= 1) ? __ldg(bpp + (size_t)t * Bpad) : (uint16_t)0;
+    __syncwarp();
+    if (lane == 0) {
+        int cur = S - 1;
+        // bit c - 1 of a word = state c advanced (exit -> N uses bit N); shifted left by one the entry state's bit is 0 and it stays.
+        // An unreachable winner keeps the exit state in its last frame and 0 before (custom_hmm.py:470).
+#pragma unroll 8
+        for (int t = Te - 1; t >= 0; t--) {
+            spath[t] = (uint8_t)(reachable ? cur : (t == Te - 1 ? S - 1 : 0));
+            cur -= (int)((((unsigned)sw[t] << 1) >> cur) & 1u);
+        }
+    }
+    __syncwarp();
+    for (int t = lane; t < Te; t += 32) best_path[off + t] = spath[t];
 }
 
 int sapr_flag_setup(sapr_ctx *ctx, SaprFlag *flag, bool first_chunk) {
@@ -493,9 +587,13 @@ int sapr_viterbi_redo_compute(sapr_ctx *ctx, sapr_models *m, const float *X, int
     const size_t per_warp = (size_t)pl.Tq * 8 * sizeof(double);
     const int wpb = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_warp));
     SAPR_CUDA(ctx, cudaFuncSetAttribute(k_redo_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wpb * per_warp)));
-    k_redo_emission<<<4 * ctx->sm_count, 256, 0, st>>>(X, ldx, offsets, flag.list, flag.count, pl.cap, m->M, m->N, m->Dp / 4, pl.Tq, first_frames,
-                                                      m->pk64, m->cst64, pl.E);
+    const size_t em_smem = (size_t)32 * (m->Dp / 4) * 16 + (size_t)(m->Dp / 4) * m->N * 64;
+    if (em_smem > 48 * 1024) SAPR_CUDA(ctx, cudaFuncSetAttribute(k_redo_emission, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em_smem));
+    { ProfScope ps(ctx, 10, st);
+    k_redo_emission<<<8 * ctx->sm_count, 256, em_smem, st>>>(X, ldx, offsets, flag.list, flag.count, pl.cap, m->M, m->N, m->Dp / 4, pl.Tq, first_frames,
+                                                             m->pk64, m->cst64, pl.E); }
     SAPR_LAUNCH_CHECK(ctx);
+    ProfScope ps(ctx, 11, st);
     k_redo_f64<<<ctx->sm_count, 32 * wpb, wpb * per_warp, st>>>(offsets, flag.list, flag.count, pl.cap, m->M, m->N, pl.Tq, first_frames, pl.E, m->la64,
                                                              m->lb64, pl.bp, (int64_t)pl.cap, pl.sc_ws);
     SAPR_LAUNCH_CHECK(ctx);
@@ -507,9 +605,11 @@ int sapr_viterbi_redo_finish(sapr_ctx *ctx, sapr_models *m, const int64_t *offse
     RedoPlan pl;
     int rc = redo_plan(ctx, m, first_frames, flag, &pl);
     if (rc || !pl.ok) return rc;
-    k_viterbi_finish_fast<uint16_t><<<(pl.cap + 127) / 128, 128, 0, ctx->stream>>>(offsets, 0, pl.cap, m->N, pl.nslots, nullptr, first_frames, pl.bp,
-                                                                                  (int64_t)pl.cap, pl.Tm, pl.sc_ws, best_word, best_score, scores,
-                                                                                  best_path, flag.list, flag.count);
+    const size_t per_warp = ((size_t)pl.Tq * 3 + 15) / 16 * 16;
+    SAPR_CUDA(ctx, cudaFuncSetAttribute(k_redo_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * per_warp)));
+    ProfScope ps(ctx, 12);
+    k_redo_finish<<<(pl.cap + 3) / 4, 128, 4 * per_warp, ctx->stream>>>(offsets, flag.list, flag.count, pl.cap, m->N, pl.nslots, first_frames, pl.bp,
+                                                                         (int64_t)pl.cap, pl.Tq, pl.sc_ws, best_word, best_score, scores, best_path);
     SAPR_LAUNCH_CHECK(ctx);
     return SAPR_OK;
 }
@@ -536,6 +636,7 @@ __global__ void k_flag_words(const double *__restrict__ scores, int u0, int nu, 
     sapr_flag_word(flag, u0 + ul, bs, second);
 }
 int sapr_viterbi_flag_words(sapr_ctx *ctx, const double *scores, int u0, int nu, int M, const SaprFlag &flag) {
+    ProfScope ps(ctx, 13);
     k_flag_words<<<(nu + 255) / 256, 256, 0, ctx->stream>>>(scores, u0, nu, M, flag);
     SAPR_LAUNCH_CHECK(ctx);
     return SAPR_OK;

@@ -1029,6 +1029,14 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v5(const V3Params p, 
 // ------------------------------------------------------------------------------------------------
 // arg-max over models (strict >, first model wins: decoder.py:42-47) + back-trace of the winner from the packed words
 struct V3Map { int grp[16], shift[16]; };
+__device__ __forceinline__ uint32_t ldg_nc_u32(const void *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void hold8(uint32_t *v) {
+    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]));
+}
 __global__ void __launch_bounds__(128)
 k_viterbi_finish_v3(const int64_t *__restrict__ offsets, int u0, int nu, int M, int Tt, int Tpad, const uint32_t *__restrict__ bp,
                     uint32_t Bpad, const V3Map map, const double *__restrict__ scores, int32_t *__restrict__ best_word,
@@ -1056,38 +1064,47 @@ k_viterbi_finish_v3(const int64_t *__restrict__ offsets, int u0, int nu, int M, 
     if (!best_path) return;
     const int wslot = bslot < 0 ? 0 : bslot;
     const bool reachable = live && bslot >= 0;
-    const uint32_t *bpp = bp + (size_t)map.grp[wslot] * Tpad * Bpad + ul;
+    const uint32_t *bpp = bp + (size_t)map.grp[wslot] * Tpad * Bpad + (live ? ul : 0);      // loads are unconditional: idle lanes read column 0
     const int sh = map.shift[wslot];
     const int Te = live ? Tt : 0;
-    int cur = 9;
     // every utterance has Tt frames: lane = utterance, 32 frames per chunk.  The chunk's words are fetched with 32 independent
-    // loads (pointer walks by a fixed stride), the traced states of the chunk are packed four per register and written with
-    // 8-byte stores when the utterance's path is 8-byte aligned (byte stores otherwise).  The winner's model group differs from
-    // lane to lane, so a lane's 4-byte word costs a 32-byte sector (3.2 KB per utterance): memory-bound at ~0.08 ms per 100 k.
+    // loads (pointer walks by a fixed stride) one chunk AHEAD of the chunk being traced, the traced states are packed four per
+    // register and written with 8-byte stores when the utterance's path is 8-byte aligned (byte stores otherwise).  The winner's
+    // model group differs from lane to lane, so a lane's 4-byte word costs a 32-byte sector (3.2 KB per utterance).
+    // The trace itself is the latency of a small launch (one dependent chain of Tt steps per thread), so a step is three
+    // dependent instructions and no branch: frame t's decisions become a "stay" mask indexed by the CURRENT state c
+    // (bit 0: the entry state stays; bit 1: state 1 stays except over the entry arc at t == 1, which sits in the exit slot;
+    // bits 2..9: the kernel's sign bits, set = stayed), and c <- c - 1 + ((mask >> c) & 1).
     const uint8_t *bpb = reinterpret_cast<const uint8_t *>(bpp);
     const size_t fstride = (size_t)Bpad * sizeof(uint32_t);
     uint8_t *out = best_path + off;
     const bool al8 = ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
-    for (int t0 = (Tt - 1) / CH * CH; t0 >= 0; t0 -= CH) {
-        uint32_t bits[CH];
-        const uint8_t *q = bpb + (size_t)t0 * fstride;
+    // volatile loads + an empty asm that "modifies" the 32 values: all loads of a chunk are issued before the first one is
+    // consumed (left alone, the compiler interleaves load and use and the chunk costs ~25 memory round trips instead of one)
+    const int tlast = Tpad - 1;
+    auto fetch = [&](int t0, uint32_t (&mask)[CH]) {
 #pragma unroll
-        for (int j = 0; j < CH; j++, q += fstride) {
+        for (int j = 0; j < CH; j++) mask[j] = ldg_nc_u32(bpb + (size_t)min(t0 + j, tlast) * fstride);
+#pragma unroll
+        for (int j = 0; j < CH; j += 8) hold8(&mask[j]);
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
             const int t = t0 + j;
-            bits[j] = (reachable && t >= 1 && t < Te) ? (*reinterpret_cast<const uint32_t *>(q) >> sh) & 0xFFu : 0xFFu;
+            const uint32_t b = (reachable && t >= 1 && t < Te) ? (mask[j] >> sh) & 0xFFu : 0xFFu;
+            mask[j] = (b << 2) | (t == 1 ? ((b >> 6) & 2u) ^ 2u : 2u) | 1u;
         }
+    };
+    uint32_t cur = 9;
+    auto walk = [&](int t0, const uint32_t (&mask)[CH]) {
         uint32_t pk[CH / 4];
 #pragma unroll
         for (int k = 0; k < CH / 4; k++) pk[k] = 0;
 #pragma unroll
         for (int j = CH - 1; j >= 0; j--) {
-            const int t = t0 + j;
-            if (t < Te) {
-                pk[j >> 2] |= (uint32_t)cur << (8 * (j & 3));
-                if (!reachable) cur = 0;                                          // unreachable cell: back-pointer stays 0 (:470)
-                else if (cur >= 2) cur -= (int)(((bits[j] >> (cur - 2)) & 1u) ^ 1u);   // a set bit = stayed (frame 0 reads as all set)
-                else if (cur == 1 && t == 1) cur -= (int)(bits[j] >> 7);         // entry arc (exit slot at t == 1)
-            }
+            // an unreachable winner (every score -inf) keeps the exit state in its last frame and 0 before (custom_hmm.py:470)
+            const uint32_t rec = reachable ? cur : (t0 + j == Te - 1 ? 9u : 0u);
+            pk[j >> 2] |= rec << (8 * (j & 3));
+            cur = cur - 1u + ((mask[j] >> cur) & 1u);
         }
         if (live) {
             const int nb = min(CH, Te - t0);                                      // bytes of this chunk
@@ -1100,6 +1117,11 @@ k_viterbi_finish_v3(const int64_t *__restrict__ offsets, int u0, int nu, int M, 
                     if (j < nb) out[t0 + j] = (uint8_t)(pk[j >> 2] >> (8 * (j & 3)));
             }
         }
+    };
+    uint32_t ma[CH];
+    for (int t0 = (Tt - 1) / CH * CH; t0 >= 0; t0 -= CH) {
+        fetch(t0, ma);
+        walk(t0, ma);
     }
 }
 
@@ -1176,8 +1198,8 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
         for (int k = 0; k < prm.nmod[g]; k++) { map.grp[prm.mod0[g] + k] = g; map.shift[prm.mod0[g] + k] = 8 * k; }
     const int exp_flags = getenv("SAPR_V_EXP") ? atoi(getenv("SAPR_V_EXP")) : 0;
     // SAPR_V_SPLIT=1: column-half products (model groups 0-1 | 2-3 split the accumulator at a multiple of 16 columns).  MEASURED SLOWER
-    // (0.93 vs 0.84 ms per 94 720 utterances): an N = 48 tcgen05.mma costs nearly what an N = 96 one does, so 30 small products per
-    // frame load the tensor pipe more than the earlier hand-off saves; kept as the record of that experiment
+    // (0.93 vs 0.84 ms per 94 720 utterances) although an N = 48 product costs half an N = 96 one (24 vs 48 cycles,
+    // tools/ubench/umma_contend.cu); kept as the record of that experiment
     prm.split_col = 8 * prm.mod0[2];
     const char *sp_env = getenv("SAPR_V_SPLIT");
     const bool split = use_v4 && !use_v5 && !exp_flags && (sp_env && sp_env[0] == '1') && prm.split_col >= 16 && prm.split_col % 16 == 0 &&
@@ -1210,7 +1232,7 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
             SAPR_CUDA(ctx, cudaMalloc(&dtr, nrec * sizeof(long long)));
             SAPR_CUDA(ctx, cudaMemsetAsync(dtr, 0, nrec * sizeof(long long), ctx->stream));
             prm.trace = dtr;
-            auto tk = exp_flags ? k_viterbi_v4<5, true, true> : k_viterbi_v4<5, true, false>;
+            auto tk = exp_flags ? k_viterbi_v4<5, true, true> : split ? k_viterbi_v4<5, true, false, true> : k_viterbi_v4<5, true, false>;
             SAPR_CUDA(ctx, cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
             tk<<<std::min(prm.ntiles, ctx->sm_count), nthreads, L.total, ctx->stream>>>(prm, tmap);
             std::vector<long long> h(nrec);
@@ -1226,31 +1248,64 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
             }
             prm.trace = nullptr;
         }
+        // A batch whose tile count is not a multiple of the SM count goes in two launches: the full rounds, then the partial
+        // round.  The arg-max / back-trace of the first part runs on the auxiliary stream beside the partial round (which leaves
+        // most SMs idle), so only the small second part's back-trace is left after the last main launch.  SAPR_V_TAIL=0: one launch.
+        const int rounds = prm.ntiles / ctx->sm_count;
+        const char *tl_env = getenv("SAPR_V_TAIL");
+        const bool tail = rounds >= 1 && prm.ntiles % ctx->sm_count != 0 && best_path && (!tl_env || tl_env[0] != '0');
+        const int nuA = tail ? rounds * ctx->sm_count * TC_ROWS : nu;      // utterances of the first launch
+        uint32_t *const bp0 = prm.bp;
+        double *const sc0 = prm.scores;
         {
             ProfScope ps(ctx, 0);
+            prm.nu = nuA; prm.ntiles = (nuA + TC_ROWS - 1) / TC_ROWS;
             kern<<<std::min(prm.ntiles, ctx->sm_count), nthreads, L.total, ctx->stream>>>(prm, tmap);
+            if (tail) {
+                SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));
+                prm.u0 = u0 + nuA; prm.nu = nu - nuA; prm.ntiles = (nu - nuA + TC_ROWS - 1) / TC_ROWS;
+                prm.bp = bp0 + nuA; prm.scores = sc0 + (size_t)nuA * M;
+                kern<<<std::min(prm.ntiles, ctx->sm_count), nthreads, L.total, ctx->stream>>>(prm, tmap);
+                prm.u0 = u0; prm.bp = bp0; prm.scores = sc0;
+            }
         }
         SAPR_LAUNCH_CHECK(ctx);
+        if (tail) {
+            SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev[8], 0));
+            k_viterbi_finish_v3<<<(nuA + 127) / 128, 128, 0, ctx->aux_stream>>>(offsets, u0, nuA, M, Tt, Tpad, bp0, prm.Bpad, map, sc0, best_word,
+                                                                                 best_score, scores, best_path, SaprFlag());
+            if (!exact) SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[9], ctx->aux_stream));
+        }
+        const int uB = tail ? nuA : 0;      // utterances whose arg-max / back-trace is still to do
         if (exact) {
-            // the near-tie list first, then the float64 re-decoding of the listed utterances on the auxiliary stream BESIDE the fp32
-            // arg-max / back-trace; its results overwrite the listed utterances once both are done
-            if ((rc = sapr_viterbi_flag_words(ctx, prm.scores, u0, nu, M, flag))) return rc;
+            // Word exactness.  The float64 re-decoding of the near-ties (list, emissions, recursion, arg-max / back-trace: four small
+            // launches, each the latency of one dependent chain) is the critical path after the last main launch, so it stays on this
+            // stream; the fp32 arg-max / back-trace runs beside it on the auxiliary stream, and the re-decoded utterances are
+            // written over its results once both are done.
             SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
             SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev[6], 0));
-            if ((rc = sapr_viterbi_redo_compute(ctx, m, X, ldx, offsets, first_frames, flag, ctx->aux_stream))) return rc;
-            SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->aux_stream));
-        }
-        {
-            ProfScope ps(ctx, 1);
-            k_viterbi_finish_v3<<<(nu + 127) / 128, 128, 0, ctx->stream>>>(offsets, u0, nu, M, Tt, Tpad, prm.bp, prm.Bpad, map, prm.scores,
-                                                                          best_word, best_score, scores, best_path, SaprFlag());
+            {
+                ProfScope ps(ctx, 1, ctx->aux_stream);
+                k_viterbi_finish_v3<<<(nu - uB + 127) / 128, 128, 0, ctx->aux_stream>>>(offsets, u0 + uB, nu - uB, M, Tt, Tpad, bp0 + uB, prm.Bpad, map,
+                                                                                       sc0 + (size_t)uB * M, best_word, best_score, scores, best_path,
+                                                                                       SaprFlag());
+            }
+            SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[9], ctx->aux_stream));
+            if ((rc = sapr_viterbi_flag_words(ctx, sc0, u0, nu, M, flag))) return rc;
+            ProfScope ps(ctx, 6);
+            if ((rc = sapr_viterbi_redo_compute(ctx, m, X, ldx, offsets, first_frames, flag, ctx->stream))) return rc;
+            SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[9], 0));
+            if ((rc = sapr_viterbi_redo_finish(ctx, m, offsets, first_frames, flag, best_word, best_score, scores, best_path))) return rc;
+        } else {
+            {
+                ProfScope ps(ctx, 1);
+                k_viterbi_finish_v3<<<(nu - uB + 127) / 128, 128, 0, ctx->stream>>>(offsets, u0 + uB, nu - uB, M, Tt, Tpad, bp0 + uB, prm.Bpad, map,
+                                                                                   sc0 + (size_t)uB * M, best_word, best_score, scores, best_path,
+                                                                                   SaprFlag());
+            }
+            if (tail) SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[9], 0));
         }
         SAPR_LAUNCH_CHECK(ctx);
-        if (exact) {
-            SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[7], 0));
-            ProfScope ps(ctx, 6);
-            if ((rc = sapr_viterbi_redo_finish(ctx, m, offsets, first_frames, flag, best_word, best_score, scores, best_path))) return rc;
-        }
     }
     *taken = true;
     return SAPR_OK;

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(26 * 32, 1) k(int N, int bg, int iters, long l
             t0 = clock64();
             for (int i = 0; i < iters; i += 5) {
 #pragma unroll
-                for (int ks = 0; ks < 5; ks++) mma_ts(tb + (uint32_t)(((i / 15) & 1) * 96), tb + 192 + 16 * ks, bdesc + 16 * ks, idesc, 1);
+                for (int ks = 0; ks < 5; ks++) mma_ts(tb + (uint32_t)(((i / 15) & 1) * (N <= 96 ? 96 : 0)), tb + 400 + 16 * ks, bdesc + 16 * ks, idesc, 1);
             }
             t1 = clock64();
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)));
@@ -141,6 +141,18 @@ int main() {
         for (int i = 2; i < 26; i++) nb += h[i];
         printf("bg %d: issue %.1f cyc/mma, complete %.1f cyc/mma; background warp-ops %lld (%.2f per cycle)\n", bg, (double)h[0] / iters,
                (double)h[1] / iters, nb, (double)nb / (double)h[1]);
+    }
+    // cost of one product as a function of N (no background work; accumulator columns 0 .. N - 1, A at column 256)
+    const int ns[] = {16, 32, 48, 64, 96, 128, 192};
+    for (int N : ns) {
+        for (int rep = 0; rep < 2; rep++) {
+            cudaMemset(d, 0, sizeof(h));
+            k<<<1, 26 * 32, 100 * 1024>>>(N, 0, iters, d, sink);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("N %d: %s\n", N, cudaGetErrorString(e)); return 1; }
+        }
+        cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("N %3d: issue %.1f cyc/mma, complete %.1f cyc/mma\n", N, (double)h[0] / iters, (double)h[1] / iters);
     }
     return 0;
 }
