@@ -141,7 +141,7 @@ __device__ __forceinline__ void sapr_flag_word(const SaprFlag &f, int u, double 
 int sapr_viterbi_redo_flagged(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int first_frames,
                               const SaprFlag &flag, int32_t *best_word, double *best_score, double *scores, uint8_t *best_path);
 int sapr_flag_setup(sapr_ctx *ctx, SaprFlag *flag, bool first_chunk);   // workspace slot 5; zeroes the per-chunk counter
-int sapr_viterbi_flag_words(sapr_ctx *ctx, const double *scores, int u0, int nu, int M, const SaprFlag &flag);
+int sapr_viterbi_flag_words(sapr_ctx *ctx, const double *scores, int u0, int nu, int M, const SaprFlag &flag, cudaStream_t st = nullptr);
 int sapr_viterbi_redo_compute(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int first_frames,
                               const SaprFlag &flag, cudaStream_t st);
 int sapr_viterbi_redo_finish(sapr_ctx *ctx, sapr_models *m, const int64_t *offsets, int first_frames, const SaprFlag &flag,

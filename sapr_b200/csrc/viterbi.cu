@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(256) k_redo_emission(const float *__restrict__
     // that loads chunk by chunk pays a memory round trip per chunk).
     extern __shared__ __align__(16) unsigned char s_em[];
     float4 *sx = reinterpret_cast<float4 *>(s_em);                                  // [32 frames][nchunk]
-    double2 *sp = reinterpret_cast<double2 *>(s_em + (size_t)32 * nchunk * 16);      // [nchunk][N][4]
+    double2 *sp = reinterpret_cast<double2 *>(s_em + (size_t)32 * nchunk * 16);      // [nchunk][4 fields][N]
     const int n = min(*utt_count, cap);
     const int nslab = (maxT + 31) / 32;
     const int t_in = threadIdx.x >> 3, j = threadIdx.x & 7;
@@ -401,7 +401,12 @@ __global__ void __launch_bounds__(256) k_redo_emission(const float *__restrict__
             if (t < Te) sx[idx] = __ldg(reinterpret_cast<const float4 *>(X + (size_t)(off + t) * ldx) + idx % nchunk);
         }
         const double2 *pm2 = reinterpret_cast<const double2 *>(pk + (size_t)m * nchunk * N * 8);
-        for (int idx = threadIdx.x; idx < nchunk * N * 4; idx += 256) sp[idx] = __ldg(pm2 + idx);
+        // packed parameters [chunk][state][mean01, mean23, weight01, weight23] -> [chunk][field][state]: the eight states of a warp
+        // read consecutive 16-byte words (state-major rows 64 bytes apart put states 0, 2, 4, 6 on the same banks)
+        for (int idx = threadIdx.x; idx < nchunk * N * 4; idx += 256) {
+            const int q = idx & 3, cj = idx >> 2, c = cj / N, jj = cj - c * N;
+            sp[(c * 4 + q) * N + jj] = __ldg(pm2 + idx);
+        }
         __syncthreads();
         const int t = slab * 32 + t_in;
         if (t >= Te) continue;
@@ -410,8 +415,8 @@ __global__ void __launch_bounds__(256) k_redo_emission(const float *__restrict__
             double acc = 0.0;
             for (int c = 0; c < nchunk; c++) {
                 const float4 xv = sx[t_in * nchunk + c];
-                const double2 *p = sp + ((size_t)c * N + j) * 4;
-                const double2 m01 = p[0], m23 = p[1], w01 = p[2], w23 = p[3];
+                const double2 *p = sp + (size_t)c * 4 * N + j;
+                const double2 m01 = p[0], m23 = p[N], w01 = p[2 * N], w23 = p[3 * N];
                 const double d0 = (double)xv.x - m01.x, d1 = (double)xv.y - m01.y, d2 = (double)xv.z - m23.x, d3 = (double)xv.w - m23.y;
                 acc = fma(d0 * d0, w01.x, acc);
                 acc = fma(d1 * d1, w01.y, acc);
@@ -431,7 +436,7 @@ __global__ void __launch_bounds__(256) k_redo_f64(const int64_t *__restrict__ of
                                                   double *__restrict__ scores) {
     extern __shared__ double s_e[];                       // [warps per block][maxT][8]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, S = N + 2;
-    double *se = s_e + (size_t)wib * maxT * 8;
+    double *se = s_e + (size_t)wib * (maxT * 8 + 8);      // + a zero slot
     const int n = min(*utt_count, cap);
     const int nw = (gridDim.x * blockDim.x) >> 5;
     for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n * M; w += nw) {
@@ -441,6 +446,7 @@ __global__ void __launch_bounds__(256) k_redo_f64(const int64_t *__restrict__ of
         const int T = (int)(offsets[u + 1] - off);
         const int Te = min((first_frames > 0 && first_frames < T) ? first_frames : T, maxT);
         const double NINF = -INFINITY;
+        if (lane == 0) se[(size_t)maxT * 8] = 0.0;
         // ---- phase 1: the utterance's emissions (k_redo_emission) into shared memory, all loads in flight at once ----
         const double *eg = E + ((size_t)pos * M + m) * maxT * 8;
         {
@@ -464,10 +470,11 @@ __global__ void __launch_bounds__(256) k_redo_f64(const int64_t *__restrict__ of
         // self-loop first and the entry state (alive at t == 1 only) second (:477-480).
         const bool adv_first = lane >= 1;
         const bool emits = lane < N;
-        for (int t = 1; t < Te; t++) {
+        if (Te > 1) {      // frame 1: the only one where the entry arc is alive (state 1 tries its self-loop first, the entry second)
+            const int t = 1;
             const double e = emits ? se[t * 8 + le] : 0.0;
             double up = __shfl_up_sync(0xffffffffu, v, 1);
-            if (lane == 0) up = (t == 1) ? 0.0 : NINF;                  // V[0, entry] = 0
+            if (lane == 0) up = 0.0;                                    // V[0, entry] = 0
             const bool open = lane < N || (lane == N && t >= N);        // the exit state opens at t >= N (:481-485)
             const double c_adv = open ? up + c_in : NINF, c_stay = open ? v + c_self : NINF;
             const double a = adv_first ? c_adv : c_stay, b2 = adv_first ? c_stay : c_adv;
@@ -478,6 +485,35 @@ __global__ void __launch_bounds__(256) k_redo_f64(const int64_t *__restrict__ of
             v = emits ? ((best > NINF) ? best + e : NINF) : best;
             const unsigned bits = __ballot_sync(0xffffffffu, adv && lane <= N);
             if (lane == 0) bpp[(size_t)t * Bpad] = (uint16_t)bits;
+        }
+        // Frames >= 2, the latency of the launch (one warp, one dependent chain): the per-lane special cases are folded into the
+        // lane's constants so every lane runs the same few instructions.  State 1 has no live predecessor (arc constant -inf: its
+        // "advance" candidate is -inf and never taken, which is what trying the self-loop first gives); the exit state's two arcs
+        // are -inf until t >= N; lanes past the exit are -inf throughout.  The comparisons and their order are the ones above:
+        // advance first, stay replaces it on strict > only; best > -inf <=> one of the two comparisons held.
+        {
+            const double *pe = emits ? se + le : se + (size_t)maxT * 8;          // non-emitting lanes add the zero slot
+            const int estep = emits ? 8 : 0;
+            uint16_t *q = bpp + 2 * Bpad;
+            auto frames = [&](int t_from, int t_to, const double cin, const double cself) {
+#pragma unroll 4
+                for (int t = t_from; t < t_to; t++, q += Bpad) {
+                    const double e = pe[t * estep];
+                    const double up = __shfl_up_sync(0xffffffffu, v, 1);
+                    const double c_adv = up + cin, c_stay = v + cself;
+                    const bool p1 = c_adv > NINF;
+                    const double best0 = p1 ? c_adv : NINF;
+                    const bool p2 = c_stay > best0;
+                    const double best = p2 ? c_stay : best0;
+                    v = (p1 || p2) ? best + e : NINF;
+                    const unsigned bits = __ballot_sync(0xffffffffu, p1 && !p2);
+                    if (lane == 0) *q = (uint16_t)bits;
+                }
+            };
+            const double cin2 = lane == 0 ? NINF : c_in;
+            const int t_open = min(max(N, 2), Te);
+            frames(2, t_open, lane == N ? NINF : cin2, lane == N ? NINF : c_self);
+            frames(t_open, Te, cin2, c_self);
         }
         if (lane == N) scores[(size_t)pos * M + m] = (Te > 0 && (v > NINF || v != v)) ? v : NINF;
         __syncwarp();
@@ -584,7 +620,7 @@ int sapr_viterbi_redo_compute(sapr_ctx *ctx, sapr_models *m, const float *X, int
     RedoPlan pl;
     int rc = redo_plan(ctx, m, first_frames, flag, &pl);
     if (rc || !pl.ok) return rc;
-    const size_t per_warp = (size_t)pl.Tq * 8 * sizeof(double);
+    const size_t per_warp = ((size_t)pl.Tq * 8 + 8) * sizeof(double);
     const int wpb = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_warp));
     SAPR_CUDA(ctx, cudaFuncSetAttribute(k_redo_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wpb * per_warp)));
     const size_t em_smem = (size_t)32 * (m->Dp / 4) * 16 + (size_t)(m->Dp / 4) * m->N * 64;
@@ -635,9 +671,10 @@ __global__ void k_flag_words(const double *__restrict__ scores, int u0, int nu, 
     }
     sapr_flag_word(flag, u0 + ul, bs, second);
 }
-int sapr_viterbi_flag_words(sapr_ctx *ctx, const double *scores, int u0, int nu, int M, const SaprFlag &flag) {
-    ProfScope ps(ctx, 13);
-    k_flag_words<<<(nu + 255) / 256, 256, 0, ctx->stream>>>(scores, u0, nu, M, flag);
+int sapr_viterbi_flag_words(sapr_ctx *ctx, const double *scores, int u0, int nu, int M, const SaprFlag &flag, cudaStream_t st) {
+    if (!st) st = ctx->stream;
+    ProfScope ps(ctx, 13, st);
+    k_flag_words<<<(nu + 255) / 256, 256, 0, st>>>(scores, u0, nu, M, flag);
     SAPR_LAUNCH_CHECK(ctx);
     return SAPR_OK;
 }

@@ -1272,6 +1272,10 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
         SAPR_LAUNCH_CHECK(ctx);
         if (tail) {
             SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev[8], 0));
+            if (exact) {      // the first part's near-tie list is ready long before the partial round ends
+                if ((rc = sapr_viterbi_flag_words(ctx, sc0, u0, nuA, M, flag, ctx->aux_stream))) return rc;
+                SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->aux_stream));
+            }
             k_viterbi_finish_v3<<<(nuA + 127) / 128, 128, 0, ctx->aux_stream>>>(offsets, u0, nuA, M, Tt, Tpad, bp0, prm.Bpad, map, sc0, best_word,
                                                                                  best_score, scores, best_path, SaprFlag());
             if (!exact) SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[9], ctx->aux_stream));
@@ -1291,7 +1295,8 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
                                                                                        SaprFlag());
             }
             SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[9], ctx->aux_stream));
-            if ((rc = sapr_viterbi_flag_words(ctx, sc0, u0, nu, M, flag))) return rc;
+            if ((rc = sapr_viterbi_flag_words(ctx, sc0 + (size_t)uB * M, u0 + uB, nu - uB, M, flag))) return rc;
+            if (tail) SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[7], 0));
             ProfScope ps(ctx, 6);
             if ((rc = sapr_viterbi_redo_compute(ctx, m, X, ldx, offsets, first_frames, flag, ctx->stream))) return rc;
             SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[9], 0));
