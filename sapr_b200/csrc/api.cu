@@ -27,7 +27,7 @@ extern "C" int sapr_ctx_destroy(sapr_ctx *ctx) {
     if (!ctx) return SAPR_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 8; i++) if (ctx->ws[i]) cudaFree(ctx->ws[i]);
+    for (int i = 0; i < 10; i++) if (ctx->ws[i]) cudaFree(ctx->ws[i]);
     for (int i = 0; i < 4; i++) if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);
     for (int i = 0; i < 10; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -24,8 +24,8 @@ struct sapr_ctx {
     int64_t launches = 0;
     int sm_count = 148;
     // grow-on-demand device workspace arenas (no cudaMalloc in steady state)
-    void *ws[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t ws_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void *ws[10] = {};               // scratch slots shared by the entry points; slot 8 belongs to the near-tie flag buffers alone
+    size_t ws_bytes[10] = {};
     // pinned staging + second stream for the host-buffer entry points
     void *pin[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t pin_bytes[4] = {0, 0, 0, 0};
@@ -39,7 +39,7 @@ struct sapr_ctx {
     std::vector<ProfRec> prof_pool;  // recycled event pairs
     // sapr_estep_grouped: the tile table of the last call (re-uploaded only when the grouping changes)
     std::vector<int32_t> eg_tab;
-    bool flag_valid = false;         // ws[5] holds the flag counters of the last fp32 Viterbi call (sapr_viterbi_flagged)
+    bool flag_valid = false;         // ws[8] holds the flag counters of the last fp32 Viterbi call (sapr_viterbi_flagged)
     int flag_maxT = 0, flag_M = 0;   // longest utterance / models of that call (size the re-decoding scratch)
 };
 
@@ -123,6 +123,7 @@ struct sapr_models {
 struct SaprFlag {
     int32_t *list = nullptr;    // [cap] utterance indices
     int32_t *count = nullptr;   // [0] entries of this chunk (may exceed cap: the surplus is not re-decoded), [1] running total of the call
+    int32_t *done = nullptr;    // [SAPR_FLAG_CAP] models completed per list entry (k_redo_fused; zero between launches)
     int cap = 0;
     float rel = 0.f;
 };
@@ -140,13 +141,7 @@ __device__ __forceinline__ void sapr_flag_word(const SaprFlag &f, int u, double 
 #define SAPR_FLAG_REL 8e-6f
 int sapr_viterbi_redo_flagged(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int first_frames,
                               const SaprFlag &flag, int32_t *best_word, double *best_score, double *scores, uint8_t *best_path);
-int sapr_flag_setup(sapr_ctx *ctx, SaprFlag *flag, bool first_chunk);   // workspace slot 5; zeroes the per-chunk counter
-int sapr_viterbi_flag_words(sapr_ctx *ctx, const double *scores, int u0, int nu, int M, const SaprFlag &flag, cudaStream_t st = nullptr);
-int sapr_viterbi_redo_compute(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int first_frames,
-                              const SaprFlag &flag, cudaStream_t st);
-int sapr_viterbi_redo_finish(sapr_ctx *ctx, sapr_models *m, const int64_t *offsets, int first_frames, const SaprFlag &flag,
-                             int32_t *best_word, double *best_score, double *scores, uint8_t *best_path);
-
+int sapr_flag_setup(sapr_ctx *ctx, SaprFlag *flag, bool first_chunk);   // workspace slot 8; zeroes the per-chunk counter
 int sapr_ws_reserve(sapr_ctx *ctx, int slot, size_t bytes);   // grows ctx->ws[slot]
 int sapr_pin_reserve(sapr_ctx *ctx, int slot, size_t bytes);  // grows ctx->pin[slot]
 int sapr_models_prepare(sapr_models *m);                      // recompute the derived arrays on device

@@ -369,94 +369,77 @@ static int launch_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx
 
 // ------------------------------------------------------------------------------------------------
 // word exactness of the fp32 production path: flag buffers and the float64 re-decoding of the flagged utterances.
-// float64 re-decoding of the listed utterances.  k_redo_emission: one thread per (list entry, model, frame, state), each with the
-// fma order of emit_diag<double>.  k_redo_f64: one warp per (list entry, model); phase 1 pulls the emissions into shared memory, phase 2 is the
-// max-product recursion, lane j < N = emitting state j + 1, lane N = exit state; the candidates, their order and the strict
-// comparisons are those of k_viterbi_fused<double> (custom_hmm.py:475-503).  Scores and back-pointer words are bit-identical to
-// the verification mode's; a frame of the recursion is a shuffle, two adds and two compares with the emission a shared-memory
-// read away (one thread walking 200 frames of ~60 dependent float64 operations each took 1.4 ms).
-__global__ void __launch_bounds__(256) k_redo_emission(const float *__restrict__ X, int ldx, const int64_t *__restrict__ offsets,
-                                                       const int32_t *__restrict__ utt_list, const int32_t *__restrict__ utt_count, int cap, int M,
-                                                       int N, int nchunk, int maxT, int first_frames, const double *__restrict__ pk,
-                                                       const double *__restrict__ cst_g, double *__restrict__ E) {
-    // persistent blocks over (list entry, model, 32-frame slab), one thread per (frame, state): the list is usually a handful of
-    // utterances, so the launch costs the latency of ONE item.  The slab's features and the model's packed parameters are staged
-    // in shared memory with one round of independent loads; the dependent fma chain then runs out of shared memory (a thread
-    // that loads chunk by chunk pays a memory round trip per chunk).
-    extern __shared__ __align__(16) unsigned char s_em[];
-    float4 *sx = reinterpret_cast<float4 *>(s_em);                                  // [32 frames][nchunk]
-    double2 *sp = reinterpret_cast<double2 *>(s_em + (size_t)32 * nchunk * 16);      // [nchunk][4 fields][N]
+// k_redo_fused, ONE launch behind the fp32 arg-max / back-trace (the list is usually a handful of utterances, so what counts is
+// the latency of one list entry: every dependent launch and every dependent memory round trip is on the critical path of
+// the whole Viterbi call).  One 256-thread block per (list entry, model):
+//   1. emissions: the utterance's features and the model's packed parameters are staged in shared memory with one round of
+//      independent loads; one thread per (frame, state) with the fma order of emit_diag<double>; results stay in shared memory
+//   2. recursion: warp 0, lane j < N = emitting state j + 1, lane N = exit state; the candidates, their order and the strict
+//      comparisons are those of k_viterbi_fused<double> (custom_hmm.py:475-503), so scores and back-pointer words are
+//      bit-identical to the verification mode's
+//   3. the block that completes an entry's last model (a counter per entry) takes the arg-max over the models and traces the
+//      winner's path, overwriting the entry's word, score, score row and path.
+__global__ void __launch_bounds__(256) k_redo_fused(const float *__restrict__ X, int ldx, const int64_t *__restrict__ offsets,
+                                                    const int32_t *__restrict__ utt_list, const int32_t *__restrict__ utt_count, int cap, int M, int N,
+                                                    int nchunk, int maxT, int xs, int first_frames, const double *__restrict__ pk,
+                                                    const double *__restrict__ cst_g, const double *__restrict__ la_g, const double *__restrict__ lb_g,
+                                                    uint16_t *bp, int64_t Bpad, double *sc, int32_t *done, int32_t *__restrict__ best_word,
+                                                    double *__restrict__ best_score, double *__restrict__ scores_out, uint8_t *__restrict__ best_path) {
+    extern __shared__ __align__(16) unsigned char s_rd[];
+    double *se = reinterpret_cast<double *>(s_rd);                                              // [maxT][8] + a zero slot
+    double2 *sp = reinterpret_cast<double2 *>(s_rd + ((size_t)maxT * 8 + 8) * sizeof(double));   // [nchunk][4 fields][8]
+    unsigned char *s_x = reinterpret_cast<unsigned char *>(sp) + (size_t)nchunk * 8 * 64;
+    float4 *sx = reinterpret_cast<float4 *>(s_x);                                               // [xs frames][nchunk]
+    uint16_t *sw = reinterpret_cast<uint16_t *>(s_x);                                           // step 3 reuses the feature slab
+    uint8_t *spath = reinterpret_cast<uint8_t *>(sw + maxT);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, S = N + 2;
+    const double NINF = -INFINITY;
     const int n = min(*utt_count, cap);
-    const int nslab = (maxT + 31) / 32;
-    const int t_in = threadIdx.x >> 3, j = threadIdx.x & 7;
-    for (int w = blockIdx.x; w < n * M * nslab; w += gridDim.x) {
-        const int slab = w % nslab, m = (w / nslab) % M, pos = w / (nslab * M);
-        const int u = utt_list[pos];
-        const int64_t off = offsets[u];
-        const int T = (int)(offsets[u + 1] - off);
-        const int Te = min((first_frames > 0 && first_frames < T) ? first_frames : T, maxT);
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < 32 * nchunk; idx += 256) {
-            const int t = slab * 32 + idx / nchunk;
-            if (t < Te) sx[idx] = __ldg(reinterpret_cast<const float4 *>(X + (size_t)(off + t) * ldx) + idx % nchunk);
-        }
-        const double2 *pm2 = reinterpret_cast<const double2 *>(pk + (size_t)m * nchunk * N * 8);
-        // packed parameters [chunk][state][mean01, mean23, weight01, weight23] -> [chunk][field][state]: the eight states of a warp
-        // read consecutive 16-byte words (state-major rows 64 bytes apart put states 0, 2, 4, 6 on the same banks)
-        for (int idx = threadIdx.x; idx < nchunk * N * 4; idx += 256) {
-            const int q = idx & 3, cj = idx >> 2, c = cj / N, jj = cj - c * N;
-            sp[(c * 4 + q) * N + jj] = __ldg(pm2 + idx);
-        }
-        __syncthreads();
-        const int t = slab * 32 + t_in;
-        if (t >= Te) continue;
-        double ev = 0.0;
-        if (j < N) {
-            double acc = 0.0;
-            for (int c = 0; c < nchunk; c++) {
-                const float4 xv = sx[t_in * nchunk + c];
-                const double2 *p = sp + (size_t)c * 4 * N + j;
-                const double2 m01 = p[0], m23 = p[N], w01 = p[2 * N], w23 = p[3 * N];
-                const double d0 = (double)xv.x - m01.x, d1 = (double)xv.y - m01.y, d2 = (double)xv.z - m23.x, d3 = (double)xv.w - m23.y;
-                acc = fma(d0 * d0, w01.x, acc);
-                acc = fma(d1 * d1, w01.y, acc);
-                acc = fma(d2 * d2, w23.x, acc);
-                acc = fma(d3 * d3, w23.y, acc);
-            }
-            ev = cst_g[(size_t)m * N + j] - acc;
-        }
-        E[(((size_t)pos * M + m) * maxT + t) * 8 + j] = ev;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_redo_f64(const int64_t *__restrict__ offsets, const int32_t *__restrict__ utt_list,
-                                                  const int32_t *__restrict__ utt_count, int cap, int M, int N, int maxT, int first_frames,
-                                                  const double *__restrict__ E, const double *__restrict__ la_g,
-                                                  const double *__restrict__ lb_g, uint16_t *__restrict__ bp, int64_t Bpad,
-                                                  double *__restrict__ scores) {
-    extern __shared__ double s_e[];                       // [warps per block][maxT][8]
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, S = N + 2;
-    double *se = s_e + (size_t)wib * (maxT * 8 + 8);      // + a zero slot
-    const int n = min(*utt_count, cap);
-    const int nw = (gridDim.x * blockDim.x) >> 5;
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n * M; w += nw) {
+    for (int w = blockIdx.x; w < n * M; w += gridDim.x) {
         const int pos = w / M, m = w % M;
         const int u = utt_list[pos];
         const int64_t off = offsets[u];
         const int T = (int)(offsets[u + 1] - off);
         const int Te = min((first_frames > 0 && first_frames < T) ? first_frames : T, maxT);
-        const double NINF = -INFINITY;
-        if (lane == 0) se[(size_t)maxT * 8] = 0.0;
-        // ---- phase 1: the utterance's emissions (k_redo_emission) into shared memory, all loads in flight at once ----
-        const double *eg = E + ((size_t)pos * M + m) * maxT * 8;
-        {
-            const double2 *eg2 = reinterpret_cast<const double2 *>(eg);
-            double2 *se2 = reinterpret_cast<double2 *>(se);
-#pragma unroll 8
-            for (int idx = lane; idx < Te * 4; idx += 32) se2[idx] = __ldg(eg2 + idx);
+        __syncthreads();                                  // the previous item is done with the shared memory
+        // ---- 1. emissions ----
+        // packed parameters [chunk][state][mean01, mean23, weight01, weight23] -> [chunk][field][state]: the eight states of a warp
+        // read consecutive 16-byte words (state-major rows 64 bytes apart put states 0, 2, 4, 6 on the same banks)
+        const double2 *pm2 = reinterpret_cast<const double2 *>(pk + (size_t)m * nchunk * N * 8);
+        for (int idx = tid; idx < nchunk * N * 4; idx += 256) {
+            const int q = idx & 3, cj = idx >> 2, c = cj / N, jj = cj - c * N;
+            sp[(c * 4 + q) * 8 + jj] = __ldg(pm2 + idx);
         }
-        __syncwarp();
-        // ---- phase 2: recursion ----
+        if (tid == 0) se[(size_t)maxT * 8] = 0.0;
+        for (int s0 = 0; s0 < Te; s0 += xs) {
+            if (s0) __syncthreads();
+            const int nf = min(xs, Te - s0);
+            for (int idx = tid; idx < nf * nchunk; idx += 256)
+                sx[idx] = __ldg(reinterpret_cast<const float4 *>(X + (size_t)(off + s0 + idx / nchunk) * ldx) + idx % nchunk);
+            __syncthreads();
+            for (int item = tid; item < nf * 8; item += 256) {
+                const int t_l = item >> 3, j = item & 7;
+                double ev = 0.0;
+                if (j < N) {
+                    double acc = 0.0;
+                    for (int c = 0; c < nchunk; c++) {
+                        const float4 xv = sx[t_l * nchunk + c];
+                        const double2 *p = sp + (size_t)c * 32 + j;
+                        const double2 m01 = p[0], m23 = p[8], w01 = p[16], w23 = p[24];
+                        const double d0 = (double)xv.x - m01.x, d1 = (double)xv.y - m01.y, d2 = (double)xv.z - m23.x, d3 = (double)xv.w - m23.y;
+                        acc = fma(d0 * d0, w01.x, acc);
+                        acc = fma(d1 * d1, w01.y, acc);
+                        acc = fma(d2 * d2, w23.x, acc);
+                        acc = fma(d3 * d3, w23.y, acc);
+                    }
+                    ev = cst_g[(size_t)m * N + j] - acc;
+                }
+                se[(size_t)(s0 + t_l) * 8 + j] = ev;
+            }
+        }
+        __syncthreads();
+        if (warp != 0) continue;
+        // ---- 2. recursion ----
         double c_in = NINF, c_self = NINF;     // advance arc into this lane's state, its self-loop
         if (lane >= 1 && lane < N) { c_in = lb_g[(size_t)m * S + lane]; c_self = la_g[(size_t)m * S + lane + 1]; }
         else if (lane == 0) { c_in = lb_g[(size_t)m * S]; c_self = la_g[(size_t)m * S + 1]; }         // entry arc, self-loop of state 1
@@ -470,7 +453,7 @@ __global__ void __launch_bounds__(256) k_redo_f64(const int64_t *__restrict__ of
         // self-loop first and the entry state (alive at t == 1 only) second (:477-480).
         const bool adv_first = lane >= 1;
         const bool emits = lane < N;
-        if (Te > 1) {      // frame 1: the only one where the entry arc is alive (state 1 tries its self-loop first, the entry second)
+        if (Te > 1) {      // frame 1: the only one where the entry arc is alive
             const int t = 1;
             const double e = emits ? se[t * 8 + le] : 0.0;
             double up = __shfl_up_sync(0xffffffffu, v, 1);
@@ -486,11 +469,11 @@ __global__ void __launch_bounds__(256) k_redo_f64(const int64_t *__restrict__ of
             const unsigned bits = __ballot_sync(0xffffffffu, adv && lane <= N);
             if (lane == 0) bpp[(size_t)t * Bpad] = (uint16_t)bits;
         }
-        // Frames >= 2, the latency of the launch (one warp, one dependent chain): the per-lane special cases are folded into the
-        // lane's constants so every lane runs the same few instructions.  State 1 has no live predecessor (arc constant -inf: its
-        // "advance" candidate is -inf and never taken, which is what trying the self-loop first gives); the exit state's two arcs
-        // are -inf until t >= N; lanes past the exit are -inf throughout.  The comparisons and their order are the ones above:
-        // advance first, stay replaces it on strict > only; best > -inf <=> one of the two comparisons held.
+        // Frames >= 2, one warp and one dependent chain: the per-lane special cases are folded into the lane's constants so every
+        // lane runs the same few instructions.  State 1 has no live predecessor (arc constant -inf: its "advance" candidate is
+        // -inf and never taken, which is what trying the self-loop first gives); the exit state's two arcs are -inf until
+        // t >= N; lanes past the exit are -inf throughout.  The comparisons and their order are the ones above: advance first,
+        // stay replaces it on strict > only; best > -inf <=> one of the two comparisons held.
         {
             const double *pe = emits ? se + le : se + (size_t)maxT * 8;          // non-emitting lanes add the zero slot
             const int estep = emits ? 8 : 0;
@@ -515,73 +498,62 @@ __global__ void __launch_bounds__(256) k_redo_f64(const int64_t *__restrict__ of
             frames(2, t_open, lane == N ? NINF : cin2, lane == N ? NINF : c_self);
             frames(t_open, Te, cin2, c_self);
         }
-        if (lane == N) scores[(size_t)pos * M + m] = (Te > 0 && (v > NINF || v != v)) ? v : NINF;
+        if (lane == N) sc[(size_t)pos * M + m] = (Te > 0 && (v > NINF || v != v)) ? v : NINF;
+        // ---- 3. the entry's last model: arg-max (strict >, first model wins, NaN never wins: decoder.py:42-47) + back-trace ----
+        __threadfence();
         __syncwarp();
-    }
-}
-
-// arg-max / back-trace of the re-decoded list: ONE WARP per list entry (the list is a handful of utterances, so the launch is
-// the latency of one entry).  The lanes take the arg-max over the models together (strict >, first model wins, NaN never wins:
-// decoder.py:42-47), fetch the winner's back-pointer words of all frames at once into shared memory, lane 0 walks them (one
-// shift / and / subtract per frame) and the lanes write the path out together.
-__global__ void __launch_bounds__(128) k_redo_finish(const int64_t *__restrict__ offsets, const int32_t *__restrict__ utt_list,
-                                                     const int32_t *__restrict__ utt_count, int cap, int N, int M, int first_frames,
-                                                     const uint16_t *__restrict__ bp, int64_t Bpad, int maxT, const double *__restrict__ sc,
-                                                     int32_t *__restrict__ best_word, double *__restrict__ best_score,
-                                                     double *__restrict__ scores_out, uint8_t *__restrict__ best_path) {
-    extern __shared__ __align__(16) unsigned char s_rf[];            // per warp: maxT words (uint16) + maxT path bytes
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int pos = blockIdx.x * (blockDim.x >> 5) + wib;
-    if (pos >= min(*utt_count, cap)) return;
-    const size_t per_warp = ((size_t)maxT * 3 + 15) / 16 * 16;
-    uint16_t *sw = reinterpret_cast<uint16_t *>(s_rf + wib * per_warp);
-    uint8_t *spath = reinterpret_cast<uint8_t *>(sw + maxT);
-    const int u = utt_list[pos];
-    const int64_t off = offsets[u];
-    const int T = (int)(offsets[u + 1] - off);
-    const int Te = min((first_frames > 0 && first_frames < T) ? first_frames : T, maxT);
-    const int S = N + 2;
-    double bs = -INFINITY;
-    int bslot = 0x7fffffff;
-    for (int s0 = lane; s0 < M; s0 += 32) {
-        const double v = sc[(size_t)pos * M + s0];
-        if (scores_out) scores_out[(size_t)u * M + s0] = v;
-        if (v > bs) { bs = v; bslot = s0; }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, bs, o);
-        const int os = __shfl_xor_sync(0xffffffffu, bslot, o);
-        if (ov > bs || (ov == bs && os < bslot)) { bs = ov; bslot = os; }
-    }
-    if (bslot == 0x7fffffff) bslot = -1;                              // every score -inf (or NaN)
-    if (lane == 0) {
-        if (best_word) best_word[u] = bslot;
-        if (best_score) best_score[u] = bs;
-    }
-    if (!best_path) return;
-    const int wslot = bslot < 0 ? 0 : bslot;
-    const bool reachable = sc[(size_t)pos * M + wslot] != -INFINITY;
-    const uint16_t *bpp = bp + ((size_t)wslot * maxT) * Bpad + pos;
-    for (int t = lane; t < Te; t += 32) sw[t] = (reachable && t >= 1) ? __ldg(bpp + (size_t)t * Bpad) : (uint16_t)0;
-    __syncwarp();
-    if (lane == 0) {
-        int cur = S - 1;
-        // bit c - 1 of a word = state c advanced (exit -> N uses bit N); shifted left by one the entry state's bit is 0 and it stays.
-        // An unreachable winner keeps the exit state in its last frame and 0 before (custom_hmm.py:470).
-#pragma unroll 8
-        for (int t = Te - 1; t >= 0; t--) {
-            spath[t] = (uint8_t)(reachable ? cur : (t == Te - 1 ? S - 1 : 0));
-            cur -= (int)((((unsigned)sw[t] << 1) >> cur) & 1u);
+        int last = 0;
+        if (lane == 0) last = atomicAdd(&done[pos], 1) == M - 1;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) continue;
+        __threadfence();
+        if (lane == 0) done[pos] = 0;                                        // ready for the next call
+        double bs = NINF;
+        int bslot = 0x7fffffff;
+        for (int s0 = lane; s0 < M; s0 += 32) {
+            const double val = __ldcg(sc + (size_t)pos * M + s0);            // written by other blocks: read at the L2
+            if (scores_out) scores_out[(size_t)u * M + s0] = val;
+            if (val > bs) { bs = val; bslot = s0; }
         }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bs, o);
+            const int os = __shfl_xor_sync(0xffffffffu, bslot, o);
+            if (ov > bs || (ov == bs && os < bslot)) { bs = ov; bslot = os; }
+        }
+        if (bslot == 0x7fffffff) bslot = -1;                                 // every score -inf (or NaN)
+        if (lane == 0) {
+            if (best_word) best_word[u] = bslot;
+            if (best_score) best_score[u] = bs;
+        }
+        if (!best_path) continue;
+        const int wslot = bslot < 0 ? 0 : bslot;
+        const bool reachable = __ldcg(sc + (size_t)pos * M + wslot) != NINF;
+        const uint16_t *wp = bp + ((size_t)wslot * maxT) * Bpad + pos;
+        for (int t = lane; t < Te; t += 32) sw[t] = (reachable && t >= 1) ? __ldcg(wp + (size_t)t * Bpad) : (uint16_t)0;
+        __syncwarp();
+        if (lane == 0) {
+            int cur = S - 1;
+            // bit c - 1 of a word = state c advanced (exit -> N uses bit N); shifted left by one the entry state's bit is 0 and it stays.
+            // An unreachable winner keeps the exit state in its last frame and 0 before (custom_hmm.py:470).
+#pragma unroll 8
+            for (int t = Te - 1; t >= 0; t--) {
+                spath[t] = (uint8_t)(reachable ? cur : (t == Te - 1 ? S - 1 : 0));
+                cur -= (int)((((unsigned)sw[t] << 1) >> cur) & 1u);
+            }
+        }
+        __syncwarp();
+        for (int t = lane; t < Te; t += 32) best_path[off + t] = spath[t];
     }
-    __syncwarp();
-    for (int t = lane; t < Te; t += 32) best_path[off + t] = spath[t];
 }
 
 int sapr_flag_setup(sapr_ctx *ctx, SaprFlag *flag, bool first_chunk) {
-    int rc = sapr_ws_reserve(ctx, 5, sizeof(int32_t) * (SAPR_FLAG_CAP + 4));
+    const size_t need = sizeof(int32_t) * (2 * SAPR_FLAG_CAP + 4);      // count, list, per-entry completion counters
+    const bool fresh = ctx->ws_bytes[8] < need;      // slot 8 has no other user: the counters survive between calls
+    int rc = sapr_ws_reserve(ctx, 8, need);
     if (rc) return rc;
-    int32_t *base = (int32_t *)ctx->ws[5];
+    int32_t *base = (int32_t *)ctx->ws[8];
+    if (fresh) SAPR_CUDA(ctx, cudaMemsetAsync(base, 0, need, ctx->stream));      // the counters are left at zero by every launch
+    flag->done = base + 4 + SAPR_FLAG_CAP;
     // list capacity: the re-decoding scratch (float64 emissions of every model and frame) stays below 256 MB
     const int64_t per = (int64_t)std::max(ctx->flag_M, 1) * std::max(ctx->flag_maxT, 1) * 8 * (int64_t)sizeof(double);
     flag->count = base; flag->list = base + 4; flag->rel = SAPR_FLAG_REL;
@@ -591,101 +563,40 @@ int sapr_flag_setup(sapr_ctx *ctx, SaprFlag *flag, bool first_chunk) {
     return SAPR_OK;
 }
 
-// float64 emissions (frame-parallel) + recursion (state-parallel) of the listed utterances on stream `st`; the kernels read the
-// list length on the device (no host round trip).  sapr_viterbi_redo_finish then takes the arg-max / back-trace of the listed
-// utterances on the context's stream and overwrites their word, score, score row and path.
-struct RedoPlan { int cap, Tm, Tq, nslots; uint16_t *bp; double *sc_ws, *E; bool ok; };
-static int redo_plan(sapr_ctx *ctx, sapr_models *m, int first_frames, const SaprFlag &flag, RedoPlan *pl) {
-    pl->ok = false;
-    if (m->N > 8) return SAPR_OK;
-    pl->nslots = m->M; pl->cap = flag.cap;
-    const int maxT = ctx->flag_maxT;
-    pl->Tm = (first_frames > 0 && first_frames < maxT) ? first_frames : maxT;
-    pl->Tq = pl->Tm > 0 ? pl->Tm : 1;
-    const size_t bp_bytes = ((size_t)pl->nslots * pl->Tq * pl->cap * sizeof(uint16_t) + 255) / 256 * 256;
-    const size_t sc_bytes = ((size_t)pl->cap * pl->nslots * sizeof(double) + 255) / 256 * 256;
-    const size_t e_bytes = (size_t)pl->cap * pl->nslots * pl->Tq * 8 * sizeof(double);
-    if ((size_t)pl->Tq * 8 * sizeof(double) > 200 * 1024) return SAPR_OK;   // utterances too long for the shared-memory emission staging: no re-decoding
-    int rc = sapr_ws_reserve(ctx, 4, bp_bytes + sc_bytes + e_bytes);
-    if (rc) return rc;
-    pl->bp = (uint16_t *)ctx->ws[4];
-    pl->sc_ws = (double *)((char *)ctx->ws[4] + bp_bytes);
-    pl->E = (double *)((char *)ctx->ws[4] + bp_bytes + sc_bytes);
-    pl->ok = true;
-    return SAPR_OK;
-}
-
-int sapr_viterbi_redo_compute(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int first_frames,
-                              const SaprFlag &flag, cudaStream_t st) {
-    RedoPlan pl;
-    int rc = redo_plan(ctx, m, first_frames, flag, &pl);
-    if (rc || !pl.ok) return rc;
-    const size_t per_warp = ((size_t)pl.Tq * 8 + 8) * sizeof(double);
-    const int wpb = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_warp));
-    SAPR_CUDA(ctx, cudaFuncSetAttribute(k_redo_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wpb * per_warp)));
-    const size_t em_smem = (size_t)32 * (m->Dp / 4) * 16 + (size_t)(m->Dp / 4) * m->N * 64;
-    if (em_smem > 48 * 1024) SAPR_CUDA(ctx, cudaFuncSetAttribute(k_redo_emission, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em_smem));
-    { ProfScope ps(ctx, 10, st);
-    k_redo_emission<<<8 * ctx->sm_count, 256, em_smem, st>>>(X, ldx, offsets, flag.list, flag.count, pl.cap, m->M, m->N, m->Dp / 4, pl.Tq, first_frames,
-                                                             m->pk64, m->cst64, pl.E); }
-    SAPR_LAUNCH_CHECK(ctx);
-    ProfScope ps(ctx, 11, st);
-    k_redo_f64<<<ctx->sm_count, 32 * wpb, wpb * per_warp, st>>>(offsets, flag.list, flag.count, pl.cap, m->M, m->N, pl.Tq, first_frames, pl.E, m->la64,
-                                                             m->lb64, pl.bp, (int64_t)pl.cap, pl.sc_ws);
-    SAPR_LAUNCH_CHECK(ctx);
-    return SAPR_OK;
-}
-
-int sapr_viterbi_redo_finish(sapr_ctx *ctx, sapr_models *m, const int64_t *offsets, int first_frames, const SaprFlag &flag,
-                             int32_t *best_word, double *best_score, double *scores, uint8_t *best_path) {
-    RedoPlan pl;
-    int rc = redo_plan(ctx, m, first_frames, flag, &pl);
-    if (rc || !pl.ok) return rc;
-    const size_t per_warp = ((size_t)pl.Tq * 3 + 15) / 16 * 16;
-    SAPR_CUDA(ctx, cudaFuncSetAttribute(k_redo_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * per_warp)));
-    ProfScope ps(ctx, 12);
-    k_redo_finish<<<(pl.cap + 3) / 4, 128, 4 * per_warp, ctx->stream>>>(offsets, flag.list, flag.count, pl.cap, m->N, pl.nslots, first_frames, pl.bp,
-                                                                         (int64_t)pl.cap, pl.Tq, pl.sc_ws, best_word, best_score, scores, best_path);
-    SAPR_LAUNCH_CHECK(ctx);
-    return SAPR_OK;
-}
-
+// float64 re-decoding of the listed utterances on the context's stream, behind the fp32 arg-max / back-trace whose word, score,
+// score row and path it overwrites; the kernel reads the list length on the device (no host round trip)
 int sapr_viterbi_redo_flagged(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const int64_t *offsets, int first_frames,
                               const SaprFlag &flag, int32_t *best_word, double *best_score, double *scores, uint8_t *best_path) {
-    ProfScope ps(ctx, 6);
-    int rc = sapr_viterbi_redo_compute(ctx, m, X, ldx, offsets, first_frames, flag, ctx->stream);
+    if (m->N > 8) return SAPR_OK;
+    const int maxT = ctx->flag_maxT;
+    const int Tm = (first_frames > 0 && first_frames < maxT) ? first_frames : maxT;
+    const int Tq = Tm > 0 ? Tm : 1, nchunk = m->Dp / 4;
+    const int xs = std::min(Tq, 256);
+    const size_t x_bytes = std::max((size_t)xs * nchunk * 16, ((size_t)Tq * 3 + 31) / 16 * 16);
+    const size_t smem = ((size_t)Tq * 8 + 8) * sizeof(double) + (size_t)nchunk * 8 * 64 + x_bytes;
+    if (smem > 220 * 1024) return SAPR_OK;      // utterances too long for the shared-memory emission staging: no re-decoding
+    const size_t bp_bytes = ((size_t)m->M * Tq * flag.cap * sizeof(uint16_t) + 255) / 256 * 256;
+    const size_t sc_bytes = ((size_t)flag.cap * m->M * sizeof(double) + 255) / 256 * 256;
+    int rc = sapr_ws_reserve(ctx, 4, bp_bytes + sc_bytes);
     if (rc) return rc;
-    return sapr_viterbi_redo_finish(ctx, m, offsets, first_frames, flag, best_word, best_score, scores, best_path);
-}
-
-// arg-max + runner-up over the models of every utterance of a chunk -> the near-tie list only (the equal-length path runs the
-// float64 re-decoding on a second stream beside the fp32 back-trace, so the list is needed before that kernel)
-__global__ void k_flag_words(const double *__restrict__ scores, int u0, int nu, int M, SaprFlag flag) {
-    const int ul = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ul >= nu) return;
-    double bs = -INFINITY, second = -INFINITY;
-    for (int s = 0; s < M; s++) {
-        const double sc = scores[(size_t)ul * M + s];
-        if (sc > bs) { second = bs; bs = sc; }
-        else if (sc > second) second = sc;
-    }
-    sapr_flag_word(flag, u0 + ul, bs, second);
-}
-int sapr_viterbi_flag_words(sapr_ctx *ctx, const double *scores, int u0, int nu, int M, const SaprFlag &flag, cudaStream_t st) {
-    if (!st) st = ctx->stream;
-    ProfScope ps(ctx, 13, st);
-    k_flag_words<<<(nu + 255) / 256, 256, 0, st>>>(scores, u0, nu, M, flag);
+    uint16_t *bp = (uint16_t *)ctx->ws[4];
+    double *sc = (double *)((char *)ctx->ws[4] + bp_bytes);
+    SAPR_CUDA(ctx, cudaFuncSetAttribute(k_redo_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / smem));
+    ProfScope ps(ctx, 6);
+    k_redo_fused<<<per_sm * ctx->sm_count, 256, smem, ctx->stream>>>(X, ldx, offsets, flag.list, flag.count, flag.cap, m->M, m->N, nchunk, Tq, xs,
+                                                                     first_frames, m->pk64, m->cst64, m->la64, m->lb64, bp, (int64_t)flag.cap, sc,
+                                                                     flag.done, best_word, best_score, scores, best_path);
     SAPR_LAUNCH_CHECK(ctx);
     return SAPR_OK;
 }
 
-// utterances the last fp32 sapr_viterbi call flagged as word near-ties (and re-decoded in float64, up to SAPR_FLAG_CAP per chunk)
 extern "C" int sapr_viterbi_flagged(sapr_ctx *ctx, int64_t *n) {
     if (!ctx || !n) return SAPR_E_INVALID;
     *n = 0;
-    if (!ctx->flag_valid || !ctx->ws[5]) return SAPR_OK;
+    if (!ctx->flag_valid || !ctx->ws[8]) return SAPR_OK;
     int32_t h[2] = {0, 0};
-    SAPR_CUDA(ctx, cudaMemcpyAsync(h, ctx->ws[5], sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    SAPR_CUDA(ctx, cudaMemcpyAsync(h, ctx->ws[8], sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     SAPR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *n = h[1];
     return SAPR_OK;

@@ -1270,47 +1270,24 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
             }
         }
         SAPR_LAUNCH_CHECK(ctx);
+        // arg-max / back-trace; with word exactness on, the same kernels list the word near-ties (best - second below the fp32
+        // error bound) and ONE more launch re-decodes the listed utterances in float64 and overwrites their results
+        const SaprFlag fl = exact ? flag : SaprFlag();
         if (tail) {
             SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev[8], 0));
-            if (exact) {      // the first part's near-tie list is ready long before the partial round ends
-                if ((rc = sapr_viterbi_flag_words(ctx, sc0, u0, nuA, M, flag, ctx->aux_stream))) return rc;
-                SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->aux_stream));
-            }
             k_viterbi_finish_v3<<<(nuA + 127) / 128, 128, 0, ctx->aux_stream>>>(offsets, u0, nuA, M, Tt, Tpad, bp0, prm.Bpad, map, sc0, best_word,
-                                                                                 best_score, scores, best_path, SaprFlag());
-            if (!exact) SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[9], ctx->aux_stream));
+                                                                                 best_score, scores, best_path, fl);
+            SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[9], ctx->aux_stream));
         }
         const int uB = tail ? nuA : 0;      // utterances whose arg-max / back-trace is still to do
-        if (exact) {
-            // Word exactness.  The float64 re-decoding of the near-ties (list, emissions, recursion, arg-max / back-trace: four small
-            // launches, each the latency of one dependent chain) is the critical path after the last main launch, so it stays on this
-            // stream; the fp32 arg-max / back-trace runs beside it on the auxiliary stream, and the re-decoded utterances are
-            // written over its results once both are done.
-            SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
-            SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev[6], 0));
-            {
-                ProfScope ps(ctx, 1, ctx->aux_stream);
-                k_viterbi_finish_v3<<<(nu - uB + 127) / 128, 128, 0, ctx->aux_stream>>>(offsets, u0 + uB, nu - uB, M, Tt, Tpad, bp0 + uB, prm.Bpad, map,
-                                                                                       sc0 + (size_t)uB * M, best_word, best_score, scores, best_path,
-                                                                                       SaprFlag());
-            }
-            SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[9], ctx->aux_stream));
-            if ((rc = sapr_viterbi_flag_words(ctx, sc0 + (size_t)uB * M, u0 + uB, nu - uB, M, flag))) return rc;
-            if (tail) SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[7], 0));
-            ProfScope ps(ctx, 6);
-            if ((rc = sapr_viterbi_redo_compute(ctx, m, X, ldx, offsets, first_frames, flag, ctx->stream))) return rc;
-            SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[9], 0));
-            if ((rc = sapr_viterbi_redo_finish(ctx, m, offsets, first_frames, flag, best_word, best_score, scores, best_path))) return rc;
-        } else {
-            {
-                ProfScope ps(ctx, 1);
-                k_viterbi_finish_v3<<<(nu - uB + 127) / 128, 128, 0, ctx->stream>>>(offsets, u0 + uB, nu - uB, M, Tt, Tpad, bp0 + uB, prm.Bpad, map,
-                                                                                   sc0 + (size_t)uB * M, best_word, best_score, scores, best_path,
-                                                                                   SaprFlag());
-            }
-            if (tail) SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[9], 0));
+        {
+            ProfScope ps(ctx, 1);
+            k_viterbi_finish_v3<<<(nu - uB + 127) / 128, 128, 0, ctx->stream>>>(offsets, u0 + uB, nu - uB, M, Tt, Tpad, bp0 + uB, prm.Bpad, map,
+                                                                               sc0 + (size_t)uB * M, best_word, best_score, scores, best_path, fl);
         }
         SAPR_LAUNCH_CHECK(ctx);
+        if (tail) SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[9], 0));
+        if (exact && (rc = sapr_viterbi_redo_flagged(ctx, m, X, ldx, offsets, first_frames, flag, best_word, best_score, scores, best_path))) return rc;
     }
     *taken = true;
     return SAPR_OK;

@@ -487,6 +487,39 @@ def test_viterbi_equal_length_multi_chunk(eng, monkeypatch):
         assert np.array_equal(one[k].cpu().numpy(), many[k].cpu().numpy()), k
 
 
+def test_viterbi_partial_round_two_launches(eng, monkeypatch):
+    """A batch whose tile count is not a multiple of the SM count runs as two launches (full rounds, then the partial round, with
+    the first part's arg-max / back-trace on a second stream beside it).  Words, scores, paths and the near-tie re-decoding must
+    equal the single-launch call bit for bit, and utterances on both sides of the split must agree with the CPU oracle."""
+    import torch
+    from sapr_b200 import synth
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B, T = sms * 128 + 300, 16                                         # one full round + three tiles (the last one partial)
+    feats, labels, mu, sd = synth.make_corpus(B, 11, 8, 39, T, T, seed=23)
+    A, means, var = synth.truth_models(mu, sd, 0.9)
+    means[7] = means[2] + 1e-7 * np.sqrt(var[2]); var[7] = var[2]; A[7] = A[2]        # near-ties in both parts
+    m = eng.WordModels(11, 8, 39)
+    m.set(means, var, A)
+    batch = eng.PackedBatch.from_features(feats)
+    two = m.viterbi(batch, None, eng.FP32, 0, want_scores=True, want_path=True)
+    f2 = m.ctx.viterbi_flagged()
+    monkeypatch.setenv("SAPR_V_TAIL", "0")
+    one = m.viterbi(batch, None, eng.FP32, 0, want_scores=True, want_path=True)
+    assert m.ctx.viterbi_flagged() == f2 and f2 > 0
+    for k in ("best_word", "best_score", "scores", "path"):
+        assert np.array_equal(one[k].cpu().numpy(), two[k].cpu().numpy()), k
+    split = sms * 128
+    pick = np.r_[0:150, split - 150:split + 150, B - 150:B]
+    sub = [feats[i] for i in pick]
+    X, offs = orc.pack(sub)
+    with np.errstate(all="ignore"):
+        bw, bs, sc, bp = orc.viterbi_batch(X, offs, A, means, var)
+    assert_close(two["scores"].cpu().numpy()[pick], sc, 1e-6, what="scores on both sides of the split")
+    assert np.array_equal(two["best_word"].cpu().numpy()[pick], bw)
+    got = two["path"].cpu().numpy().astype(np.int32).reshape(B, T)[pick].reshape(-1)
+    assert np.mean(got == bp) > 0.995
+
+
 @pytest.mark.parametrize("M,D", [(4, 39), (7, 36), (12, 38), (11, 12), (12, 15), (5, 13)])
 def test_viterbi_equal_length_shape_sweep_vs_oracle(eng, M, D):
     """k_viterbi_v4 over the shapes it takes (4 <= M <= 12 models split 1-3 per recursion group, D in the 10- and 4-chunk

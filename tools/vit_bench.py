@@ -23,10 +23,9 @@ for _ in range(steps):
     out = m.viterbi(batch, None, engine.FP32, 0, want_scores=False, want_path=True)
 e1.record(); torch.cuda.synchronize()
 k_ms, k_n = ctx.profile_read(0); f_ms, f_n = ctx.profile_read(1); r_ms, r_n = ctx.profile_read(6)
-small = {n: ctx.profile_read(i)[0] / steps * 1e3 for n, i in (("emission_us", 10), ("redo_f64_us", 11), ("redo_finish_us", 12), ("flag_words_us", 13))}
 ctx.profile(False)
 acc = float((out["best_word"] == labels).float().mean().item())
 flagged = ctx.viterbi_flagged()
 print(json.dumps({"tma": os.environ.get("SAPR_TMA", "1"), "utts": B, "step_ms": e0.elapsed_time(e1) / steps, "kernel_ms": k_ms / max(k_n, 1),
-                  "finish_ms": f_ms / max(f_n, 1), "flagged": flagged, **small, "redo_ms": r_ms / max(r_n, 1),  "frac": 31412 * B / (k_ms / max(k_n, 1) / 1e3) / 1e9 / 6552.3, "word_acc": acc,
+                  "finish_ms": f_ms / max(f_n, 1), "flagged": flagged, "redo_ms": r_ms / max(r_n, 1),  "frac": 31412 * B / (k_ms / max(k_n, 1) / 1e3) / 1e9 / 6552.3, "word_acc": acc,
                   "wsum": int(out["best_word"].sum().item()), "psum": int(out["path"].to(torch.int64).sum().item())}))
