@@ -264,7 +264,10 @@ def main():
                 "kernel_share_of_step": k_ms / (ms_per_step * args.steps),
                 "finish_kernel_ms_per_step": f_ms / args.steps,
                 "note": ("issue / ALU-pipe and hand-off latency bound (ncu: issue slots 67 % busy, ALU pipe 51 %, tensor pipe 58 %); "
-                         "features are read once from HBM") if tc else "SIMT fp32 emission: FMA-issue bound (SURVEY 8d)"}
+                         "features are read once from HBM; a batch whose 128-utterance tile count is not a multiple of the SM count "
+                         "runs as two back-to-back launches of the kernel (full rounds, then the partial round beside the first part's "
+                         "back-trace): `launches` counts such a pair once and avg_launch_ms is the pair's duration") if tc
+                else "SIMT fp32 emission: FMA-issue bound (SURVEY 8d)"}
 
     # ---- end to end through the host-buffer C-ABI call (pinned host features) ----
     e2e = None

@@ -32,6 +32,7 @@ struct V3Params {
     uint32_t rw;                        // bytes per row of the raw ring: (nck + 1) * 16
     long long *trace;                   // [V4_TRACE_ROLES][V4_TRACE_FRAMES][4] clock64 stamps of CTA 0 or null (SAPR_V_TRACE=file)
     int split_col;                      // SPLIT kernels: accumulator columns of model groups 0-1 (a multiple of 16)
+    int halves;                         // SPLIT kernels: 1 = two CTAs per tile, one column half each (the partial round of a batch)
     int flags;                          // tuning what-ifs (SAPR_V_EXP, k_viterbi_v4<.., EXP = true>): 1 = no MMAs, 2 = no recursion arithmetic, 4 = no conversion arithmetic, 8 = no back-pointer stores, 16 = every tile of a CTA re-reads its first tile (L2 hits)
 };
 
@@ -444,7 +445,10 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
     const uint32_t tmem_base = *sTmem;
     const uint32_t tmem_acc = tmem_base, tmem_a = tmem_base + 2u * ncols;
     const int Tt = p.Tt, Tpad = p.Tpad;
-    const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // SPLIT kernels with p.halves set: TWO CTAs per tile, each with one column half (half the products, half the recursion warps)
+    const int half = (SPLIT && p.halves) ? (int)(blockIdx.x & 1u) : -1;
+    const int cta = half >= 0 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ncta = half >= 0 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int my_tiles = (p.ntiles - cta + ncta - 1) / ncta;
     const int nblk = my_tiles * (Tpad / V3_FB);          // four-frame blocks this CTA walks
     auto trace = [&](int role, int frame, int ev) {
         if (TRACE && blockIdx.x == 0 && lane == 0 && frame < V4_TRACE_FRAMES) p.trace[((size_t)role * V4_TRACE_FRAMES + frame) * 4 + ev] = clock64();
@@ -455,8 +459,8 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
         if (lane == 0) {
             tma_prefetch_desc(&tmap);
             uint32_t G = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                const int urow = (EXP && (p.flags & 16)) ? p.u0 + (int)blockIdx.x * TC_ROWS : p.u0 + tile * TC_ROWS;      // what-if 16: L2-resident features
+            for (int tile = cta; tile < p.ntiles; tile += ncta) {
+                const int urow = (EXP && (p.flags & 16)) ? p.u0 + cta * TC_ROWS : p.u0 + tile * TC_ROWS;      // what-if 16: L2-resident features
                 for (int t0 = 0; t0 < Tpad; t0 += V3_FB, G++) {
                     const uint32_t s = G & 1u, ph = (G >> 1) & 1u;
                     const uint32_t bar = barRawFull + 8 * s;
@@ -491,7 +495,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
                     p.trace[((size_t)0 * V4_TRACE_FRAMES + 4 * b + i) * 4 + 1] = (long long)ns;
                 }
-                mbar_wait2(barAFull + 8 * i, aph, barAccEmpty + 16 * (i & 1), ((i >> 1) & 1) ^ 1);
+                mbar_wait2(barAFull + 8 * i, aph, barAccEmpty + 16 * (i & 1) + (half == 1 ? 8 : 0), ((i >> 1) & 1) ^ 1);
                 trace(0, 4 * b + i, 2);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_acc + (uint32_t)(i & 1) * (uint32_t)ncols;
@@ -513,7 +517,8 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
                 } else {
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
-                        if (h == 1) { mbar_wait(barAccEmpty + 16 * (i & 1) + 8, ((i >> 1) & 1) ^ 1); tc_fence_after(); }
+                        if (half >= 0 && h != half) continue;
+                        if (h == 1 && half < 0) { mbar_wait(barAccEmpty + 16 * (i & 1) + 8, ((i >> 1) & 1) ^ 1); tc_fence_after(); }
                         if (elect_one()) {
                             const uint32_t dh = d_tmem + (h ? colA : 0u);
                             const uint32_t idh = h ? idescB : idescA;
@@ -525,7 +530,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
 #pragma unroll
                             for (int ks = 0; ks < NKS; ks++) umma_f16_ts(dh, a_hi + ks * 16, wh + (uint64_t)(16 * ks), idh, 1);
                             umma_commit(barAccFull + 16 * (i & 1) + 8 * h);
-                            if (h == 1) umma_commit(barAEmpty + 8 * i);
+                            if (h == 1 || half == 0) umma_commit(barAEmpty + 8 * i);
                         }
                         __syncwarp();
                     }
@@ -617,7 +622,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
                 if (lane0) mbar_arrive(bEmpty);
             }
             int tiles_left = my_tiles;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            for (int tile = cta; tile < p.ntiles; tile += ncta) {
                 tiles_left--;
                 const int ul = tile * TC_ROWS + r;
                 float W[MC][8], Wx[MC], base[MC];
@@ -630,7 +635,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
                 uint32_t bpo = (uint32_t)g * (uint32_t)Tpad * p.Bpad + (uint32_t)ul;
                 uint32_t sb = 0;
                 const int trole = rwp == 0 ? 3 : rwp == 15 ? 4 : -1;
-                const int fbase = ((tile - (int)blockIdx.x) / (int)gridDim.x) * Tpad;
+                const int fbase = ((tile - cta) / ncta) * Tpad;
                 // frame t0 + I: its columns are in ev; frame t0 + I + 1 (stage (I + 1) & 1, phase ((I + 1) >> 1) & 1 -- tiles start at a
                 // multiple of four frames) is fetched behind it unless this is the CTA's last frame
                 auto recurse = [&](auto Ic, auto GENc, int t0, bool more) {
@@ -721,8 +726,9 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
                 }
             }
         };
-        const int mcnt = p.nmod[g];
-        if (mcnt == 3) run(std::integral_constant<int, 3>{});
+        const int mcnt = (half >= 0 && (g >> 1) != half) ? 0 : p.nmod[g];      // the other CTA of the pair owns the other half
+        if (mcnt == 0 && half >= 0) { }
+        else if (mcnt == 3) run(std::integral_constant<int, 3>{});
         else if (mcnt == 2) run(std::integral_constant<int, 2>{});
         else if (mcnt == 1) run(std::integral_constant<int, 1>{});
         else __trap();
@@ -1209,6 +1215,13 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
                                       : (split ? k_viterbi_v4<2, false, false, true> : k_viterbi_v4<2>))
                        : (nck == 10) ? k_viterbi_v3<5> : (nck == 4) ? k_viterbi_v3<2> : k_viterbi_v3<0>;
     const int nthreads = use_v4 ? V4_THREADS : V3_THREADS;
+    // SAPR_V_HALF=0: the partial round as ordinary one-CTA tiles
+    const char *hf_env = getenv("SAPR_V_HALF");
+    const bool can_half = use_v4 && !use_v5 && !exp_flags && (!hf_env || hf_env[0] != '0') && prm.split_col >= 16 && prm.split_col % 16 == 0 &&
+                          ncols - prm.split_col >= 16 && (ncols - prm.split_col) % 16 == 0;
+    auto kern_half = !can_half ? nullptr : nck == 10 ? k_viterbi_v4<5, false, false, true> : k_viterbi_v4<2, false, false, true>;
+    if (kern_half) SAPR_CUDA(ctx, cudaFuncSetAttribute(kern_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    prm.halves = 0;
     SAPR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     const char *ex_env = getenv("SAPR_EXACT_WORDS");
     const bool exact = !ex_env || ex_env[0] != '0';
@@ -1265,8 +1278,16 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
                 SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));
                 prm.u0 = u0 + nuA; prm.nu = nu - nuA; prm.ntiles = (nu - nuA + TC_ROWS - 1) / TC_ROWS;
                 prm.bp = bp0 + nuA; prm.scores = sc0 + (size_t)nuA * M;
-                kern<<<std::min(prm.ntiles, ctx->sm_count), nthreads, L.total, ctx->stream>>>(prm, tmap);
+                if (kern_half && 2 * prm.ntiles <= ctx->sm_count) {
+                    // the partial round leaves most SMs idle: two CTAs per tile, each with the products and the recursion warps of
+                    // one column half (model groups 0-1 | 2-3); both convert the tile's features
+                    prm.halves = 1;
+                    kern_half<<<2 * prm.ntiles, nthreads, L.total, ctx->stream>>>(prm, tmap);
+                    prm.halves = 0;
+                } else
+                    kern<<<std::min(prm.ntiles, ctx->sm_count), nthreads, L.total, ctx->stream>>>(prm, tmap);
                 prm.u0 = u0; prm.bp = bp0; prm.scores = sc0;
+                ctx->launches++;
             }
         }
         SAPR_LAUNCH_CHECK(ctx);
@@ -1277,6 +1298,7 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
             SAPR_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev[8], 0));
             k_viterbi_finish_v3<<<(nuA + 127) / 128, 128, 0, ctx->aux_stream>>>(offsets, u0, nuA, M, Tt, Tpad, bp0, prm.Bpad, map, sc0, best_word,
                                                                                  best_score, scores, best_path, fl);
+            SAPR_LAUNCH_CHECK(ctx);
             SAPR_CUDA(ctx, cudaEventRecord(ctx->ev[9], ctx->aux_stream));
         }
         const int uB = tail ? nuA : 0;      // utterances whose arg-max / back-trace is still to do
