@@ -209,13 +209,13 @@ def main():
     def step():
         return models.viterbi(batch, None, prec, 0, want_scores=False, want_path=True)
 
-    for _ in range(W):
-        step()
-    torch.cuda.synchronize()
     sampler = ClockSampler(dist.local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.3)          # the sampler is up before the warm-up, so nothing idles the GPU between warm-up and timed steps
+    dist.barrier()
+    for _ in range(W):
+        step()
     dist.barrier()
     torch.cuda.synchronize()
     ctx.profile(True)
