@@ -30,7 +30,7 @@ struct sapr_ctx {
     void *pin[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t pin_bytes[4] = {0, 0, 0, 0};
     cudaStream_t copy_stream = nullptr;
-    cudaStream_t aux_stream = nullptr;      // float64 re-decoding of word near-ties beside the fp32 back-trace
+    cudaStream_t aux_stream = nullptr;      // arg-max / back-trace of a batch's full rounds beside its partial round (viterbi_v3.cu)
     cudaEvent_t ev[10] = {};
     // optional per-kernel event timing (bench.py roofline)
     bool profiling = false;
