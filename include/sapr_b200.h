@@ -105,7 +105,10 @@ int sapr_viterbi(sapr_ctx *ctx, sapr_models *m, const float *X, int ldx, const i
  * scores differ by less than 8e-6 |best| -- closer than the fp32 scores resolve -- is re-decoded in float64 inside the same
  * call (word, score, score row and path then are the verification mode's), so the recognised word equals the float64 one
  * except on exact float64 ties (decoder.py:42-47 keeps the first).  n = utterances flagged by the last call on this context
- * (synchronises the stream); at most 8192 per 1 GB scratch chunk are re-decoded.  SAPR_EXACT_WORDS=0 disables the pass. */
+ * (synchronises the stream); at most 8192 per 1 GB scratch chunk are re-decoded.  SAPR_EXACT_WORDS=0 disables the pass.
+ * Stream order: part of an equal-length batch's arg-max / back-trace may run on a context-owned auxiliary stream beside the
+ * last launch of the main kernel; it is joined back into the context's stream before the call returns, so work the caller
+ * enqueues on that stream afterwards sees every output. */
 int sapr_viterbi_flagged(sapr_ctx *ctx, int64_t *n);
 
 /* Parity/debug: the tensor-core emission tile of the fused Viterbi kernel written out, E_out float32
