@@ -33,6 +33,7 @@ struct V3Params {
     long long *trace;                   // [V4_TRACE_ROLES][V4_TRACE_FRAMES][4] clock64 stamps of CTA 0 or null (SAPR_V_TRACE=file)
     int split_col;                      // SPLIT kernels: accumulator columns of model groups 0-1 (a multiple of 16)
     int halves;                         // SPLIT kernels: 1 = two CTAs per tile, one column half each (the partial round of a batch)
+    int hmod0[2][4], hnmod[2][4], hplane[2][4], hshift[2][4], hroles[2];      // halves: per half and warp group: first model, models (0-2), decision-word plane and byte, active groups
     int flags;                          // tuning what-ifs (SAPR_V_EXP, k_viterbi_v4<.., EXP = true>): 1 = no MMAs, 2 = no recursion arithmetic, 4 = no conversion arithmetic, 8 = no back-pointer stores, 16 = every tile of a CTA re-reads its first tile (L2 hits)
 };
 
@@ -420,6 +421,9 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
     uint32_t *sTmem = reinterpret_cast<uint32_t *>(sBar + 24);
     const uint32_t barRawFull = smem_u32(sBar), barRawEmpty = barRawFull + 16, barAFull = barRawFull + 32, barAEmpty = barRawFull + 64;
     const uint32_t barAccFull = barRawFull + 96, barAccEmpty = barRawFull + 128;      // + 16 * stage + 8 * half
+    // SPLIT kernels with p.halves set: TWO CTAs per tile, each with the products of one column half; the half's models are dealt
+    // to all four recursion warp groups (at most two models per thread, V3Params::h*)
+    const int half = (SPLIT && p.halves) ? (int)(blockIdx.x & 1u) : -1;
 
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.wimg);
@@ -433,7 +437,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
     if (tid == 0) {
         for (int s = 0; s < 2; s++) { mbar_init(barRawFull + 8 * s, 1); mbar_init(barRawEmpty + 8 * s, V4_CONV_WARPS); }
         for (int s = 0; s < 4; s++) { mbar_init(barAFull + 8 * s, V4_CONV_WARPS); mbar_init(barAEmpty + 8 * s, 1); }
-        for (int s = 0; s < 4; s++) { mbar_init(barAccFull + 8 * s, 1); mbar_init(barAccEmpty + 8 * s, SPLIT ? V4_REC_WARPS / 2 : V4_REC_WARPS); }
+        for (int s = 0; s < 4; s++) { mbar_init(barAccFull + 8 * s, 1); mbar_init(barAccEmpty + 8 * s, half >= 0 ? 4 * p.hroles[half] : SPLIT ? V4_REC_WARPS / 2 : V4_REC_WARPS); }
         fence_barrier_init();
     }
     constexpr uint32_t a_cols = 8u * nck;
@@ -445,8 +449,6 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
     const uint32_t tmem_base = *sTmem;
     const uint32_t tmem_acc = tmem_base, tmem_a = tmem_base + 2u * ncols;
     const int Tt = p.Tt, Tpad = p.Tpad;
-    // SPLIT kernels with p.halves set: TWO CTAs per tile, each with one column half (half the products, half the recursion warps)
-    const int half = (SPLIT && p.halves) ? (int)(blockIdx.x & 1u) : -1;
     const int cta = half >= 0 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ncta = half >= 0 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int my_tiles = (p.ntiles - cta + ncta - 1) / ncta;
     const int nblk = my_tiles * (Tpad / V3_FB);          // four-frame blocks this CTA walks
@@ -594,11 +596,11 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
         // ===================== recursion: thread = (row, model group) =====================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
         const int rwp = warp - V4_REC_WARP0, q = rwp & 3, g = rwp >> 2, r = q * 32 + lane;
-        const int mbeg = p.mod0[g];
+        const int mbeg = half >= 0 ? p.hmod0[half][g] : p.mod0[g];
         const uint32_t acc0 = pin_reg(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)mbeg * 8u);
         const uint32_t acc1 = pin_reg(acc0 + (uint32_t)ncols);
         const uint32_t lane0 = pin_reg(lane == 0 ? 1u : 0u);
-        const uint32_t hb = SPLIT ? 8u * (uint32_t)(g >> 1) : 0u;                          // this group's column half
+        const uint32_t hb = SPLIT ? 8u * (uint32_t)(half >= 0 ? half : (g >> 1)) : 0u;      // this group's column half
         const uint32_t bFull = pin_reg(barAccFull + hb), bEmpty = pin_reg(barAccEmpty + hb);
         const uint32_t bstride = pin_reg(p.Bpad);
         uint32_t *const bpp = p.bp;
@@ -632,7 +634,18 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
 #pragma unroll
                     for (int j = 0; j < 8; j++) W[k][j] = -INFINITY;
                 }
-                uint32_t bpo = (uint32_t)g * (uint32_t)Tpad * p.Bpad + (uint32_t)ul;
+                // decision words: plane = the model group of the one-CTA layout; a column-half CTA's thread owns one or two of
+                // the word's bytes (same layout, narrower stores), so the arg-max / back-trace kernel does not change
+                uint32_t bpo = (uint32_t)(half >= 0 ? p.hplane[half][g] : g) * (uint32_t)Tpad * p.Bpad + (uint32_t)ul;
+                const uint32_t bsh = half >= 0 ? (uint32_t)p.hshift[half][g] : 0u;
+                auto store_bp = [&](uint32_t v) {
+                    if (SPLIT && half >= 0 && MC < 3) {
+                        uint8_t *b = reinterpret_cast<uint8_t *>(bpp + bpo) + bsh;
+                        if (MC == 2) *reinterpret_cast<uint16_t *>(b) = (uint16_t)v;
+                        else *b = (uint8_t)v;
+                    } else
+                        bpp[bpo] = v;
+                };
                 uint32_t sb = 0;
                 const int trole = rwp == 0 ? 3 : rwp == 15 ? 4 : -1;
                 const int fbase = ((tile - cta) / ncta) * Tpad;
@@ -667,7 +680,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
                             if (MC == 2) sb = __byte_perm(sbk[0], sbk[1], 0x3340);
                             if (MC == 3) sb = __byte_perm(__byte_perm(sbk[0], sbk[1], 0x3340), sbk[2], 0x3410);
                         }
-                        if (!EXP || !(p.flags & 8)) bpp[bpo] = sb;
+                        if (!EXP || !(p.flags & 8)) store_bp(sb);
                     } else {
                         if (t < Tt) {
                             if (t == 0) {
@@ -680,7 +693,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
 #pragma unroll
                                 for (int k = MC - 1; k >= 0; k--) v3_step(W[k], Wx[k], aex[k], ev[k], sb);
                             }
-                            bpp[bpo] = sb;
+                            store_bp(sb);
                         }
                         if (more) {
 #pragma unroll
@@ -726,7 +739,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_viterbi_v4(const V3Params p, 
                 }
             }
         };
-        const int mcnt = (half >= 0 && (g >> 1) != half) ? 0 : p.nmod[g];      // the other CTA of the pair owns the other half
+        const int mcnt = half >= 0 ? p.hnmod[half][g] : p.nmod[g];
         if (mcnt == 0 && half >= 0) { }
         else if (mcnt == 3) run(std::integral_constant<int, 3>{});
         else if (mcnt == 2) run(std::integral_constant<int, 2>{});
@@ -1222,6 +1235,25 @@ int sapr_viterbi_v3_launch(sapr_ctx *ctx, sapr_models *m, const float *X, int ld
     auto kern_half = !can_half ? nullptr : nck == 10 ? k_viterbi_v4<5, false, false, true> : k_viterbi_v4<2, false, false, true>;
     if (kern_half) SAPR_CUDA(ctx, cudaFuncSetAttribute(kern_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     prm.halves = 0;
+    if (can_half) {
+        // a half's two model groups (1-3 models each) are dealt to the four recursion warp groups of its CTA: 3 -> 2 + 1, 2 -> 1 + 1,
+        // 1 -> 1 + idle; a warp group keeps the bytes its models have in the group's decision word
+        for (int h = 0; h < 2; h++) {
+            prm.hroles[h] = 0;
+            for (int k = 0; k < 2; k++) {
+                const int g = 2 * h + k, n = prm.nmod[g], first = n == 3 ? 2 : n >= 1 ? 1 : 0;
+                const int cnt[2] = {first, n - first};
+                for (int r = 0; r < 2; r++) {
+                    const int role = 2 * k + r;
+                    prm.hmod0[h][role] = prm.mod0[g] + (r ? first : 0);
+                    prm.hnmod[h][role] = cnt[r];
+                    prm.hplane[h][role] = g;
+                    prm.hshift[h][role] = r ? first : 0;
+                    prm.hroles[h] += cnt[r] > 0;
+                }
+            }
+        }
+    }
     SAPR_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     const char *ex_env = getenv("SAPR_EXACT_WORDS");
     const bool exact = !ex_env || ex_env[0] != '0';
